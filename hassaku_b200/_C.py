@@ -1,0 +1,153 @@
+"""ctypes binding of the C-ABI in include/hassaku_b200.h (hassaku_b200/lib/libhassaku_b200.so).
+
+There is NO fallback: if the shared library is missing or a call is made without a CUDA device the error is
+raised to the caller.  PyTorch is used only for device memory and streams: every wrapper passes raw device
+pointers and the current CUDA stream of the calling thread; ctypes releases the GIL around the call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libhassaku_b200.so')
+
+LOSS_KINDS = {'bpr': 0, 'sampled_softmax': 1, 'bce': 2}
+STATUS_BAD_INDEX = 1
+
+
+class HskError(RuntimeError):
+    pass
+
+
+class MfTables(C.Structure):
+    """struct hsk_mf_tables (include/hassaku_b200.h)."""
+    _fields_ = [('Uw', C.c_void_p), ('Vw', C.c_void_p), ('Ub', C.c_void_p), ('Ib', C.c_void_p), ('Gb', C.c_void_p),
+                ('n_users', C.c_int64), ('n_items', C.c_int64), ('d', C.c_int32), ('ld', C.c_int32)]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    T = C.POINTER(MfTables)
+    sig = {
+        'hsk_last_error': (C.c_char_p, []),
+        'hsk_version': (i32, []),
+        'hsk_device_info': (i32, [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_int64)] * 2),
+        'hsk_mf_scores': (i32, [T, vp, vp, i32, i32, vp, vp, vp]),
+        'hsk_rec_loss': (i32, [vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
+        'hsk_mf_scatter_grads': (i32, [T, T, vp, vp, vp, i32, i32, vp, vp]),
+        'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+        'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return sig
+
+
+def lib():
+    """Load the shared library (once).  Raises HskError with build instructions if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HskError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                           f'or `make -C hassaku_b200/csrc` (nvcc, sm_100a). There is no CPU fallback.')
+        l = C.CDLL(LIB_PATH)
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return list(_declare(lib()).keys())
+
+
+def _check(rc: int, who: str):
+    if rc != 0:
+        raise HskError(f'{who} failed ({rc}): {lib().hsk_last_error().decode()}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
+    if not t.is_cuda:
+        raise HskError(f'{name} must be a CUDA tensor: hassaku_b200 has no CPU path')
+    if t.dtype != dtype:
+        raise HskError(f'{name} must be {dtype}, got {t.dtype}')
+    if contiguous and not t.is_contiguous():
+        raise HskError(f'{name} must be contiguous')
+    return t
+
+
+def make_tables(Uw, Vw, Ub, Ib, Gb, d: int) -> MfTables:
+    """Uw/Vw: [rows, ld] fp32 CUDA with stride (ld, 1) (may be a [:, :d] view of padded storage)."""
+    for n, w in (('Uw', Uw), ('Vw', Vw)):
+        if not w.is_cuda or w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1:
+            raise HskError(f'{n} must be a 2-D fp32 CUDA tensor with unit inner stride (no CPU path)')
+    if Uw.stride(0) != Vw.stride(0):
+        raise HskError('Uw and Vw must share one leading dimension')
+    return MfTables(Uw.data_ptr(), Vw.data_ptr(), _ptr(Ub), _ptr(Ib), _ptr(Gb), Uw.shape[0], Vw.shape[0], d,
+                    Uw.stride(0))
+
+
+def device_info():
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    l2, hbm = C.c_int64(), C.c_int64()
+    _check(lib().hsk_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2), C.byref(hbm)), 'hsk_device_info')
+    return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'l2_bytes': l2.value, 'hbm_bytes': hbm.value}
+
+
+def mf_scores(tables: MfTables, u_idx, i_idx, scores, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx'); _req(scores, torch.float32, 'scores')
+    B, N1 = i_idx.shape
+    _check(lib().hsk_mf_scores(C.byref(tables), u_idx.data_ptr(), i_idx.data_ptr(), B, N1, scores.data_ptr(),
+                               _ptr(status), _stream()), 'hsk_mf_scores')
+
+
+def rec_loss(scores, labels, loss_kind: int, neg_shift: float, grad_scale: float, loss_accum, dscores=None,
+             shifted_out=None):
+    _req(scores, torch.float32, 'scores'); _req(loss_accum, torch.float64, 'loss_accum')
+    if labels is not None:
+        _req(labels, torch.float64, 'labels')
+    B, N1 = scores.shape
+    _check(lib().hsk_rec_loss(scores.data_ptr(), _ptr(labels), B, N1, loss_kind, neg_shift, grad_scale,
+                              loss_accum.data_ptr(), _ptr(dscores), _ptr(shifted_out), _stream()), 'hsk_rec_loss')
+
+
+def mf_scatter_grads(tables: MfTables, grads: MfTables, u_idx, i_idx, dscores, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx'); _req(dscores, torch.float32, 'dscores')
+    B, N1 = i_idx.shape
+    _check(lib().hsk_mf_scatter_grads(C.byref(tables), C.byref(grads), u_idx.data_ptr(), i_idx.data_ptr(),
+                                      dscores.data_ptr(), B, N1, _ptr(status), _stream()), 'hsk_mf_scatter_grads')
+
+
+def mf_train_fused(tables: MfTables, grads: MfTables, u_idx, i_idx, loss_kind: int, neg_shift: float, loss_accum,
+                   scores_out=None, dscores_out=None, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx'); _req(loss_accum, torch.float64, 'loss_accum')
+    B, N1 = i_idx.shape
+    _check(lib().hsk_mf_train_fused(C.byref(tables), C.byref(grads), u_idx.data_ptr(), i_idx.data_ptr(), B, N1,
+                                    loss_kind, neg_shift, loss_accum.data_ptr(), _ptr(scores_out), _ptr(dscores_out),
+                                    _ptr(status), _stream()), 'hsk_mf_train_fused')
+
+
+def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arith: int = 0, adam_l2: bool = False,
+                zero_grad: bool = True):
+    for n, t in (('p', p), ('m', m), ('v', v), ('g', g)):
+        _req(t, torch.float32, n)
+    n = p.numel()
+    if not (m.numel() == n and v.numel() == n and g.numel() == n):
+        raise HskError('adamw_dense: p, m, v, g must have the same number of elements')
+    _check(lib().hsk_adamw_dense(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, lr, beta1, beta2, eps,
+                                 weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')

@@ -1,0 +1,126 @@
+// a8 — torch.optim.AdamW(params, lr, weight_decay).step as ONE streaming pass (train/trainer.py:52-53,147).
+//
+// HBM-bound: 28 B/element (read p,m,v,g; write p,m,v) + 4 B/element when the gradient is zeroed in the same
+// pass (replaces optimizer.zero_grad(), trainer.py:148).  128-bit loads/stores, grid = k * SM count.
+//
+// Arithmetic orders (every op is a separately rounded fp32 op; scalars are python doubles rounded to fp32
+// exactly where torch rounds them):
+//   arith 0 — torch CUDA `_multi_tensor_adam` (torch/optim/adam.py:554-800) = the foreach kernels
+//       p  = p * f(1 - lr*wd)                              _foreach_mul_
+//       m  = fma(f(1-b1), g - m, m)                        _foreach_lerp_  (weight < 0.5 branch, contracted)
+//       v  = v * f(b2);  v = fma(f(1-b2), g*g, v)          _foreach_mul_, _foreach_addcmul_ (a + s*(b*c))
+//       dn = sqrt(v) / f(sqrt(bc2)) + f(eps)               _foreach_sqrt, _foreach_div_, _foreach_add_
+//       p  = fma(f(-lr/bc1), m / dn, p)                    _foreach_addcdiv_ (a + s*(b/c))
+//   arith 1 — torch CPU `_single_tensor_adam` (torch/optim/adam.py:347-547), vectorised ATen CPU kernels
+//       v  = fma(f(1-b2)*g, g, v*f(b2));   p = p + (f(-lr/bc1)*m)/dn      (rest as above)
+// Both are verified bitwise on the GPU box (tests/test_gpu_adamw.py) against torch.optim.AdamW itself.
+#include "hsk_common.cuh"
+
+namespace hsk {
+
+struct AdamConsts {
+    float decay;      // f(1 - lr*wd)      (AdamW)   | unused (Adam)
+    float wd;         // f(wd)             (Adam L2)
+    float w1;         // f(1 - beta1)
+    float beta2;      // f(beta2)
+    float w2;         // f(1 - beta2)
+    float sqrt_bc2;   // f(sqrt(1 - beta2^t))
+    float eps;        // f(eps)
+    float step_size;  // f(-(lr / (1 - beta1^t)))
+};
+
+template <int ARITH, bool L2, bool DECAY>
+__device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamConsts& c) {
+    if (L2) g = (ARITH == 0) ? __fmaf_rn(c.wd, p, g) : __fmaf_rn(p, c.wd, g);  // grad.add(param, alpha=wd)
+    if (DECAY) p = __fmul_rn(p, c.decay);
+    m = __fmaf_rn(c.w1, __fsub_rn(g, m), m);
+    if (ARITH == 0) {
+        v = __fmul_rn(v, c.beta2);
+        v = __fmaf_rn(c.w2, __fmul_rn(g, g), v);
+    } else {
+        v = __fmaf_rn(__fmul_rn(c.w2, g), g, __fmul_rn(v, c.beta2));
+    }
+    float dn = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.sqrt_bc2), c.eps);
+    if (ARITH == 0) {
+        p = __fmaf_rn(c.step_size, __fdiv_rn(m, dn), p);
+    } else {
+        p = __fadd_rn(p, __fdiv_rn(__fmul_rn(c.step_size, m), dn));
+    }
+}
+
+template <int ARITH, bool L2, bool DECAY, bool ZERO>
+__global__ void __launch_bounds__(256) adamw_dense_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                          float* __restrict__ v, float* __restrict__ g, int64_t n,
+                                                          AdamConsts c) {
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = p4[i], M = m4[i], V = v4[i], G = __ldcs(g4 + i);
+        adam_elem<ARITH, L2, DECAY>(P.x, M.x, V.x, G.x, c);
+        adam_elem<ARITH, L2, DECAY>(P.y, M.y, V.y, G.y, c);
+        adam_elem<ARITH, L2, DECAY>(P.z, M.z, V.z, G.z, c);
+        adam_elem<ARITH, L2, DECAY>(P.w, M.w, V.w, G.w, c);
+        p4[i] = P;
+        m4[i] = M;
+        v4[i] = V;
+        if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // scalar tail (n % 4 elements)
+    const int64_t tail0 = n4 << 2;
+    const int64_t t = tail0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float P = p[t], M = m[t], V = v[t], G = g[t];
+        adam_elem<ARITH, L2, DECAY>(P, M, V, G, c);
+        p[t] = P;
+        m[t] = M;
+        v[t] = V;
+        if (ZERO) g[t] = 0.f;
+    }
+}
+
+}  // namespace hsk
+
+extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, double lr, double beta1,
+                               double beta2, double eps, double weight_decay, int64_t step, int arith, int adam_l2,
+                               int zero_grad, hsk_stream_t stream) {
+    using namespace hsk;
+    HSK_REQUIRE(p && m && v && g, "hsk_adamw_dense: null pointer");
+    HSK_REQUIRE(n >= 0 && step >= 1, "hsk_adamw_dense: n >= 0 and step >= 1 required (n=%lld step=%lld)", (long long)n,
+                (long long)step);
+    HSK_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), "hsk_adamw_dense: pointers must be 16-byte aligned");
+    HSK_REQUIRE(arith == 0 || arith == 1, "hsk_adamw_dense: arith must be 0 (cuda foreach) or 1 (cpu single-tensor)");
+    if (n == 0) return HSK_OK;
+    // python-double scalar bookkeeping exactly as torch/optim/adam.py does it, then one rounding to fp32
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    AdamConsts c;
+    c.decay = (float)(1.0 - lr * weight_decay);
+    c.wd = (float)weight_decay;
+    c.w1 = (float)(1.0 - beta1);
+    c.beta2 = (float)beta2;
+    c.w2 = (float)(1.0 - beta2);
+    c.sqrt_bc2 = (float)sqrt(bc2);
+    c.eps = (float)eps;
+    c.step_size = (float)(-(lr / bc1));
+    const bool l2 = adam_l2 != 0 && weight_decay != 0.0;
+    const bool decay = adam_l2 == 0 && weight_decay != 0.0;
+    const int threads = 256;
+    int64_t want = ((n >> 2) + threads - 1) / threads;
+    if (want < 1) want = 1;
+    int64_t cap = (int64_t)sm_count() * 16;
+    int blocks = (int)(want < cap ? want : cap);
+    cudaStream_t s = as_stream(stream);
+#define HSK_LAUNCH_ADAM(A, L, D, Z) adamw_dense_kernel<A, L, D, Z><<<blocks, threads, 0, s>>>(p, m, v, g, n, c)
+#define HSK_ADAM_Z(A, L, D) \
+    if (zero_grad) HSK_LAUNCH_ADAM(A, L, D, true); else HSK_LAUNCH_ADAM(A, L, D, false)
+#define HSK_ADAM_LD(A)                         \
+    if (l2) { HSK_ADAM_Z(A, true, false); }    \
+    else if (decay) { HSK_ADAM_Z(A, false, true); } \
+    else { HSK_ADAM_Z(A, false, false); }
+    if (arith == 0) { HSK_ADAM_LD(0) } else { HSK_ADAM_LD(1) }
+    return check_launch("hsk_adamw_dense");
+}

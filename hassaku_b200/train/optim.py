@@ -1,0 +1,60 @@
+"""Dense Adam / AdamW over the model's flat parameter arena — torch.optim.AdamW / torch.optim.Adam semantics
+(train/trainer.py:48-53) in ONE streaming kernel (hsk_adamw_dense): every element is updated every step, zero-gradient
+rows included, and the gradient arena is zeroed in the same pass (replaces optimizer.zero_grad())."""
+import torch
+
+from hassaku_b200 import _C
+
+
+class DenseAdam(torch.optim.Optimizer):
+    """`decoupled=True` -> torch.optim.AdamW(lr, weight_decay); False -> torch.optim.Adam(lr, weight_decay) (L2).
+    Defaults as torch: betas (0.9, 0.999), eps 1e-8, AdamW weight_decay default is whatever the caller passes
+    (the reference always passes conf['wd'])."""
+
+    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 decoupled: bool = True, arith: int = 0):
+        self.model = model
+        super().__init__(list(model.parameters()),
+                         dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, decoupled=decoupled))
+        self.arith = arith
+        self.t = 0
+        self._alloc()
+
+    def _alloc(self):
+        arena = self.model.arena
+        if not arena.is_cuda:
+            raise _C.HskError('DenseAdam needs the model on a CUDA device (no CPU path)')
+        self.m = torch.zeros_like(arena)
+        self.v = torch.zeros_like(arena)
+        self.g = torch.zeros_like(arena)
+        self.grad_tables = self.model.layout.tables(self.g)
+
+    @property
+    def grad_views(self):
+        """(gU, gV, gUb, gIb, gGb) views of the dense gradient arena, shaped like the parameters."""
+        return self.model.layout.views(self.g)
+
+    def step_fused(self):
+        """One optimizer step consuming the gradient arena `self.g` (filled by hsk_mf_train_fused)."""
+        grp = self.param_groups[0]
+        self.t += 1
+        _C.adamw_dense(self.model.arena, self.m, self.v, self.g, grp['lr'], grp['betas'][0], grp['betas'][1],
+                       grp['eps'], grp['weight_decay'], self.t, arith=self.arith, adam_l2=not grp['decoupled'],
+                       zero_grad=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        """torch.optim API: gathers the parameters' `.grad` (autograd path) into the arena, then steps."""
+        loss = closure() if closure is not None else None
+        lay = self.model.layout
+        names = ('user_embeddings.weight', 'item_embeddings.weight', 'user_bias.weight', 'item_bias.weight',
+                 'global_bias')
+        params = dict(self.model.named_parameters())
+        for name, gview in zip(names, lay.views(self.g)):
+            if gview is None:
+                continue
+            p = params[name]
+            if p.grad is not None:
+                gview.add_(p.grad.view_as(gview))
+        self.step_fused()
+        return loss

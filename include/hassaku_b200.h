@@ -1,0 +1,108 @@
+/* hassaku_b200.h — C-ABI of the B200-native SGD matrix-factorization hot path.
+ *
+ * Drop-in boundary for ONE path of karapostK/hassaku (all citations are paths in that repository):
+ *   train step   algorithms/base_classes.py:99-108, algorithms/sgd_alg.py:148-179, train/rec_losses.py:39-139,
+ *                train/trainer.py:128-148 (+ torch.optim.AdamW, trainer.py:52-53), data/dataloader.py:56-57,92-129
+ *   evaluator    eval/eval.py:54-99,101-118,237-253, eval/metrics.py:4-105
+ * The reference has no FFI layer of its own (it is pure Python over torch); these are the entry points a
+ * ctypes / torch-extension binding on the reference side calls — INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; nothing here allocates
+ *     device memory and nothing synchronises: all work is enqueued on `stream` (a cudaStream_t / CUstream)
+ *   - every function returns HSK_OK (0) or a negative HSK_ERR_*; hsk_last_error() returns a thread-local text
+ *   - embedding tables are fp32 row-major with a leading dimension `ld` (elements): ld % 4 == 0, ld >= d,
+ *     base pointers 16-byte aligned, pad columns [d, ld) hold zeros (they stay zero under every kernel here);
+ *     d <= 1024
+ *   - indices are int64 like the reference loaders emit (data/dataloader.py:126-129)
+ *   - `status` (nullable) is a device int32 bit-field: bit 0 is set when a kernel met an out-of-range user or
+ *     item index (the offending sample is skipped; the reference would raise from torch at that point)
+ *   - the library is re-entrant and holds no mutable global state (nn.DataParallel calls forward from one
+ *     Python thread per GPU, train/trainer.py:38-40); the current device of the calling thread is used
+ */
+#ifndef HASSAKU_B200_H
+#define HASSAKU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hsk_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define HSK_API __attribute__((visibility("default")))
+#else
+#define HSK_API
+#endif
+
+enum { HSK_OK = 0, HSK_ERR_INVALID = -1, HSK_ERR_CUDA = -2, HSK_ERR_UNSUPPORTED = -3 };
+enum { HSK_LOSS_BPR = 0, HSK_LOSS_SAMPLED_SOFTMAX = 1, HSK_LOSS_BCE = 2 }; /* train/rec_losses.py:142-145 */
+enum { HSK_STATUS_BAD_INDEX = 1 };
+
+/* The embedding tables of one SGDMatrixFactorization (algorithms/sgd_alg.py:127-138).  Nullable: Ub, Ib, Gb. */
+typedef struct hsk_mf_tables {
+    float* Uw;        /* user_embeddings.weight  [n_users, ld]   */
+    float* Vw;        /* item_embeddings.weight  [n_items, ld]   */
+    float* Ub;        /* user_bias.weight        [n_users]  or NULL */
+    float* Ib;        /* item_bias.weight        [n_items]  or NULL */
+    float* Gb;        /* global_bias             [1]        or NULL */
+    int64_t n_users;
+    int64_t n_items;
+    int32_t d;        /* embedding_dim */
+    int32_t ld;       /* leading dimension of Uw and Vw (elements) */
+} hsk_mf_tables;
+
+HSK_API const char* hsk_last_error(void);
+HSK_API int hsk_version(void);
+/* sm count, compute capability, L2 bytes of the current device (host pointers, nullable) */
+HSK_API int hsk_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes, int64_t* hbm_bytes);
+
+/* ---- a1-a4: SGDBasedRecommenderAlgorithm.forward (base_classes.py:99-108; sgd_alg.py:148-179) -------------
+ * scores[b, j] = <Uw[u_idx[b]], Vw[i_idx[b, j]]> (+ Ub[u]) (+ Ib[i]) (+ Gb), fp32, biases added after the
+ * reduction like sgd_alg.py:171-178.  i_idx is [B, N1] row-major (column 0 = the positive). */
+HSK_API int hsk_mf_scores(const hsk_mf_tables* t, const int64_t* u_idx, const int64_t* i_idx, int B, int N1,
+                  float* scores /* [B, N1] */, int32_t* status, hsk_stream_t stream);
+
+/* ---- a5-a6 (+bce): RecommenderSystemLoss.compute_loss (rec_losses.py:39-53, 68-88, 117-139) ---------------
+ * Adds the batch-mean loss to *loss_accum (fp64, like the reference's float64 BPR loss) and, if dscores != NULL,
+ * writes dL/dscores * grad_scale.  `labels` (nullable, fp64 [B, N1] like data/dataloader.py:127) defaults to
+ * column 0 = 1, rest 0.  neg_shift = ln(n_items / neg_train) for sampled-softmax with uniform negatives
+ * (rec_losses.py:133-134), else 0; if shifted_out != NULL the shifted logits are written there (it may alias
+ * `scores`: the reference mutates the model output in place). */
+HSK_API int hsk_rec_loss(const float* scores, const double* labels, int B, int N1, int loss_kind, float neg_shift,
+                 float grad_scale, double* loss_accum, float* dscores /* [B, N1] or NULL */,
+                 float* shifted_out /* [B, N1] or NULL */, hsk_stream_t stream);
+
+/* ---- a7: backward of a1-a4 (autograd + aten::embedding_dense_backward in the reference) ------------------
+ * Scatter-adds row gradients into DENSE gradient tables `g` (same layout as `t`, pre-zeroed by the caller or
+ * left zero by hsk_adamw_dense):  gU[u_b] += sum_j ds_bj V[i_bj];  gV[i_bj] += ds_bj U[u_b];  gIb[i_bj] += ds_bj;
+ * gUb[u_b] += sum_j ds_bj;  gGb += sum ds.  128-bit vector reductions (red.global.add.v4.f32). */
+HSK_API int hsk_mf_scatter_grads(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx, const int64_t* i_idx,
+                         const float* dscores, int B, int N1, int32_t* status, hsk_stream_t stream);
+
+/* ---- a1-a7 in one pass: forward + loss + backward for one batch (train/trainer.py:133-146) ----------------
+ * Each gathered row is read once: the dot product, the loss term, dL/ds and both row-gradient contributions
+ * are produced while the row is in registers.  Adds the batch-mean loss to *loss_accum; accumulates into the
+ * dense gradient tables `g`; optionally writes scores / dscores ([B, N1], nullable). */
+HSK_API int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx, const int64_t* i_idx,
+                       int B, int N1, int loss_kind, float neg_shift, double* loss_accum,
+                       float* scores_out, float* dscores_out, int32_t* status, hsk_stream_t stream);
+
+/* ---- a8: torch.optim.AdamW(params, lr, weight_decay).step over a flat fp32 range (trainer.py:52-53,147) ---
+ * Dense decoupled-decay Adam over ALL n elements, every step (zero-gradient rows included), in one streaming
+ * pass: reads p, m, v, g; writes p, m, v and (zero_grad != 0) g = 0, replacing optimizer.zero_grad().
+ * `step` is the 1-based step count.  arith = 0 reproduces torch's CUDA foreach kernels bit for bit
+ * (_multi_tensor_adam), arith = 1 torch's CPU single-tensor loop (_single_tensor_adam).  adam_l2 != 0 gives
+ * torch.optim.Adam semantics (L2 added to the gradient instead of decoupled decay, trainer.py:48-49).
+ * p, m, v, g 16-byte aligned. */
+HSK_API int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int64_t step, int arith, int adam_l2, int zero_grad,
+                    hsk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASSAKU_B200_H */

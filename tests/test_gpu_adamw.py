@@ -1,0 +1,91 @@
+"""hsk_adamw_dense against torch.optim.AdamW / Adam ITSELF (the third-party dependency the reference calls,
+train/trainer.py:48-53), bit for bit: arith 0 vs torch's CUDA foreach path, arith 1 vs torch's CPU path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_torch(p0, grads, device, opt_name, lr, wd, foreach=None):
+    p = torch.nn.Parameter(p0.clone().to(device))
+    cls = torch.optim.AdamW if opt_name == 'adamw' else torch.optim.Adam
+    kw = {} if foreach is None else {'foreach': foreach}
+    opt = cls([p], lr=lr, weight_decay=wd, **kw)
+    outs = []
+    for g in grads:
+        p.grad = g.clone().to(device)
+        opt.step()
+        st = opt.state[p]
+        outs.append((p.detach().cpu().clone(), st['exp_avg'].cpu().clone(), st['exp_avg_sq'].cpu().clone()))
+    return outs
+
+
+def _run_hsk(p0, grads, arith, opt_name, lr, wd):
+    from hassaku_b200 import _C
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    outs = []
+    for t, g in enumerate(grads, 1):
+        gg = g.clone().cuda()
+        _C.adamw_dense(p, m, v, gg, lr, 0.9, 0.999, 1e-8, wd, t, arith=arith, adam_l2=opt_name == 'adam', zero_grad=True)
+        assert float(gg.abs().max()) == 0.0
+        outs.append((p.cpu().clone(), m.cpu().clone(), v.cpu().clone()))
+    return outs
+
+
+def _grads(n, steps, seed):
+    gen = torch.Generator().manual_seed(seed)
+    gs = []
+    for s in range(steps):
+        g = torch.randn(n, generator=gen) * 10 ** float(torch.randint(-9, 1, (1,), generator=gen))
+        g[torch.rand(n, generator=gen) < 0.5] = 0.  # dense grads are mostly exact zeros (untouched rows)
+        gs.append(g)
+    return gs
+
+
+@pytest.mark.parametrize('opt_name,lr,wd', [('adamw', 3e-4, 4e-5), ('adamw', 1e-3, 0.0), ('adam', 1e-3, 1e-4),
+                                            ('adam', 1e-3, 0.0)])
+@pytest.mark.parametrize('n', [4 * 1000 + 3, 1 << 20])
+def test_bitwise_vs_torch_cuda_foreach(opt_name, lr, wd, n):
+    gen = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=gen) * 0.01
+    grads = _grads(n, 6, 1)
+    ref = _run_torch(p0, grads, 'cuda', opt_name, lr, wd)
+    got = _run_hsk(p0, grads, 0, opt_name, lr, wd)
+    for s, (r, g) in enumerate(zip(ref, got)):
+        for name, a, b in zip('pmv', r, g):
+            assert torch.equal(a, b), f'step {s} {name}: {(a != b).sum().item()} / {n} elements differ, ' \
+                                      f'max rel {((a - b).abs() / a.abs().clamp_min(1e-30)).max().item():.3e}'
+
+
+@pytest.mark.parametrize('opt_name,lr,wd', [('adamw', 3e-4, 4e-5), ('adam', 1e-3, 1e-4)])
+def test_bitwise_vs_torch_cpu_single_tensor(opt_name, lr, wd):
+    n = 4 * 5000 + 1
+    gen = torch.Generator().manual_seed(5)
+    p0 = torch.randn(n, generator=gen) * 0.01
+    grads = _grads(n, 6, 7)
+    torch.set_num_threads(1)
+    ref = _run_torch(p0, grads, 'cpu', opt_name, lr, wd)
+    got = _run_hsk(p0, grads, 1, opt_name, lr, wd)
+    # torch's CPU kernels are not self-consistent bit for bit: the vectorised body and the scalar tail of each
+    # parallel chunk contract a*b+c differently, so a handful of elements per chunk follow another rounding.
+    # Gate: m and v identical, p identical for > 99% of the elements and within 2 ulp everywhere.
+    for s, (r, g) in enumerate(zip(ref, got)):
+        for name, a, b in zip('pmv', r, g):
+            diff = (a != b)
+            if name == 'p':
+                assert diff.float().mean().item() < 0.01, f'step {s}: {diff.sum().item()} / {n} elements differ'
+                ulp = torch.abs(a) * 2 ** -23
+                assert ((a - b).abs() <= 2 * ulp + 1e-38).all()
+            else:
+                assert not diff.any(), f'step {s} {name}: {diff.sum().item()} / {n} elements differ'
+
+
+def test_rejects_misaligned_and_bad_args():
+    from hassaku_b200 import _C
+    p = torch.zeros(64, device='cuda')
+    with pytest.raises(_C.HskError):
+        _C.adamw_dense(p[1:33], p[:32].clone(), p[:32].clone(), p[:32].clone(), 1e-3, .9, .999, 1e-8, 0., 1)
+    with pytest.raises(_C.HskError):
+        _C.adamw_dense(p, p.clone(), p.clone(), p.clone(), 1e-3, .9, .999, 1e-8, 0., 0)
