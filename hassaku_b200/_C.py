@@ -44,6 +44,13 @@ def _declare(lib):
         'hsk_mf_scatter_grads': (i32, [T, T, vp, vp, vp, i32, i32, vp, vp]),
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
+        'hsk_eval_topk_scratch_bytes': (i64, [i32, i64, i32]),
+        'hsk_eval_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+        'hsk_topk_merge': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        'hsk_topk_dense': (i32, [vp, i32, i64, i64, i32, vp, vp, vp]),
+        'hsk_rank_metrics': (i32, [vp, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+        'hsk_rank_metrics_dense': (i32, [vp, i32, i32, C.POINTER(C.c_int), i32, vp, vp, i64, vp, i32, vp, vp, vp, vp,
+                                         vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -151,3 +158,67 @@ def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arit
         raise HskError('adamw_dense: p, m, v, g must have the same number of elements')
     _check(lib().hsk_adamw_dense(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, lr, beta1, beta2, eps,
                                  weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')
+
+
+# ---- evaluator ----
+def eval_topk_scratch_bytes(Be: int, n_local_items: int, k: int) -> int:
+    return int(lib().hsk_eval_topk_scratch_bytes(Be, n_local_items, k))
+
+
+def eval_topk(tables: MfTables, u_idx, k: int, top_scores, top_ids, scratch, excl_indptr=None, excl_indices=None,
+              id_offset: int = 0, id_stride: int = 1, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
+    if excl_indptr is not None:
+        _req(excl_indptr, torch.int64, 'excl_indptr'); _req(excl_indices, torch.int32, 'excl_indices')
+    Be = u_idx.numel()
+    _check(lib().hsk_eval_topk(C.byref(tables), u_idx.data_ptr(), Be, id_offset, id_stride, _ptr(excl_indptr),
+                               _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(), scratch.data_ptr(),
+                               scratch.numel() * scratch.element_size(), _ptr(status), _stream()), 'hsk_eval_topk')
+
+
+def topk_merge(scores, ids, out_scores, out_ids):
+    _req(scores, torch.float32, 'scores'); _req(ids, torch.int32, 'ids')
+    _req(out_scores, torch.float32, 'out_scores'); _req(out_ids, torch.int32, 'out_ids')
+    G, rows, k = scores.shape
+    _check(lib().hsk_topk_merge(scores.data_ptr(), ids.data_ptr(), G, rows, k, out_scores.data_ptr(),
+                                out_ids.data_ptr(), _stream()), 'hsk_topk_merge')
+
+
+def topk_dense(logits, k: int, out_scores, out_ids):
+    _req(logits, torch.float32, 'logits', contiguous=False)
+    if logits.dim() != 2 or logits.stride(1) != 1:
+        raise HskError('logits must be 2-D with unit inner stride')
+    _req(out_scores, torch.float32, 'out_scores'); _req(out_ids, torch.int32, 'out_ids')
+    rows, cols = logits.shape
+    _check(lib().hsk_topk_dense(logits.data_ptr(), rows, cols, logits.stride(0), k, out_scores.data_ptr(),
+                                out_ids.data_ptr(), _stream()), 'hsk_topk_dense')
+
+
+def _ks_array(ks):
+    return (C.c_int * len(ks))(*[int(k) for k in ks])
+
+
+def rank_metrics(top_ids, ks, u_idx, lab_indptr, lab_indices, discount, sums, counts, user_group=None, n_groups=0,
+                 per_user=None):
+    _req(top_ids, torch.int32, 'top_ids'); _req(u_idx, torch.int64, 'u_idx')
+    _req(lab_indptr, torch.int64, 'lab_indptr'); _req(lab_indices, torch.int32, 'lab_indices')
+    _req(discount, torch.float32, 'discount'); _req(sums, torch.float64, 'sums'); _req(counts, torch.int64, 'counts')
+    if user_group is not None:
+        _req(user_group, torch.int32, 'user_group')
+    Be, k_max = top_ids.shape
+    _check(lib().hsk_rank_metrics(top_ids.data_ptr(), Be, k_max, _ks_array(ks), len(ks), u_idx.data_ptr(),
+                                  lab_indptr.data_ptr(), lab_indices.data_ptr(), _ptr(user_group), n_groups,
+                                  discount.data_ptr(), _ptr(per_user), sums.data_ptr(), counts.data_ptr(), _stream()),
+           'hsk_rank_metrics')
+
+
+def rank_metrics_dense(top_ids, ks, u_idx, y_true, discount, sums, counts, user_group=None, n_groups=0, per_user=None):
+    _req(top_ids, torch.int32, 'top_ids'); _req(u_idx, torch.int64, 'u_idx'); _req(y_true, torch.float32, 'y_true')
+    _req(discount, torch.float32, 'discount'); _req(sums, torch.float64, 'sums'); _req(counts, torch.int64, 'counts')
+    if user_group is not None:
+        _req(user_group, torch.int32, 'user_group')
+    Be, k_max = top_ids.shape
+    _check(lib().hsk_rank_metrics_dense(top_ids.data_ptr(), Be, k_max, _ks_array(ks), len(ks), u_idx.data_ptr(),
+                                        y_true.data_ptr(), y_true.shape[1], _ptr(user_group), n_groups,
+                                        discount.data_ptr(), _ptr(per_user), sums.data_ptr(), counts.data_ptr(),
+                                        _stream()), 'hsk_rank_metrics_dense')

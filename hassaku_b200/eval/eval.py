@@ -1,0 +1,216 @@
+"""Full-rank evaluation behind the reference API (eval/eval.py:14-118, 211-258).
+
+`evaluate_recommender_algorithm(alg, eval_loader, evaluator, device, verbose)` keeps its signature and returned dict,
+but for an SGDMatrixFactorization the per-batch body (eval.py:243-253: [Be, I, d] broadcast product, host-side CSR
+densify + H2D mask, torch.topk, 12-36 `.item()` syncs) is two kernels per user batch —
+hsk_eval_topk (scoring + exclusion mask + running top-100, nothing materialised) and hsk_rank_metrics (all 12 metrics
+and their per-group sums accumulated on the device) — and ONE host sync per sweep in `get_results()`.
+The labels / exclusions are read straight from the dataset's CSR matrices (`iteration_matrix`, `exclude_data`,
+data/dataset.py:174-191) uploaded once; the loader's dense `[Be, I]` label rows (dataset.py:199-201) are never built.
+"""
+import logging
+from typing import Optional
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from hassaku_b200 import _C
+from hassaku_b200.algorithms.base_classes import RecommenderAlgorithm
+from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+from hassaku_b200.eval.metrics import dense_topk, discount_table
+
+METRIC_ORDER = ('precision@{}', 'recall@{}', 'ndcg@{}')  # eval.py:78-80; column order of hsk_rank_metrics
+
+
+class DeviceCSR:
+    """A scipy CSR matrix as (indptr int64, indices int32) device tensors with sorted rows."""
+
+    def __init__(self, m, device):
+        m = getattr(m, 'm', m)  # unwrap oracle/ref_shim CsrCompat-style adapters
+        m = m.tocsr()
+        if not m.has_sorted_indices:
+            m = m.sorted_indices()
+        self.shape = m.shape
+        self.indptr = torch.from_numpy(m.indptr.astype(np.int64)).to(device)
+        self.indices = torch.from_numpy(m.indices.astype(np.int32)).to(device)
+
+
+def device_csr(owner, attr: str, device) -> DeviceCSR:
+    """Upload `getattr(owner, attr)` once per (dataset, device) and cache it on the dataset object."""
+    cache = owner.__dict__.setdefault('_hsk_device_csr', {})
+    key = (attr, str(device))
+    if key not in cache:
+        cache[key] = DeviceCSR(getattr(owner, attr), device)
+    return cache[key]
+
+
+class FullEvaluator:
+    """Reference `FullEvaluator` (eval/eval.py:14-118): accumulates precision / recall / ndcg @ K_VALUES for the 'ALL'
+    group (-1) and each user group; `get_results()` returns the means and resets.  Accumulators live on the device."""
+    K_VALUES = [5, 10, 50, 100]  # eval.py:20
+
+    def __init__(self, aggr_by_group: bool = True, n_groups: int = 0, user_to_user_group: dict = None):
+        self.aggr_by_group = aggr_by_group
+        self.n_groups = n_groups
+        self.user_to_user_group = user_to_user_group
+        self._reset_internal_dict()
+
+    def _reset_internal_dict(self):
+        self._sums = None
+        self._counts = None
+        self._per_user = []   # (per_user [B, n_ks, 3], group [B]) when aggr_by_group is False
+        self._group_dev = None
+
+    def get_n_groups(self):
+        return self.n_groups
+
+    def get_user_to_user_group(self):
+        return self.user_to_user_group
+
+    # ---- internals ----
+    def _ks(self):
+        return sorted(self.K_VALUES, reverse=True)
+
+    def _prepare(self, device):
+        if self._sums is None:
+            n_ks = len(self.K_VALUES)
+            self._sums = torch.zeros((1 + self.n_groups, n_ks, 3), dtype=torch.float64, device=device)
+            self._counts = torch.zeros(1 + self.n_groups, dtype=torch.int64, device=device)
+            if self.n_groups > 0:
+                g = self.user_to_user_group
+                g = g if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g))
+                self._group_dev = g.to(device=device, dtype=torch.int32).contiguous()
+
+    def _per_user_buf(self, B, device):
+        if self.aggr_by_group:
+            return None
+        return torch.empty((B, len(self.K_VALUES), 3), dtype=torch.float32, device=device)
+
+    def _keep(self, u_idxs, per_user):
+        if per_user is not None:
+            grp = self._group_dev[u_idxs] if self.n_groups > 0 else None
+            self._per_user.append((per_user, grp))
+
+    # ---- reference API: dense logits / labels (eval.py:54-99) ----
+    def eval_batch(self, u_idxs: torch.Tensor, logits: torch.Tensor, y_true: torch.Tensor):
+        """u_idxs [B], logits [B, n_items], y_true [B, n_items] (dense, like FullEvalDataset feeds the reference)."""
+        if not logits.is_cuda:
+            raise _C.HskError('FullEvaluator.eval_batch needs CUDA tensors (hassaku_b200 has no CPU path)')
+        dev = logits.device
+        self._prepare(dev)
+        ks = self._ks()
+        _, ids = dense_topk(logits, ks[0])  # eval.py:61-63
+        u = u_idxs.to(dev, torch.int64).contiguous()
+        y = y_true.to(dev, torch.float32).contiguous()
+        per_user = self._per_user_buf(len(u), dev)
+        _C.rank_metrics_dense(ids, ks, u, y, discount_table(ks[0], dev), self._sums, self._counts,
+                              user_group=self._group_dev, n_groups=self.n_groups, per_user=per_user)
+        self._keep(u, per_user)
+
+    # ---- fused path: ranked ids + CSR labels ----
+    def eval_batch_topk(self, u_idxs: torch.Tensor, top_ids: torch.Tensor, labels: DeviceCSR):
+        """u_idxs int64 [B] (device), top_ids int32 [B, 100] ranked item ids, labels = CSR of the evaluated split."""
+        dev = top_ids.device
+        self._prepare(dev)
+        ks = self._ks()
+        assert top_ids.shape[-1] == ks[0], 'Top-k indexes have different "k" compared to K_VALUES'
+        per_user = self._per_user_buf(len(u_idxs), dev)
+        _C.rank_metrics(top_ids, ks, u_idxs, labels.indptr, labels.indices, discount_table(ks[0], dev), self._sums,
+                        self._counts, user_group=self._group_dev, n_groups=self.n_groups, per_user=per_user)
+        self._keep(u_idxs, per_user)
+
+    def get_results(self):
+        """eval.py:101-118 — {metric: mean over the users seen}; 'group_{g}_' prefix for user groups.  One host sync."""
+        metrics_dict = dict()
+        ks = self._ks()
+        if self._sums is None:
+            return metrics_dict
+        if self.aggr_by_group:
+            sums = self._sums.cpu().numpy()
+            counts = self._counts.cpu().numpy()
+            for g in range(-1, self.n_groups):
+                for t, k in enumerate(ks):
+                    for c, name in enumerate(METRIC_ORDER):
+                        key = name.format(k) if g == -1 else f'group_{g}_' + name.format(k)
+                        metrics_dict[key] = float(sums[g + 1, t, c]) / int(counts[g + 1])
+        else:
+            per_user = torch.cat([p for p, _ in self._per_user]).cpu().numpy()
+            grp = torch.cat([g for _, g in self._per_user]).cpu().numpy() if self.n_groups > 0 else None
+            for g in range(-1, self.n_groups):
+                sel = slice(None) if g == -1 else (grp == g)
+                for t, k in enumerate(ks):
+                    for c, name in enumerate(METRIC_ORDER):
+                        key = name.format(k) if g == -1 else f'group_{g}_' + name.format(k)
+                        metrics_dict[key] = per_user[sel, t, c]
+        self._reset_internal_dict()
+        return metrics_dict
+
+
+def log_info_results(metrics_values: dict):
+    """utilities/utils.py:29-40 of the reference."""
+    for name in sorted(metrics_values):
+        v = metrics_values[name]
+        if np.ndim(v) == 0:
+            logging.info('{:<30}{:.5f}'.format(name, v))
+
+
+class TopKScorer:
+    """hsk_eval_topk for one model: owns the scratch and output buffers for a fixed user-batch size."""
+
+    def __init__(self, alg: SGDMatrixFactorization, batch_size: int, k: int):
+        self.alg, self.k = alg, k
+        dev = alg.arena.device
+        self.scratch = torch.empty(_C.eval_topk_scratch_bytes(batch_size, alg.n_items, k), dtype=torch.uint8,
+                                   device=dev)
+        self.scores = torch.empty((batch_size, k), dtype=torch.float32, device=dev)
+        self.ids = torch.empty((batch_size, k), dtype=torch.int32, device=dev)
+        self.batch_size = batch_size
+
+    def __call__(self, u_idxs: torch.Tensor, exclude: Optional[DeviceCSR]):
+        B = len(u_idxs)
+        assert B <= self.batch_size
+        scores, ids = self.scores[:B], self.ids[:B]
+        _C.eval_topk(self.alg._tables(), u_idxs, self.k, scores, ids, self.scratch,
+                     exclude.indptr if exclude is not None else None,
+                     exclude.indices if exclude is not None else None, status=self.alg._status())
+        return scores, ids
+
+
+def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evaluator: FullEvaluator, device='cpu',
+                                   verbose=False):
+    """Evaluation procedure that calls FullEvaluator on the dataset (eval/eval.py:211-258)."""
+    dataset = eval_loader.dataset
+    if isinstance(alg, SGDMatrixFactorization):
+        if not alg.arena.is_cuda:  # the reference's run_test evaluates with device='cpu' (experiment_helper.py:116)
+            alg.to('cuda')
+        dev = alg.arena.device
+        if dataset.n_items < max(evaluator.K_VALUES):
+            raise RuntimeError('selected index k out of range')  # what torch.topk raises in the reference (eval.py:63)
+        labels = device_csr(dataset, 'iteration_matrix', dev)
+        exclude = device_csr(dataset, 'exclude_data', dev)
+        bs = getattr(eval_loader, 'batch_size', None) or 8192
+        scorer = TopKScorer(alg, min(bs, dataset.n_users), max(evaluator.K_VALUES))
+        starts = range(0, dataset.n_users, bs)
+        with torch.no_grad():
+            for s in (tqdm(starts) if verbose else starts):
+                u_idxs = torch.arange(s, min(s + bs, dataset.n_users), dtype=torch.int64, device=dev)
+                _, ids = scorer(u_idxs, exclude)
+                evaluator.eval_batch_topk(u_idxs, ids, labels)
+        alg.check_status()
+    else:
+        # generic algorithms: the reference's dense path (eval.py:224-236) on CUDA tensors
+        dev = torch.device('cuda' if str(device) == 'cpu' else device)
+        exclude = getattr(dataset.exclude_data, 'm', dataset.exclude_data)
+        for u_idxs, i_idxs, labels in (tqdm(eval_loader) if verbose else eval_loader):
+            out = alg.predict(u_idxs.to(dev), i_idxs.to(dev))
+            if not isinstance(out, torch.Tensor):
+                out = torch.tensor(out)
+            out = out.to(dev, torch.float32)
+            batch_mask = torch.from_numpy(exclude[u_idxs.cpu().numpy()].toarray().astype(bool)).to(dev)
+            out[batch_mask] = -torch.inf
+            evaluator.eval_batch(u_idxs.to(dev), out, labels.to(dev))
+
+    metrics_values = evaluator.get_results()
+    log_info_results(metrics_values)
+    return metrics_values

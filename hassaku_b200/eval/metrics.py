@@ -1,0 +1,72 @@
+"""Batch ranking metrics behind the reference API (eval/metrics.py:4-105): dense `[B, I]` logits / y_true in,
+per-user vector or batch sum out.  Top-k comes from hsk_topk_dense (ties: lower item id first — torch.topk leaves tie
+order unspecified), the metric arithmetic from hsk_rank_metrics_dense; binary relevance like the reference."""
+import functools
+
+import torch
+
+from hassaku_b200 import _C
+
+
+@functools.lru_cache(maxsize=None)
+def _discount_cpu(k: int) -> torch.Tensor:
+    return 1. / torch.log2(torch.arange(2, k + 2).float())  # metrics.py:91 (fp32 table)
+
+
+def discount_table(k: int, device) -> torch.Tensor:
+    return _discount_cpu(k).to(device)
+
+
+def dense_topk(logits: torch.Tensor, k: int):
+    """logits.topk(k) -> (scores fp32 [B, k], ids int32 [B, k]) on the GPU kernel."""
+    if not logits.is_cuda:
+        raise _C.HskError('hassaku_b200 metrics need CUDA tensors (no CPU path)')
+    x = logits if logits.dtype == torch.float32 else logits.float()
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.reshape(x.shape[0], -1).contiguous()
+    scores = torch.empty((x.shape[0], k), dtype=torch.float32, device=x.device)
+    ids = torch.empty((x.shape[0], k), dtype=torch.int32, device=x.device)
+    _C.topk_dense(x, k, scores, ids)
+    return scores, ids
+
+
+def dense_metrics(logits: torch.Tensor, y_true: torch.Tensor, ks, idx_topk: torch.Tensor = None) -> torch.Tensor:
+    """-> per-user fp32 [B, len(ks), 3] (precision, recall, ndcg) for dense inputs."""
+    k_max = max(ks)
+    if idx_topk is None:
+        _, idx_topk = dense_topk(logits, k_max)
+    dev = y_true.device if y_true.is_cuda else idx_topk.device
+    ids = idx_topk.to(dev, torch.int32).contiguous()
+    y = y_true.to(dev, torch.float32).contiguous()
+    B = ids.shape[0]
+    per_user = torch.empty((B, len(ks), 3), dtype=torch.float32, device=dev)
+    sums = torch.zeros((1, len(ks), 3), dtype=torch.float64, device=dev)
+    counts = torch.zeros(1, dtype=torch.int64, device=dev)
+    u = torch.zeros(B, dtype=torch.int64, device=dev)
+    _C.rank_metrics_dense(ids, list(ks), u, y, discount_table(ids.shape[1], dev), sums, counts, per_user=per_user)
+    return per_user
+
+
+def _one_metric(which: int, logits, y_true, k, aggr_sum, idx_topk):
+    if idx_topk is not None:
+        assert idx_topk.shape[-1] == k, 'Top-k indexes have different "k" compared to the parameter function'
+    res = dense_metrics(logits, y_true, [k], idx_topk)[:, 0, which]
+    return res.sum() if aggr_sum else res
+
+
+def recall_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, aggr_sum: bool = True,
+                      idx_topk: torch.Tensor = None):
+    """Recall@k (metrics.py:4-36): hits / positives, 0 for users without positives."""
+    return _one_metric(1, logits, y_true, k, aggr_sum, idx_topk)
+
+
+def precision_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, aggr_sum: bool = True,
+                         idx_topk: torch.Tensor = None):
+    """Precision@k (metrics.py:39-67): hits / k."""
+    return _one_metric(0, logits, y_true, k, aggr_sum, idx_topk)
+
+
+def ndcg_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, aggr_sum: bool = True,
+                    idx_topk: torch.Tensor = None):
+    """NDCG@k with binary relevance (metrics.py:70-105), clamped to 1, 0 for users without positives."""
+    return _one_metric(2, logits, y_true, k, aggr_sum, idx_topk)

@@ -102,6 +102,47 @@ HSK_API int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, d
                     double eps, double weight_decay, int64_t step, int arith, int adam_l2, int zero_grad,
                     hsk_stream_t stream);
 
+/* ==== full-rank evaluator (eval/eval.py:54-99, 101-118, 237-253; eval/metrics.py:4-105) ========================= */
+
+/* ---- a12 + top-k of a14: evaluate_recommender_algorithm's SGD branch for one user batch (eval.py:243-253, :63) ---
+ * For every user u_idx[r], r < Be: scores against ALL rows of the item table `t->Vw` (this GPU's item shard;
+ * local row j has global item id id_offset + j * id_stride), score = <U_u, V_j> (+ Ub) (+ Ib) (+ Gb) in fp32
+ * (eval.py:247-248), -inf on every id in the user's exclusion row (CSR, sorted global ids, int32; eval.py:250-251),
+ * then the k best: top_scores/top_ids [Be, k], ordered by score descending, ties by item id ascending (torch.topk
+ * leaves tie order unspecified).  Slots beyond the number of items get id -1 / score -inf.  The [Be, I] score matrix
+ * is never materialised.  `scratch`: hsk_eval_topk_scratch_bytes(Be, t->n_items, k) bytes of device memory. */
+HSK_API int64_t hsk_eval_topk_scratch_bytes(int Be, int64_t n_local_items, int k);
+HSK_API int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int Be, int64_t id_offset, int64_t id_stride,
+                          const int64_t* excl_indptr /* [n_users + 1] or NULL */, const int32_t* excl_indices,
+                          int k /* <= 128 */, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
+                          int32_t* status, hsk_stream_t stream);
+
+/* ---- merge of G per-shard top-k lists (item-sharded evaluation: all-gather, then this) --------------------------
+ * scores/ids: [G, rows, k] (id < 0 = empty slot) -> out [rows, k], same ordering rule as hsk_eval_topk. */
+HSK_API int hsk_topk_merge(const float* scores, const int32_t* ids, int G, int rows, int k, float* out_scores,
+                           int32_t* out_ids, hsk_stream_t stream);
+
+/* ---- logits.topk(k) of a dense [rows, n_cols] fp32 matrix: FullEvaluator.eval_batch's dense API (eval.py:61-63) -- */
+HSK_API int hsk_topk_dense(const float* logits, int rows, int64_t n_cols, int64_t row_stride, int k, float* out_scores,
+                           int32_t* out_ids, hsk_stream_t stream);
+
+/* ---- a14-a17: precision / recall / ndcg @ ks (eval/metrics.py:4-105) and their per-group sums (eval.py:66-99) ----
+ * top_ids [Be, k_max] ranked item ids (id < 0 = empty); labels as CSR rows of the evaluation split (sorted int32 item
+ * ids per user) or, in the _dense variant, y_true [Be, n_items] fp32 0/1 rows (the reference's dense API).
+ * discount [k_max] fp32 = 1 / log2(r + 2).  Per user and cut-off ks[t]: precision = hits / k; recall = hits / n+
+ * (0 if the user has no positives); ndcg = min(1, dcg / idcg) (0 if no positives).  Adds into
+ * sums [(1 + n_groups), n_ks, 3] (fp64; row 0 = all users, row 1 + g = users with user_group[u] == g) and
+ * counts [1 + n_groups] (int64); if per_user != NULL also writes [Be, n_ks, 3] fp32.  The caller zeroes sums/counts
+ * at the start of a sweep and reads them once at the end (one host sync per sweep instead of >= 12 per batch). */
+HSK_API int hsk_rank_metrics(const int32_t* top_ids, int Be, int k_max, const int* ks /* host */, int n_ks,
+                             const int64_t* u_idx, const int64_t* lab_indptr, const int32_t* lab_indices,
+                             const int32_t* user_group /* [n_users] or NULL */, int n_groups, const float* discount,
+                             float* per_user, double* sums, int64_t* counts, hsk_stream_t stream);
+HSK_API int hsk_rank_metrics_dense(const int32_t* top_ids, int Be, int k_max, const int* ks /* host */, int n_ks,
+                                   const int64_t* u_idx, const float* y_true, int64_t n_items,
+                                   const int32_t* user_group, int n_groups, const float* discount, float* per_user,
+                                   double* sums, int64_t* counts, hsk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
