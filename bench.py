@@ -1,0 +1,408 @@
+"""bench.py — BPR-MF train triples/s (+ full-rank eval users/s, NDCG@10) on B200, the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3]
+
+Workload at N = 1: BASELINE.json configs[1] ("cfg2"): synthetic ML-1M shape (6 040 users x 3 706 items, ~0.93 M unique
+interactions, 80/10/10 split), d = 402, train_batch_size 8192, neg_train 50, item bias, BPR, AdamW(lr 3e-4, wd 4e-5),
+fp32 exact mode, followed by one full-rank evaluation sweep over all users.
+
+A "step" = one pass of the hot path over one batch: hsk_mf_train_fused (gather + score + BPR loss + gradient scatter)
++ hsk_adamw_dense (dense AdamW over all parameters, gradient zeroing fused).  Prints ONE JSON line (rank 0).
+
+  value      whole-job triples/s with the batches already resident in HBM, device-timed (CUDA events, max over ranks);
+             L2 is flushed between timed steps (the 63 MB of tables + optimizer state fit the 126 MB L2, so without the
+             flush the number is an L2-bandwidth number; it is reported as `value_l2_warm`)
+  e2e        the same metric through the public API (FusedMFTrainStep called with HOST batches): per step the H2D copy
+             of the int64 index batch from pinned memory and a D2H read of the loss are inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the launch stream)
+             against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the oracle port of the reference's torch path (oracle/mf_oracle.py: the same ATen
+             op sequence as train/trainer.py:133-148) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #        data     d    B     N    loss               lr     wd
+    'cfg1': ('ml1m', 402, 128, 50, 'bpr', 3e-4, 4e-5),
+    'cfg2': ('ml1m', 402, 8192, 50, 'bpr', 3e-4, 4e-5),
+    'cfg3': ('ml10m', 128, 8192, 100, 'sampled_softmax', 3e-4, 4e-5),
+}
+
+
+def algorithmic_bytes(U, I, d, B, N, item_bias=True):
+    """A = 4 d B (N+2) (every gathered row once); small = index + bias traffic; 28 B per parameter."""
+    A = 4 * d * B * (N + 2)
+    small = 8 * B * (N + 1) + 8 * B * (N + 2)
+    P = (U + I) * d + (I if item_bias else 0)
+    return {'gather_scatter': 2 * A + small, 'adamw': 28 * P, 'total': 2 * A + small + 28 * P, 'P': P, 'A': A}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {'sm_mhz': float(np.median(top)), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_batches(data, B, N, n_batches, seed=64):
+    """Captured training batches with the reference loader's semantics (data/dataloader.py:92-129): positives drawn
+    from the shuffled train interactions, N uniform negatives per row none of which is a train item of the user."""
+    rng = np.random.default_rng(seed)
+    coo = data.train.tocoo()
+    I = data.n_items
+    keys = np.sort(coo.row.astype(np.int64) * I + coo.col.astype(np.int64))
+    us, its = [], []
+    for _ in range(n_batches):
+        sel = rng.integers(0, coo.nnz, B)
+        u = coo.row[sel].astype(np.int64)
+        neg = rng.integers(0, I, (B, N), dtype=np.int64)
+        while True:
+            k = (u[:, None] * I + neg).ravel()
+            pos = np.searchsorted(keys, k)
+            hit = (keys[np.minimum(pos, len(keys) - 1)] == k).reshape(B, N)
+            if not hit.any():
+                break
+            neg[hit] = rng.integers(0, I, int(hit.sum()), dtype=np.int64)
+        us.append(u)
+        its.append(np.column_stack([coo.col[sel].astype(np.int64), neg]))
+    return us, its
+
+
+def init_like_reference(model, seed=64):
+    import torch
+    torch.manual_seed(seed)  # conf_parser.py:18 default seed; weights ~ N(0, (0.1/shape[-1])^2) (train/utils.py:13)
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the step (oracle port) on all host threads."""
+    import torch
+    from oracle import mf_oracle as O
+    from hassaku_b200.data.synthetic import make_named
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    name, d, B, N, loss, lr, wd = wl
+    data = make_named(name)
+    U, I = data.n_users, data.n_items
+    torch.manual_seed(64)
+    model = O.OracleMF(U, I, d, use_item_bias=True)
+    tr = O.OracleTrainer(model, loss, lr, wd, 'adamw', neg_train=N)
+    nb = min(args.steps + args.warmup, 8)
+    us, its = make_batches(data, B, N, nb)
+    us = [torch.from_numpy(x) for x in us]
+    its = [torch.from_numpy(x) for x in its]
+    labels = O.make_labels(B, N + 1)
+    for s in range(args.warmup):
+        tr.step(us[s % nb], its[s % nb], labels)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        tr.step(us[s % nb], its[s % nb], labels)
+    dt = time.perf_counter() - t0
+    v = args.steps * B * N / dt
+    cores = torch.get_num_threads()
+    line = {'impl': 'reference', 'metric': 'BPR-MF train triples/s', 'value': v, 'unit': 'triples/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, wl, U, I),
+            'cpu_baseline': {'value': v, 'unit': 'triples/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{args.steps} steps of {args.workload} (B={B}, N={N}) on the oracle port of '
+                                       f'train/trainer.py:133-148 (torch CPU, {cores} threads, {os.cpu_count()} cpus)'},
+            'e2e': {'value': v, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def workload_config(wname, wl, U, I):
+    name, d, B, N, loss, lr, wd = wl
+    return {'workload': f'{wname}: BPR-MF train step + full-rank eval, synthetic {name} shape', 'n_users': U, 'n_items': I,
+            'embedding_dim': d, 'train_batch_size': B, 'neg_train': N, 'rec_loss': loss, 'optimizer': 'adamw', 'lr': lr,
+            'wd': wd, 'item_bias': True, 'eval_batch_size': 8192, 'precision': 'fp32 exact',
+            'l2': 'flushed between timed steps (tables + optimizer state fit L2); value_l2_warm = back to back'}
+
+
+def cpu_baseline(wl, data, us, its, budget_s=20.0):
+    import torch
+    from oracle import mf_oracle as O
+    name, d, B, N, loss, lr, wd = wl
+    torch.manual_seed(64)
+    model = O.OracleMF(data.n_users, data.n_items, d, use_item_bias=True)
+    tr = O.OracleTrainer(model, loss, lr, wd, 'adamw', neg_train=N)
+    labels = O.make_labels(B, N + 1)
+    tr.step(torch.from_numpy(us[0]), torch.from_numpy(its[0]), labels)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        tr.step(torch.from_numpy(us[n % len(us)]), torch.from_numpy(its[n % len(us)]), labels)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 30:
+            break
+    cores = torch.get_num_threads()
+    return {'value': n * B * N / dt, 'unit': 'triples/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{n} steps of the same workload (B={B}, N={N}) on the oracle port (torch CPU, {cores} threads of '
+                      f'{os.cpu_count()} cpus), {dt:.1f} s'}
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.data.synthetic import make_named
+    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+    from hassaku_b200.train.optim import DenseAdam
+    from hassaku_b200.train.rec_losses import RecommenderSystemLossesEnum
+    from hassaku_b200.train.trainer_step import FusedMFTrainStep
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    name, d, B, N, loss, lr, wd = wl
+    data = make_named(name)
+    U, I = data.n_users, data.n_items
+    K, W = args.steps, max(args.warmup, 0)
+
+    init_like_reference(None)
+    model = SGDMatrixFactorization(U, I, d, use_item_bias=True).to(dev)
+
+    class _DS:
+        n_items = I
+
+    loss_fn = RecommenderSystemLossesEnum[loss].value.build_from_conf({'train_neg_strategy': 'uniform', 'neg_train': N},
+                                                                      _DS())
+    opt = DenseAdam(model, lr=lr, weight_decay=wd, decoupled=True)
+    step = FusedMFTrainStep(model, loss_fn, opt)
+
+    n_distinct = 16
+    us, its = make_batches(data, B, N, n_distinct, seed=64 + rank)
+    u_dev = [torch.from_numpy(x).to(dev) for x in us]
+    i_dev = [torch.from_numpy(x).to(dev) for x in its]
+    u_pin = [torch.from_numpy(x).pin_memory() for x in us]
+    i_pin = [torch.from_numpy(x).pin_memory() for x in its]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- (1) resident inputs, L2 flushed between timed steps ----
+    for s in range(W):
+        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        for s in range(K):
+            flush.zero_()
+            ev0[s].record()
+            step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+            ev1[s].record()
+        barrier()
+    ms_flushed = max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
+
+    # ---- (2) back to back (L2 warm), one event pair around K steps ----
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clk_warm:
+        a.record()
+        for s in range(K):
+            step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+        b.record()
+        barrier()
+    ms_warm = max_over_ranks(a.elapsed_time(b))
+
+    # ---- (3) per-kernel durations (events between the two launches), L2 flushed ----
+    tabs, gtabs = model._tables(), opt.grad_tables
+    kind, shift = _C.LOSS_KINDS[loss_fn.loss_kind], float(loss_fn.neg_shift())
+    e = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier()
+    for s in range(K):
+        flush.zero_()
+        e[s][0].record()
+        _C.mf_train_fused(tabs, gtabs, u_dev[s % n_distinct], i_dev[s % n_distinct], kind, shift, step.loss_accum,
+                          status=model._status())
+        e[s][1].record()
+        opt.step_fused()
+        e[s][2].record()
+    barrier()
+    ms_fused = sum(x[0].elapsed_time(x[1]) for x in e) / K
+    ms_adamw = sum(x[1].elapsed_time(x[2]) for x in e) / K
+
+    # ---- (4) end to end through the public API with HOST batches ----
+    loss_pin = torch.zeros(K, dtype=torch.float64).pin_memory()
+    loss_dev = torch.zeros(K, dtype=torch.float64, device=dev)
+    for s in range(min(W, 3)):
+        step(u_pin[s % n_distinct], i_pin[s % n_distinct])
+    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    a2.record()
+    for s in range(K):
+        step(u_pin[s % n_distinct], i_pin[s % n_distinct], loss_out=loss_dev[s:s + 1])
+        loss_pin[s:s + 1].copy_(loss_dev[s:s + 1], non_blocking=True)
+    b2.record()
+    barrier()
+    wall_e2e = (time.perf_counter() - t_wall0) * 1e3
+    ms_e2e = max_over_ranks(max(a2.elapsed_time(b2), 0.0))
+    last_loss = float(loss_pin[K - 1])
+    model.check_status()
+    assert math.isfinite(last_loss), 'training diverged'
+
+    # ---- (5) full-rank evaluation sweep (all users, top-100, 12 metrics) ----
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, data.n_user_groups)
+
+    class _Loader:
+        dataset, batch_size = ds, 8192
+
+    def eval_once():
+        ev = FullEvaluator(True, ds.n_user_groups, ds.user_to_user_group)
+        return evaluate_recommender_algorithm(model, _Loader, ev, dev)
+
+    eval_once()
+    barrier()
+    t0 = time.perf_counter()
+    n_eval = 5
+    for _ in range(n_eval):
+        res = eval_once()
+    torch.cuda.synchronize()
+    eval_ms = (time.perf_counter() - t0) * 1e3 / n_eval
+
+    if rank != 0:
+        return
+    ab = algorithmic_bytes(U, I, d, B, N)
+    peak, peak_src = measured_peaks()
+    dom = 'hsk_mf_train_fused' if ms_fused >= ms_adamw else 'hsk_adamw_dense'
+    dom_bytes = ab['gather_scatter'] if dom == 'hsk_mf_train_fused' else ab['adamw']
+    dom_ms = max(ms_fused, ms_adamw)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    triples = B * N * world
+    line = {
+        'metric': 'BPR-MF train triples/s', 'value': triples * K / (ms_flushed * 1e-3), 'unit': 'triples/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_flushed / K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, wl, U, I),
+        'value_l2_warm': triples * K / (ms_warm * 1e-3), 'ms_per_step_l2_warm': ms_warm / K,
+        'samples_per_s': B * world * K / (ms_flushed * 1e-3),
+        'e2e': {'value': triples * K / (ms_e2e * 1e-3), 'unit': 'triples/s',
+                'h2d_bytes_per_step': int(us[0].nbytes + its[0].nbytes), 'd2h_bytes_per_step': 8,
+                'ms_per_step': ms_e2e / K, 'wall_ms_per_step': wall_e2e / K},
+        'gpu_launches': 2 * K,
+        'kernels_ms': {'hsk_mf_train_fused': ms_fused, 'hsk_adamw_dense': ms_adamw},
+        'roofline': {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': dom_bytes,
+                     'step': {'algorithmic_bytes': ab['total'], 'achieved': ab['total'] / (ms_flushed / K * 1e-3) / 1e9,
+                              'frac': ab['total'] / (ms_flushed / K * 1e-3) / 1e9 / peak},
+                     'note': 'tables + optimizer state (63 MB) are L2-resident: algorithmic GB/s may exceed DRAM peak'},
+        'clocks': clk.summary(),
+        'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
+                 'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U, 'timing': 'host wall clock incl. the '
+                 'single D2H sync of the sweep'},
+        'final_loss': last_loss,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            line['cpu_baseline'] = cpu_baseline(wl, data, us, its)
+        except Exception as ex:  # never lose the GPU numbers to a baseline problem
+            line['cpu_baseline'] = {'error': repr(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

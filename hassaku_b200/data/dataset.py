@@ -40,7 +40,7 @@ class RecDataset(data.Dataset):
         self.n_users, self.n_items = len(users), len(items)
         if 'group_idx' in users.columns:  # dataset.py:68-72
             grp = users[['user_idx', 'group_idx']].set_index('user_idx').sort_index().group_idx
-            self.user_to_user_group = torch.Tensor(grp.to_numpy())
+            self.user_to_user_group = torch.Tensor(grp.to_numpy().copy())
             self.n_user_groups = users.group_idx.nunique()
         self.lhs = self._load_lhs(self.split_set)
         logging.info(f'Loaded {self.split_set}: {self.n_users} users, {self.n_items} items, {len(self.lhs)} interactions')
