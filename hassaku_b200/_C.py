@@ -44,6 +44,7 @@ def _declare(lib):
         'hsk_mf_scatter_grads': (i32, [T, T, vp, vp, vp, i32, i32, vp, vp]),
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
+        'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
         'hsk_eval_topk_scratch_bytes': (i64, [i32, i64, i32]),
         'hsk_eval_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
         'hsk_topk_merge': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
@@ -158,6 +159,20 @@ def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arit
         raise HskError('adamw_dense: p, m, v, g must have the same number of elements')
     _check(lib().hsk_adamw_dense(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, lr, beta1, beta2, eps,
                                  weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')
+
+
+def sample_negatives(u_idx, pos_idx, n_neg: int, n_items: int, n_users: int, csr_indptr, csr_indices, seed: int,
+                     step: int, i_idx, distinct_in_row: bool = True, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx')
+    _req(csr_indptr, torch.int64, 'csr_indptr'); _req(csr_indices, torch.int32, 'csr_indices')
+    if pos_idx is not None:
+        _req(pos_idx, torch.int64, 'pos_idx')
+    B = u_idx.numel()
+    if tuple(i_idx.shape) != (B, n_neg + 1):
+        raise HskError(f'i_idx must be [{B}, {n_neg + 1}]')
+    _check(lib().hsk_sample_negatives(u_idx.data_ptr(), _ptr(pos_idx), B, n_neg, n_items, n_users, csr_indptr.data_ptr(),
+                                      csr_indices.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, step, int(distinct_in_row),
+                                      i_idx.data_ptr(), _ptr(status), _stream()), 'hsk_sample_negatives')
 
 
 # ---- evaluator ----

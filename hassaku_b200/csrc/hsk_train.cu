@@ -10,37 +10,11 @@
 // sample (user row in registers, item slots strided over the warps); when the batch alone cannot fill the
 // machine the item slots are additionally split over gridDim.y (gradients are linear in dL/ds, so partial
 // CTAs simply add their share).  All kernels are HBM/L2-bandwidth bound: ~25 issue slots per 16 B moved.
-#include "hsk_common.cuh"
+#include <stdlib.h>
+
+#include "hsk_train.cuh"
 
 namespace hsk {
-
-constexpr int kWarpsPerCta = 4;
-
-struct TrainArgs {
-    const float* __restrict__ Uw;
-    const float* __restrict__ Vw;
-    const float* __restrict__ Ub;
-    const float* __restrict__ Ib;
-    const float* __restrict__ Gb;
-    float* gU;
-    float* gV;
-    float* gUb;
-    float* gIb;
-    float* gGb;
-    const int64_t* __restrict__ u_idx;
-    const int64_t* __restrict__ i_idx;
-    int64_t n_users, n_items;
-    int B, N1, ld, nvec;
-    int j_per_cta;  // item slots (excluding slot 0) handled by one CTA along gridDim.y
-    int loss_kind;
-    float neg_shift;
-    double inv_count;  // 1/(B*N) bpr, 1/B sampled-softmax, 1/(B*N1) bce
-    double* loss_accum;
-    float* scores_out;
-    float* dscores_out;
-    const float* __restrict__ dscores_in;
-    int32_t* status;
-};
 
 // ------------------------------------------------------------------------------------------------
 // forward only
@@ -509,19 +483,29 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
     cudaStream_t s = as_stream(stream);
     const int nv = (a.nvec + 31) / 32;
     const int threads = kWarpsPerCta * 32;
+    // bpr / bce default to the TMA-pipelined kernel (hsk_train_tma.cu); HSK_TRAIN_FUSED=regs selects the
+    // register-gather kernel of this file (kept for A/B measurements and as the sampled-softmax path)
+    const char* variant = getenv("HSK_TRAIN_FUSED");
+    const bool use_tma = !(variant && strcmp(variant, "regs") == 0);
+    const char* nored = getenv("HSK_DEBUG_NORED");
+    a.debug_flags = (nored && nored[0] == '1') ? 1 : 0;
     if (loss_kind == HSK_LOSS_BPR) {
         a.inv_count = 1.0 / ((double)B * (double)(N1 - 1));
         a.j_per_cta = pick_j_per_cta(B, N1 - 1, true);
+        if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 - 1 + a.j_per_cta - 1) / a.j_per_cta);
         if (grid.y > 1 && dscores_out) {  // positive-slot dL/ds is accumulated across gridDim.y
             cudaError_t e = cudaMemsetAsync(dscores_out, 0, sizeof(float) * (size_t)B * N1, s);
             if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_mf_train_fused: memset: %s", cudaGetErrorString(e));
         }
+        if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BPR><<<grid, threads, 0, s>>>(a)));
     } else if (loss_kind == HSK_LOSS_BCE) {
         a.inv_count = 1.0 / ((double)B * (double)N1);
         a.j_per_cta = pick_j_per_cta(B, N1, true);
+        if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 + a.j_per_cta - 1) / a.j_per_cta);
+        if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BCE><<<grid, threads, 0, s>>>(a)));
     } else {
         a.inv_count = 1.0 / (double)B;

@@ -1,0 +1,40 @@
+// Argument block shared by the training-step kernels (hsk_train.cu, hsk_train_tma.cu).
+#pragma once
+#include "hsk_common.cuh"
+
+namespace hsk {
+
+constexpr int kWarpsPerCta = 4;
+
+struct TrainArgs {
+    const float* __restrict__ Uw;
+    const float* __restrict__ Vw;
+    const float* __restrict__ Ub;
+    const float* __restrict__ Ib;
+    const float* __restrict__ Gb;
+    float* gU;
+    float* gV;
+    float* gUb;
+    float* gIb;
+    float* gGb;
+    const int64_t* __restrict__ u_idx;
+    const int64_t* __restrict__ i_idx;
+    int64_t n_users, n_items;
+    int B, N1, ld, nvec;
+    int j_per_cta;  // item slots (excluding slot 0) handled by one CTA along gridDim.y
+    int loss_kind;
+    float neg_shift;
+    double inv_count;  // 1/(B*N) bpr, 1/B sampled-softmax, 1/(B*N1) bce
+    double* loss_accum;
+    float* scores_out;
+    float* dscores_out;
+    const float* __restrict__ dscores_in;
+    int32_t* status;
+    int debug_flags;  // bit 0: skip item-gradient reductions (HSK_DEBUG_NORED=1, measurement only)
+};
+
+
+// hsk_train_tma.cu: the bulk-copy (TMA) pipelined fused step for bpr / bce; returns HSK_OK or an error code
+int launch_train_fused_tma(const TrainArgs& a, int loss_kind, cudaStream_t s);
+
+}  // namespace hsk

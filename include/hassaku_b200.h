@@ -102,6 +102,17 @@ HSK_API int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, d
                     double eps, double weight_decay, int64_t step, int arith, int adam_l2, int zero_grad,
                     hsk_stream_t stream);
 
+/* ---- a10: uniform negative sampling on the device (data/dataloader.py:56-57, 92-129) -------------------------------
+ * For every batch row b: i_idx[b, 0] = pos_idx[b] (if pos_idx != NULL) and i_idx[b, 1..N] = N items drawn uniformly
+ * from [0, n_items) none of which is a TRAIN item of user u_idx[b] (CSR of the training interactions: indptr int64
+ * [n_users + 1], indices int32 sorted per row), redrawing flagged slots until the row is clean — the reference's
+ * collate loop.  distinct_in_row != 0 additionally redraws a slot when a higher slot of the row holds the same item
+ * (numpy's assume_unique sort path; the reference's common case).  Stream: Philox4x32-10 keyed by (seed, step), a
+ * pure function of (seed, step, b, slot) — restated bit-exactly by oracle/philox.py.  i_idx is [B, 1 + N] int64. */
+HSK_API int hsk_sample_negatives(const int64_t* u_idx, const int64_t* pos_idx /* nullable */, int B, int N, int64_t n_items,
+                                 int64_t n_users, const int64_t* csr_indptr, const int32_t* csr_indices, uint64_t seed,
+                                 uint64_t step, int distinct_in_row, int64_t* i_idx, int32_t* status, hsk_stream_t stream);
+
 /* ==== full-rank evaluator (eval/eval.py:54-99, 101-118, 237-253; eval/metrics.py:4-105) ========================= */
 
 /* ---- a12 + top-k of a14: evaluate_recommender_algorithm's SGD branch for one user batch (eval.py:243-253, :63) ---

@@ -1,0 +1,71 @@
+"""Kernel micro-benchmarks (CUDA events, L2 flushed between launches) for A/B-ing kernel variants on the GPU box.
+    python scripts/kbench.py train [--workload cfg2] [--variants regs,tma]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def time_kernel(fn, iters=30, flush=None):
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts = sorted(ts)
+    return ts[len(ts) // 2], ts[0]
+
+
+def train(args):
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.synthetic import make_named
+    from hassaku_b200.train.optim import DenseAdam
+    name, d, B, N, loss, lr, wd = bench.WORKLOADS[args.workload]
+    data = make_named(name)
+    U, I = data.n_users, data.n_items
+    torch.manual_seed(64)
+    model = SGDMatrixFactorization(U, I, d, use_item_bias=True).to('cuda')
+    opt = DenseAdam(model, lr=lr, weight_decay=wd)
+    us, its = bench.make_batches(data, B, N, 4)
+    u = [torch.from_numpy(x).cuda() for x in us]
+    i = [torch.from_numpy(x).cuda() for x in its]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    kind = _C.LOSS_KINDS[loss]
+    shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
+    ab = bench.algorithmic_bytes(U, I, d, B, N)
+    for v in args.variants.split(','):
+        os.environ['HSK_TRAIN_FUSED'] = v
+        k = [0]
+
+        def fn():
+            _C.mf_train_fused(model._tables(), opt.grad_tables, u[k[0] % 4], i[k[0] % 4], kind, shift, acc)
+            k[0] += 1
+        for _ in range(3):
+            fn()
+        med, best = time_kernel(fn, 30, flush)
+        medw, bestw = time_kernel(fn, 30, None)
+        print(f'fused[{v:5s}] flushed med {med*1e3:8.1f} us best {best*1e3:8.1f} us | warm med {medw*1e3:8.1f} us  '
+              f'-> {ab["gather_scatter"]/med/1e6:8.0f} GB/s algorithmic')
+        opt.g.zero_()
+    med, best = time_kernel(lambda: opt.step_fused(), 30, flush)
+    print(f'adamw        flushed med {med*1e3:8.1f} us best {best*1e3:8.1f} us -> {ab["adamw"]/med/1e6:8.0f} GB/s (28 B/param)')
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('what', choices=['train'])
+    ap.add_argument('--workload', default='cfg2')
+    ap.add_argument('--variants', default='regs,tma')
+    train(ap.parse_args())
