@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libhassaku_b200.so')
 
 LOSS_KINDS = {'bpr': 0, 'sampled_softmax': 1, 'bce': 2}
 STATUS_BAD_INDEX = 1
+PRECISIONS = {'fp32': 0, 'tf32': 1, 'bf16': 2}
 
 
 class HskError(RuntimeError):
@@ -47,6 +48,11 @@ def _declare(lib):
         'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
         'hsk_eval_topk_scratch_bytes': (i64, [i32, i64, i32]),
         'hsk_eval_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+        'hsk_eval_tc_kpad': (i32, [i32, i32]),
+        'hsk_pack_rows': (i32, [vp, i32, i32, vp, i64, i64, vp, i32, i32, vp, vp]),
+        'hsk_eval_topk_tc_scratch_bytes': (i64, [i32, i64, i32]),
+        'hsk_eval_topk_tc': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp,
+                                   i64, vp, vp]),
         'hsk_topk_merge': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         'hsk_topk_dense': (i32, [vp, i32, i64, i64, i32, vp, vp, vp]),
         'hsk_rank_metrics': (i32, [vp, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
@@ -189,6 +195,40 @@ def eval_topk(tables: MfTables, u_idx, k: int, top_scores, top_ids, scratch, exc
     _check(lib().hsk_eval_topk(C.byref(tables), u_idx.data_ptr(), Be, id_offset, id_stride, _ptr(excl_indptr),
                                _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(), scratch.data_ptr(),
                                scratch.numel() * scratch.element_size(), _ptr(status), _stream()), 'hsk_eval_topk')
+
+
+def eval_tc_kpad(d: int, precision: int) -> int:
+    return int(lib().hsk_eval_tc_kpad(d, precision))
+
+
+def pack_rows(src, d: int, precision: int, row_idx=None, out=None, status=None):
+    """fp32 table rows [n, ld] (optionally gathered by row_idx) -> packed [rows, kpad] bf16 / tf32 operand."""
+    if not src.is_cuda or src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
+        raise HskError('pack_rows: src must be a 2-D fp32 CUDA tensor with unit inner stride')
+    kpad = eval_tc_kpad(d, precision)
+    n_out = src.shape[0] if row_idx is None else row_idx.numel()
+    dt = torch.float32 if precision == PRECISIONS['tf32'] else torch.bfloat16
+    if out is None:
+        out = torch.empty((n_out, kpad), dtype=dt, device=src.device)
+    if row_idx is not None:
+        _req(row_idx, torch.int64, 'row_idx')
+    _check(lib().hsk_pack_rows(src.data_ptr(), src.stride(0), d, _ptr(row_idx), n_out, src.shape[0], out.data_ptr(), kpad,
+                               precision, _ptr(status), _stream()), 'hsk_pack_rows')
+    return out
+
+
+def eval_topk_tc_scratch_bytes(Be: int, n_local_items: int, k: int) -> int:
+    return int(lib().hsk_eval_topk_tc_scratch_bytes(Be, n_local_items, k))
+
+
+def eval_topk_tc(Uq, Vq, precision: int, u_idx, n_users: int, k: int, top_scores, top_ids, scratch, Ub=None, Ib=None,
+                 Gb=None, excl_indptr=None, excl_indices=None, id_offset: int = 0, id_stride: int = 1, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
+    Be, kpad = Uq.shape
+    _check(lib().hsk_eval_topk_tc(Uq.data_ptr(), Vq.data_ptr(), kpad, precision, _ptr(Ub), _ptr(Ib), _ptr(Gb),
+                                  u_idx.data_ptr(), Be, n_users, Vq.shape[0], id_offset, id_stride, _ptr(excl_indptr),
+                                  _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(), scratch.data_ptr(),
+                                  scratch.numel() * scratch.element_size(), _ptr(status), _stream()), 'hsk_eval_topk_tc')
 
 
 def topk_merge(scores, ids, out_scores, out_ids):

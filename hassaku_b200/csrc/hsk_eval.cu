@@ -401,6 +401,11 @@ static void eval_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_spli
     *n_splits = (nt + tps - 1) / tps;
 }
 
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s) {
+    topk_merge_keys_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lists, n_lists, rows, kCap, k, out_scores, out_ids);
+    return check_launch("topk merge");
+}
+
 }  // namespace hsk
 
 using namespace hsk;
@@ -442,10 +447,7 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int B
     eval_topk_f32_kernel<<<grid, kEvalThreads, 0, s>>>(a);
     int rc = check_launch("hsk_eval_topk");
     if (rc) return rc;
-    if (a.n_splits > 1) {
-        topk_merge_keys_kernel<<<(Be + 7) / 8, 256, 0, s>>>(a.cand, a.n_splits, Be, kCap, k, top_scores, top_ids);
-        rc = check_launch("hsk_eval_topk(merge)");
-    }
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s);
     return rc;
 }
 

@@ -1,0 +1,439 @@
+// Full-rank evaluator, tensor-core mode (TF32 / BF16): scores = U_b · V^T on tcgen05 with TMEM accumulators, fed by TMA,
+// fused with bias add, exclusion mask and running top-k — the [Be, I] score matrix never leaves the SM.
+//
+// Per CTA (192 threads, 1 per SM):
+//   warp 0      TMA producer: the 128-user A tile is loaded ONCE (resident for every item tile); item (B) tiles of
+//               128 rows x 128 bytes of K stream through a 4-stage ring (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//   warp 1      allocates 256 TMEM columns (2 accumulator stages x 128 fp32 columns) and issues tcgen05.mma
+//               (cta_group::1, M = 128, N = 128, 32 bytes of K per instruction), tcgen05.commit -> mbarriers
+//   warps 2-5   epilogue: thread r of the quarter owns accumulator lane (= user row) r; tcgen05.ld 32 columns at a time,
+//               + item bias, chunk max against the row's running k-th score; only survivors take the slow path
+//               (exclusion-CSR binary search, key build, append to the row's candidate list); lists are cut back by a
+//               warp-cooperative bitonic sort (hsk_topk.cuh).  The accumulator stage is released before the pruning so
+//               the MMA of tile t+1 overlaps the epilogue of tile t.
+// Operands are packed row-major [rows, kpad] (K-major for both A and B) by hsk_pack_rows: bf16 (round-to-nearest-even)
+// or tf32 (fp32 container, rna-rounded), zero padded to a multiple of 128 bytes of K.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "hsk_topk.cuh"
+
+namespace hsk {
+
+constexpr int TC_BM = 128;        // users per CTA tile (UMMA_M)
+constexpr int TC_BN = 128;        // items per tile (UMMA_N)
+constexpr int TC_KB_BYTES = 128;  // bytes of K per k-block (one 128B swizzle atom)
+constexpr int TC_STAGES = 4;
+constexpr int TC_TILE_BYTES = TC_BN * TC_KB_BYTES;  // 16 KB per operand tile per k-block
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_KB = 8;      // kpad * elem_size <= 1024 bytes -> d <= 512 (bf16) / 256 (tf32)
+
+struct EvalTcArgs {
+    const float* __restrict__ Ub;   // user bias TABLE (indexed by u_idx) or null
+    const float* __restrict__ Ib;   // local item bias or null
+    const float* __restrict__ Gb;
+    const int64_t* __restrict__ u_idx;
+    const int64_t* __restrict__ excl_indptr;
+    const int32_t* __restrict__ excl_indices;
+    int64_t n_users, n_local, id_offset, id_stride;
+    int Be, k, num_kb, kelems_per_kb;
+    int n_tiles, tiles_per_split, n_splits;
+    uint64_t* cand;
+    float* out_scores;
+    int32_t* out_ids;
+    int32_t* status;
+};
+
+// ---- PTX wrappers ----
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+                     "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::
+                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    } else {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::
+                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
+// start address >> 4 | SBO = 1024 B (8 rows x 128 B) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_a, bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM;
+    const int split = blockIdx.y;
+    const int t_begin = split * a.tiles_per_split;
+    const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
+    const int n_my_tiles = t_end - t_begin;
+
+    // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smA = smem;                                        // num_kb x 16 KB, resident
+    unsigned char* smB = smem + (size_t)a.num_kb * TC_TILE_BYTES;     // TC_STAGES x 16 KB
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {  // TMEM: 2 accumulator stages x 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA));
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB));
+            mbar_expect_tx(&bar_a, (uint32_t)a.num_kb * TC_TILE_BYTES);
+            for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d(smA + (size_t)kb * TC_TILE_BYTES, &tmA, kb * a.kelems_per_kb, m0, &bar_a);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < n_my_tiles; ++t) {
+                const int n0 = (t_begin + t) * TC_BN;
+                for (int kb = 0; kb < a.num_kb; ++kb) {
+                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&bar_full[s], TC_TILE_BYTES);
+                    tma_load_2d(smB + (size_t)s * TC_TILE_BYTES, &tmB, kb * a.kelems_per_kb, n0, &bar_full[s]);
+                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16 (1) | TF32 (2), K-major both, N = 128, M = 128
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            mbar_wait(&bar_a, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < n_my_tiles; ++t) {
+                const int as = t & 1;
+                mbar_wait(&bar_tempty[as], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + (uint32_t)as * TC_BN;
+                for (int kb = 0; kb < a.num_kb; ++kb) {
+                    mbar_wait(&bar_full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc(smem_u32(smA + (size_t)kb * TC_TILE_BYTES));
+                    const uint64_t db = umma_desc(smem_u32(smB + (size_t)s * TC_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TC_KB_BYTES / 32; ++k)  // 32 bytes of K per MMA: advance the start address by 2 (x16 B)
+                        tc_mma<TF32>(tmem_c, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&bar_empty[s]);
+                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(&bar_tfull[as]);
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;   // row within the tile == TMEM lane
+        const int row = m0 + r;
+        bool row_ok = row < a.Be;
+        int64_t ex_lo = 0, ex_hi = 0;
+        float ub = 0.f;
+        if (row_ok) {
+            const int64_t u = a.u_idx[row];
+            if (bad_index(u, a.n_users)) {
+                row_ok = false;
+                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
+            } else {
+                if (a.excl_indptr) { ex_lo = a.excl_indptr[u]; ex_hi = a.excl_indptr[u + 1]; }
+                if (a.Ub) ub = a.Ub[u];
+            }
+        }
+        const float base_bias = ub + (a.Gb ? a.Gb[0] : 0.f);
+        uint64_t* list = a.cand + ((int64_t)split * a.Be + (row < a.Be ? row : 0)) * kCap;
+        int cnt = 0;
+        float tauf = -INFINITY;
+        uint64_t taukey = 0ull;
+        const int prune_at = kCap - TC_BN;
+
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int as = t & 1;
+            const int64_t n0 = (int64_t)(t_begin + t) * TC_BN;
+            const int ncols = (int)min((int64_t)TC_BN, a.n_local - n0);
+            mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN; c += 32) {
+                float v[32];
+                tc_ld32(taddr + (uint32_t)c, v);
+                if (c >= ncols) continue;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    float s = v[e] + base_bias;
+                    if (a.Ib) s += (c + e < ncols) ? __ldg(a.Ib + n0 + c + e) : 0.f;
+                    v[e] = s;
+                    mx = fmaxf(mx, (c + e < ncols) ? s : -INFINITY);
+                }
+                if (row_ok && mx >= tauf) {
+#pragma unroll 1
+                    for (int e = 0; e < 32; ++e) {
+                        if (c + e >= ncols) break;
+                        float s = v[e];
+                        if (s >= tauf) {
+                            const int64_t gid = a.id_offset + (n0 + c + e) * a.id_stride;
+                            if (csr_contains(a.excl_indices, ex_lo, ex_hi, (int32_t)gid)) s = -INFINITY;
+                            const uint64_t key = make_key(s, (uint32_t)gid);
+                            if (key > taukey) list[cnt++] = key;
+                        }
+                    }
+                }
+            }
+            // release the accumulator stage, then prune (the MMA of the next tile runs meanwhile)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            const bool last = (t + 1 == n_my_tiles);
+            unsigned need = __ballot_sync(kFull, row_ok && (cnt > prune_at || last));
+            while (need) {
+                const int rr = __ffs(need) - 1;
+                need &= need - 1;
+                const int n_r = __shfl_sync(kFull, cnt, rr);
+                const unsigned long long lp = __shfl_sync(kFull, (unsigned long long)list, rr);
+                uint64_t thr;
+                __syncwarp();
+                const int nn = warp_prune_list(reinterpret_cast<uint64_t*>(lp), n_r, a.k, lane, &thr);
+                if (lane == rr) {
+                    cnt = nn;
+                    taukey = thr;
+                    tauf = thr ? key_score(thr) : -INFINITY;
+                }
+                if (last && a.n_splits == 1) {
+                    __syncwarp();
+                    const int64_t orow = (int64_t)(m0 + quarter * 32 + rr) * a.k;
+                    for (int e = lane; e < a.k; e += 32) {
+                        const uint64_t key = reinterpret_cast<uint64_t*>(lp)[e];
+                        a.out_scores[orow + e] = key ? key_score(key) : -INFINITY;
+                        a.out_ids[orow + e] = key_id(key);
+                    }
+                }
+            }
+        }
+        // rows with a bad user index (or an empty split): empty lists / -1 ids
+        if (row < a.Be && !row_ok) {
+            if (a.n_splits == 1) {
+                for (int e = 0; e < a.k; ++e) { a.out_scores[(int64_t)row * a.k + e] = -INFINITY; a.out_ids[(int64_t)row * a.k + e] = -1; }
+            } else {
+                for (int e = 0; e < a.k; ++e) list[e] = 0ull;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256));
+    }
+}
+
+// ---- operand packing: fp32 table rows (optionally gathered) -> [rows, kpad] bf16 | tf32, zero padded ----
+template <bool TF32>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, int ld, int d, const int64_t* __restrict__ idx,
+                                                        int64_t n_out, int64_t n_src, void* __restrict__ dst, int kpad, int32_t* status) {
+    const int64_t total = n_out * kpad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / kpad;
+        const int k = (int)(e - r * kpad);
+        float v = 0.f;
+        if (k < d) {
+            int64_t sr = idx ? idx[r] : r;
+            if (bad_index(sr, n_src)) {
+                if (status) atomicOr(status, HSK_STATUS_BAD_INDEX);
+            } else {
+                v = src[sr * ld + k];
+            }
+        }
+        if (TF32) {
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(t) : "f"(v));
+            reinterpret_cast<uint32_t*>(dst)[e] = t;
+        } else {
+            reinterpret_cast<__nv_bfloat16*>(dst)[e] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* map, const void* base, bool tf32, int kpad, int64_t rows, int kelems_per_kb) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return set_err(HSK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const size_t esz = tf32 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * esz};
+    cuuint32_t box[2] = {(cuuint32_t)kelems_per_kb, (cuuint32_t)TC_BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(HSK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HSK_OK;
+}
+
+static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split, int* n_splits) {
+    const int row_tiles = (Be + TC_BM - 1) / TC_BM;
+    const int nt = (int)((n_local + TC_BN - 1) / TC_BN);
+    const int want = sm_count();
+    int splits = 1;
+    if (row_tiles < want) splits = (want + row_tiles - 1) / row_tiles;
+    const int max_splits = nt / 8 > 0 ? nt / 8 : 1;   // at least 8 item tiles per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    const int tps = (nt + splits - 1) / splits;
+    *n_tiles = nt;
+    *tiles_per_split = tps;
+    *n_splits = (nt + tps - 1) / tps;
+}
+
+}  // namespace hsk
+
+using namespace hsk;
+
+extern "C" int hsk_eval_tc_kpad(int d, int precision) {
+    const int per_kb = (precision == HSK_PREC_TF32) ? 32 : 64;
+    return ((d + per_kb - 1) / per_kb) * per_kb;
+}
+
+extern "C" int hsk_pack_rows(const float* src, int ld, int d, const int64_t* row_idx, int64_t n_out, int64_t n_src, void* dst,
+                             int kpad, int precision, int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(src && dst, "hsk_pack_rows: null pointer");
+    HSK_REQUIRE(precision == HSK_PREC_TF32 || precision == HSK_PREC_BF16, "hsk_pack_rows: precision must be TF32 or BF16");
+    HSK_REQUIRE(d >= 1 && ld >= d && kpad >= d && n_out >= 0, "hsk_pack_rows: bad sizes");
+    if (n_out == 0) return HSK_OK;
+    const int64_t total = n_out * kpad;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (precision == HSK_PREC_TF32)
+        pack_rows_kernel<true><<<(int)blocks, 256, 0, as_stream(stream)>>>(src, ld, d, row_idx, n_out, n_src, dst, kpad, status);
+    else
+        pack_rows_kernel<false><<<(int)blocks, 256, 0, as_stream(stream)>>>(src, ld, d, row_idx, n_out, n_src, dst, kpad, status);
+    return check_launch("hsk_pack_rows");
+}
+
+extern "C" int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items, int k) {
+    (void)k;
+    int nt, tps, ns;
+    tc_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, &nt, &tps, &ns);
+    return (int64_t)ns * (Be > 0 ? Be : 1) * kCap * (int64_t)sizeof(uint64_t);
+}
+
+extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
+                                const float* Gb, const int64_t* u_idx, int Be, int64_t n_users, int64_t n_local,
+                                int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
+                                int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
+                                int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(Uq && Vq && u_idx && top_scores && top_ids, "hsk_eval_topk_tc: null pointer");
+    HSK_REQUIRE(precision == HSK_PREC_TF32 || precision == HSK_PREC_BF16, "hsk_eval_topk_tc: precision must be TF32 or BF16");
+    const bool tf32 = precision == HSK_PREC_TF32;
+    const int per_kb = tf32 ? 32 : 64;
+    HSK_REQUIRE(kpad >= per_kb && kpad % per_kb == 0, "hsk_eval_topk_tc: kpad must be a multiple of %d", per_kb);
+    const int num_kb = kpad / per_kb;
+    if (num_kb > TC_MAX_KB)
+        return set_err(HSK_ERR_UNSUPPORTED, "hsk_eval_topk_tc: embedding_dim too large for the tensor-core mode (kpad=%d)", kpad);
+    HSK_REQUIRE((reinterpret_cast<uintptr_t>(Uq) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vq) & 15) == 0, "hsk_eval_topk_tc: operands must be 16-byte aligned");
+    HSK_REQUIRE(k >= 1 && k <= kMaxK && Be >= 0 && n_local >= 1, "hsk_eval_topk_tc: bad sizes");
+    HSK_REQUIRE(id_stride >= 1 && id_offset >= 0 && id_offset + (n_local - 1) * id_stride < 0x7FFFFFFFll, "hsk_eval_topk_tc: bad id mapping");
+    HSK_REQUIRE((excl_indptr == nullptr) == (excl_indices == nullptr), "hsk_eval_topk_tc: exclusion CSR needs both arrays");
+    if (Be == 0) return HSK_OK;
+    EvalTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Ub = Ub; a.Ib = Ib; a.Gb = Gb; a.u_idx = u_idx; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
+    a.n_users = n_users; a.n_local = n_local; a.id_offset = id_offset; a.id_stride = id_stride;
+    a.Be = Be; a.k = k; a.num_kb = num_kb; a.kelems_per_kb = per_kb;
+    tc_plan(Be, n_local, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
+    const int64_t need = (int64_t)a.n_splits * Be * kCap * (int64_t)sizeof(uint64_t);
+    HSK_REQUIRE(scratch && scratch_bytes >= need, "hsk_eval_topk_tc: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
+    a.cand = reinterpret_cast<uint64_t*>(scratch);
+    a.out_scores = top_scores; a.out_ids = top_ids; a.status = status;
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, Uq, tf32, kpad, Be, per_kb);
+    if (rc) return rc;
+    rc = make_map(&tmB, Vq, tf32, kpad, n_local, per_kb);
+    if (rc) return rc;
+    const size_t smem = (size_t)(num_kb + TC_STAGES) * TC_TILE_BYTES + 1024;
+    cudaStream_t s = as_stream(stream);
+    dim3 grid((Be + TC_BM - 1) / TC_BM, a.n_splits);
+    cudaError_t e;
+    if (tf32) {
+        e = cudaFuncSetAttribute(eval_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+    } else {
+        e = cudaFuncSetAttribute(eval_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) eval_topk_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+    }
+    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc: smem attribute: %s", cudaGetErrorString(e));
+    rc = check_launch("hsk_eval_topk_tc");
+    if (rc) return rc;
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s);
+    return rc;
+}

@@ -105,4 +105,7 @@ __device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ idx, in
     return lo < end && __ldg(idx + lo) == x;
 }
 
+// hsk_eval.cu: merge of n_lists sorted key lists per row laid out [list][row][kCap] (split plans of the eval kernels)
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s);
+
 }  // namespace hsk

@@ -156,24 +156,51 @@ def log_info_results(metrics_values: dict):
 
 
 class TopKScorer:
-    """hsk_eval_topk for one model: owns the scratch and output buffers for a fixed user-batch size."""
+    """hsk_eval_topk / hsk_eval_topk_tc for one model: owns the scratch, output buffers and (tensor-core modes) the
+    packed operand copies for a fixed user-batch size.  precision: 'fp32' (exact, SIMT FFMA), 'tf32' or 'bf16'
+    (tcgen05).  Call `refresh()` after the model's weights changed (re-packs the item table)."""
 
-    def __init__(self, alg: SGDMatrixFactorization, batch_size: int, k: int):
-        self.alg, self.k = alg, k
+    def __init__(self, alg: SGDMatrixFactorization, batch_size: int, k: int, precision: str = 'fp32'):
+        if precision not in _C.PRECISIONS:
+            raise ValueError(f'eval precision {precision!r} not in {sorted(_C.PRECISIONS)}')
+        self.alg, self.k, self.precision = alg, k, _C.PRECISIONS[precision]
         dev = alg.arena.device
-        self.scratch = torch.empty(_C.eval_topk_scratch_bytes(batch_size, alg.n_items, k), dtype=torch.uint8,
-                                   device=dev)
+        if self.precision == 0:
+            nbytes = _C.eval_topk_scratch_bytes(batch_size, alg.n_items, k)
+        else:
+            nbytes = _C.eval_topk_tc_scratch_bytes(batch_size, alg.n_items, k)
+            kpad = _C.eval_tc_kpad(alg.embedding_dim, self.precision)
+            dt = torch.float32 if self.precision == 1 else torch.bfloat16
+            self.Uq = torch.empty((batch_size, kpad), dtype=dt, device=dev)
+            self.Vq = torch.empty((alg.n_items, kpad), dtype=dt, device=dev)
+            self.refresh()
+        self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.scores = torch.empty((batch_size, k), dtype=torch.float32, device=dev)
         self.ids = torch.empty((batch_size, k), dtype=torch.int32, device=dev)
         self.batch_size = batch_size
+
+    def refresh(self):
+        if self.precision != 0:
+            _C.pack_rows(self.alg.item_embeddings.weight.detach(), self.alg.embedding_dim, self.precision, out=self.Vq)
 
     def __call__(self, u_idxs: torch.Tensor, exclude: Optional[DeviceCSR]):
         B = len(u_idxs)
         assert B <= self.batch_size
         scores, ids = self.scores[:B], self.ids[:B]
-        _C.eval_topk(self.alg._tables(), u_idxs, self.k, scores, ids, self.scratch,
-                     exclude.indptr if exclude is not None else None,
-                     exclude.indices if exclude is not None else None, status=self.alg._status())
+        ex_p = exclude.indptr if exclude is not None else None
+        ex_i = exclude.indices if exclude is not None else None
+        alg = self.alg
+        if self.precision == 0:
+            _C.eval_topk(alg._tables(), u_idxs, self.k, scores, ids, self.scratch, ex_p, ex_i, status=alg._status())
+        else:
+            Uq = self.Uq[:B]
+            _C.pack_rows(alg.user_embeddings.weight.detach(), alg.embedding_dim, self.precision, row_idx=u_idxs, out=Uq,
+                         status=alg._status())
+            _C.eval_topk_tc(Uq, self.Vq, self.precision, u_idxs, alg.n_users, self.k, scores, ids, self.scratch,
+                            Ub=alg.user_bias.weight.detach() if alg.use_user_bias else None,
+                            Ib=alg.item_bias.weight.detach() if alg.use_item_bias else None,
+                            Gb=alg.global_bias.detach() if alg.use_global_bias else None,
+                            excl_indptr=ex_p, excl_indices=ex_i, status=alg._status())
         return scores, ids
 
 
@@ -190,7 +217,8 @@ def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evalu
         labels = device_csr(dataset, 'iteration_matrix', dev)
         exclude = device_csr(dataset, 'exclude_data', dev)
         bs = getattr(eval_loader, 'batch_size', None) or 8192
-        scorer = TopKScorer(alg, min(bs, dataset.n_users), max(evaluator.K_VALUES))
+        scorer = TopKScorer(alg, min(bs, dataset.n_users), max(evaluator.K_VALUES),
+                            getattr(alg, 'eval_precision', 'fp32'))
         starts = range(0, dataset.n_users, bs)
         with torch.no_grad():
             for s in (tqdm(starts) if verbose else starts):

@@ -41,6 +41,7 @@ typedef void* hsk_stream_t; /* cudaStream_t */
 enum { HSK_OK = 0, HSK_ERR_INVALID = -1, HSK_ERR_CUDA = -2, HSK_ERR_UNSUPPORTED = -3 };
 enum { HSK_LOSS_BPR = 0, HSK_LOSS_SAMPLED_SOFTMAX = 1, HSK_LOSS_BCE = 2 }; /* train/rec_losses.py:142-145 */
 enum { HSK_STATUS_BAD_INDEX = 1 };
+enum { HSK_PREC_FP32 = 0, HSK_PREC_TF32 = 1, HSK_PREC_BF16 = 2 }; /* evaluator scoring precision */
 
 /* The embedding tables of one SGDMatrixFactorization (algorithms/sgd_alg.py:127-138).  Nullable: Ub, Ib, Gb. */
 typedef struct hsk_mf_tables {
@@ -127,6 +128,22 @@ HSK_API int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int Be, 
                           const int64_t* excl_indptr /* [n_users + 1] or NULL */, const int32_t* excl_indices,
                           int k /* <= 128 */, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                           int32_t* status, hsk_stream_t stream);
+
+/* ---- the same on the tensor cores (TF32 / BF16 mode): tcgen05.mma with TMEM accumulators, TMA-fed, fused epilogue ------
+ * Operands are packed copies of the tables: Uq = the user batch's rows [Be, kpad], Vq = the item shard [n_local, kpad],
+ * row-major, bf16 (HSK_PREC_BF16) or tf32-rounded fp32 (HSK_PREC_TF32), zero padded to kpad = hsk_eval_tc_kpad(d, prec)
+ * — build them with hsk_pack_rows (row_idx = u_idx gathers the batch; row_idx = NULL packs a whole table).
+ * Biases stay fp32 and are added in the epilogue (Ub is the user-bias TABLE, indexed by u_idx).  Everything else as
+ * hsk_eval_topk.  Supports kpad * element size <= 1024 bytes (d <= 512 bf16, d <= 256 tf32). */
+HSK_API int hsk_eval_tc_kpad(int d, int precision);
+HSK_API int hsk_pack_rows(const float* src, int ld, int d, const int64_t* row_idx /* nullable */, int64_t n_out, int64_t n_src,
+                          void* dst, int kpad, int precision, int32_t* status, hsk_stream_t stream);
+HSK_API int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items, int k);
+HSK_API int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
+                             const float* Gb, const int64_t* u_idx, int Be, int64_t n_users, int64_t n_local,
+                             int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
+                             int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
+                             int32_t* status, hsk_stream_t stream);
 
 /* ---- merge of G per-shard top-k lists (item-sharded evaluation: all-gather, then this) --------------------------
  * scores/ids: [G, rows, k] (id < 0 = empty slot) -> out [rows, k], same ordering rule as hsk_eval_topk. */

