@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
     __shared__ float s_tauf[TM];
     __shared__ uint64_t s_taukey[TM];
     __shared__ int s_cnt[TM];
+    __shared__ int s_checked[TM];   // leading entries of the row's list already tested against the exclusion row
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
             }
         }
         s_uoff[tid] = off; s_ex_lo[tid] = lo; s_ex_hi[tid] = hi; s_ubias[tid] = ub;
-        s_tauf[tid] = -INFINITY; s_taukey[tid] = 0ull; s_cnt[tid] = 0;
+        s_tauf[tid] = -INFINITY; s_taukey[tid] = 0ull; s_cnt[tid] = 0; s_checked[tid] = 0;
     }
     __syncthreads();
 
@@ -167,9 +168,8 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
                 if (a.Ub) s += ub;            // sgd_alg.py:173-178 order: user bias, item bias, global bias
                 if (a.Ib) s += __ldg(a.Ib + n);
                 if (a.Gb) s += gb;
-                if (s >= tauf) {
+                if (s >= tauf) {  // raw candidate; the exclusion mask (eval.py:250-251) is applied when the list is pruned
                     const int64_t gid = a.id_offset + n * a.id_stride;
-                    if (csr_contains(a.excl_indices, s_ex_lo[r], s_ex_hi[r], (int32_t)gid)) s = -INFINITY;  // eval.py:250-251
                     const uint64_t key = make_key(s, (uint32_t)gid);
                     if (key > s_taukey[r]) {
                         const int pos = atomicAdd(&s_cnt[r], 1);
@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
             if (n > prune_at || last) {
                 uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * kCap;
                 uint64_t thr;
-                const int nn = warp_prune_list(list, n, a.k, lane, &thr);
+                const int nn = warp_prune_list_masked(list, n, s_checked[r], a.k, lane, &thr, a.excl_indices, s_ex_lo[r], s_ex_hi[r]);
+                __syncwarp();
                 if (lane == 0) {
                     s_cnt[r] = nn;
+                    s_checked[r] = nn;
                     s_taukey[r] = thr;
                     s_tauf[r] = thr ? key_score(thr) : -INFINITY;
                 }
@@ -220,7 +222,9 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
 
 // ---- merge of G sorted key lists per row (lists[g] at base + (g * rows + row) * stride) ----
 __global__ void __launch_bounds__(256) topk_merge_keys_kernel(const uint64_t* __restrict__ lists, int G, int rows,
-                                                              int stride, int k, float* out_s, int32_t* out_i) {
+                                                              int stride, int k, float* out_s, int32_t* out_i,
+                                                              const float* __restrict__ Ub, const float* __restrict__ Gb,
+                                                              const int64_t* __restrict__ u_idx, int64_t n_users) {
     __shared__ uint64_t buf[8][kCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * 8 + warp;
@@ -236,6 +240,12 @@ __global__ void __launch_bounds__(256) topk_merge_keys_kernel(const uint64_t* __
         __syncwarp();
     }
     write_topk_row(mine, k, out_s + (int64_t)row * k, out_i + (int64_t)row * k, lane);
+    if (Ub || Gb) {  // keys of the tensor-core kernel exclude the per-row user / global bias: add it to the scores now
+        float base = Gb ? Gb[0] : 0.f;
+        if (Ub) { const int64_t u = u_idx[row]; if (!bad_index(u, n_users)) base += Ub[u]; }
+        __syncwarp();
+        for (int e = lane; e < k; e += 32) out_s[(int64_t)row * k + e] += base;
+    }
 }
 
 // ---- merge of G (scores, ids) lists per row: the multi-GPU all-gather merge ----
@@ -401,8 +411,9 @@ static void eval_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_spli
     *n_splits = (nt + tps - 1) / tps;
 }
 
-int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s) {
-    topk_merge_keys_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lists, n_lists, rows, kCap, k, out_scores, out_ids);
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
+                      const float* Ub, const float* Gb, const int64_t* u_idx, int64_t n_users) {
+    topk_merge_keys_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lists, n_lists, rows, kCap, k, out_scores, out_ids, Ub, Gb, u_idx, n_users);
     return check_launch("topk merge");
 }
 
@@ -447,7 +458,7 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int B
     eval_topk_f32_kernel<<<grid, kEvalThreads, 0, s>>>(a);
     int rc = check_launch("hsk_eval_topk");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, nullptr, nullptr, nullptr, 0);
     return rc;
 }
 

@@ -1,16 +1,17 @@
 // Full-rank evaluator, tensor-core mode (TF32 / BF16): scores = U_b · V^T on tcgen05 with TMEM accumulators, fed by TMA,
 // fused with bias add, exclusion mask and running top-k — the [Be, I] score matrix never leaves the SM.
 //
-// Per CTA (192 threads, 1 per SM):
+// Per CTA (320 threads, 1 per SM):
 //   warp 0      TMA producer: the 128-user A tile is loaded ONCE (resident for every item tile); item (B) tiles of
 //               128 rows x 128 bytes of K stream through a 4-stage ring (cp.async.bulk.tensor.2d, SWIZZLE_128B)
 //   warp 1      allocates 256 TMEM columns (2 accumulator stages x 128 fp32 columns) and issues tcgen05.mma
 //               (cta_group::1, M = 128, N = 128, 32 bytes of K per instruction), tcgen05.commit -> mbarriers
-//   warps 2-5   epilogue: thread r of the quarter owns accumulator lane (= user row) r; tcgen05.ld 32 columns at a time,
-//               + item bias, chunk max against the row's running k-th score; only survivors take the slow path
-//               (exclusion-CSR binary search, key build, append to the row's candidate list); lists are cut back by a
-//               warp-cooperative bitonic sort (hsk_topk.cuh).  The accumulator stage is released before the pruning so
-//               the MMA of tile t+1 overlaps the epilogue of tile t.
+//   warps 2-9   epilogue (two warps per scheduler): a thread owns accumulator lane (= user row) r and one 64-column half of
+//               the tile; tcgen05.ld 32 columns at a time, + item bias (128-bit uniform loads), chunk max against the row's
+//               running k-th score; only survivors are keyed and appended to the row's candidate list (shared-memory
+//               counter); the exclusion mask is applied lazily when a list is cut back by the warp-cooperative bitonic
+//               sort (hsk_topk.cuh).  The accumulator stage is released before the pruning so the MMA of tile t+1
+//               overlaps the epilogue of tile t.
 // Operands are packed row-major [rows, kpad] (K-major for both A and B) by hsk_pack_rows: bf16 (round-to-nearest-even)
 // or tf32 (fp32 container, rna-rounded), zero padded to a multiple of 128 bytes of K.
 #include <cuda.h>
@@ -25,7 +26,8 @@ constexpr int TC_BN = 128;        // items per tile (UMMA_N)
 constexpr int TC_KB_BYTES = 128;  // bytes of K per k-block (one 128B swizzle atom)
 constexpr int TC_STAGES = 4;
 constexpr int TC_TILE_BYTES = TC_BN * TC_KB_BYTES;  // 16 KB per operand tile per k-block
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TC_MAX_KB = 8;      // kpad * elem_size <= 1024 bytes -> d <= 512 (bf16) / 256 (tf32)
 
 struct EvalTcArgs {
@@ -97,12 +99,39 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return d;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Epilogue of one 32-column chunk for one row: v[] already holds score' = acc + item bias (the per-row user/global bias
+// does not change the ranking inside a row and is added when the final scores are written).
+__device__ __forceinline__ void tc_scan_chunk(const float (&v)[32], float tau, uint64_t taukey, int64_t gid0, int64_t id_stride,
+                                              int* s_cnt_row, uint64_t* list) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        if (v[e] >= tau) {
+            const uint64_t key = make_key(v[e], (uint32_t)(gid0 + e * id_stride));
+            if (key > taukey) {
+                const int pos = atomicAdd(s_cnt_row, 1);
+                list[pos] = key;
+            }
+        }
+    }
+}
+
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_a, bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t s_tmem_base;
+    // per-row top-k state shared by the two epilogue warps of a row (column halves)
+    __shared__ float s_tau[TC_BM];
+    __shared__ uint64_t s_taukey[TC_BM];
+    __shared__ int s_cnt[TC_BM], s_checked[TC_BM];
+    __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
+    __shared__ float s_base[TC_BM];
+    __shared__ int s_rowok[TC_BM];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
@@ -119,12 +148,32 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_a, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], TC_EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == 1) {  // TMEM: 2 accumulator stages x 128 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "n"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_BM) {  // per-row state
+        const int r = threadIdx.x - 64;
+        const int row = m0 + r;
+        int ok = 0;
+        int64_t lo = 0, hi = 0;
+        float base = 0.f;
+        if (row < a.Be) {
+            const int64_t u = a.u_idx[row];
+            if (bad_index(u, a.n_users)) {
+                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
+            } else {
+                ok = 1;
+                if (a.excl_indptr) { lo = a.excl_indptr[u]; hi = a.excl_indptr[u + 1]; }
+                if (a.Ub) base += a.Ub[u];
+            }
+        }
+        if (a.Gb) base += a.Gb[0];
+        s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
+        s_tau[r] = -INFINITY; s_taukey[r] = 0ull; s_cnt[r] = 0; s_checked[r] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -180,100 +229,97 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int ew = warp - 2;
         const int quarter = warp & 3;
+        const int half = ew >> 2;
         const int r = quarter * 32 + lane;   // row within the tile == TMEM lane
-        const int row = m0 + r;
-        bool row_ok = row < a.Be;
-        int64_t ex_lo = 0, ex_hi = 0;
-        float ub = 0.f;
-        if (row_ok) {
-            const int64_t u = a.u_idx[row];
-            if (bad_index(u, a.n_users)) {
-                row_ok = false;
-                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
-            } else {
-                if (a.excl_indptr) { ex_lo = a.excl_indptr[u]; ex_hi = a.excl_indptr[u + 1]; }
-                if (a.Ub) ub = a.Ub[u];
-            }
-        }
-        const float base_bias = ub + (a.Gb ? a.Gb[0] : 0.f);
-        uint64_t* list = a.cand + ((int64_t)split * a.Be + (row < a.Be ? row : 0)) * kCap;
-        int cnt = 0;
-        float tauf = -INFINITY;
-        uint64_t taukey = 0ull;
+        const bool row_ok = s_rowok[r] != 0;
+        uint64_t* list = a.cand + ((int64_t)split * a.Be + min(m0 + r, a.Be - 1)) * kCap;
         const int prune_at = kCap - TC_BN;
+        const bool ib_vec = a.Ib != nullptr && ((reinterpret_cast<uintptr_t>(a.Ib) & 15) == 0);
 
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
             const int64_t n0 = (int64_t)(t_begin + t) * TC_BN;
             const int ncols = (int)min((int64_t)TC_BN, a.n_local - n0);
+            const float tau = s_tau[r];
+            const uint64_t taukey = s_taukey[r];
             mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN;
 #pragma unroll 1
-            for (int c = 0; c < TC_BN; c += 32) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 64 + cc * 32;
                 float v[32];
                 tc_ld32(taddr + (uint32_t)c, v);
                 if (c >= ncols) continue;
-                float mx = -INFINITY;
+                const int64_t gid0 = a.id_offset + (n0 + c) * a.id_stride;
+                if (c + 32 <= ncols) {
+                    float mx = -INFINITY;
+                    if (ib_vec) {
+                        const float4* ibp = reinterpret_cast<const float4*>(a.Ib + n0 + c);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    float s = v[e] + base_bias;
-                    if (a.Ib) s += (c + e < ncols) ? __ldg(a.Ib + n0 + c + e) : 0.f;
-                    v[e] = s;
-                    mx = fmaxf(mx, (c + e < ncols) ? s : -INFINITY);
-                }
-                if (row_ok && mx >= tauf) {
-#pragma unroll 1
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = __ldg(ibp + q);
+                            v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                        }
+                    } else if (a.Ib) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] += __ldg(a.Ib + n0 + c + e);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(v[e], v[e + 1]));
+                    if (row_ok && mx >= tau) tc_scan_chunk(v, tau, taukey, gid0, a.id_stride, &s_cnt[r], list);
+                } else {  // the ragged last tile: out-of-range columns never become candidates
+#pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        if (c + e >= ncols) break;
-                        float s = v[e];
-                        if (s >= tauf) {
-                            const int64_t gid = a.id_offset + (n0 + c + e) * a.id_stride;
-                            if (csr_contains(a.excl_indices, ex_lo, ex_hi, (int32_t)gid)) s = -INFINITY;
-                            const uint64_t key = make_key(s, (uint32_t)gid);
-                            if (key > taukey) list[cnt++] = key;
+                        const bool in = c + e < ncols;
+                        v[e] = in ? v[e] + (a.Ib ? __ldg(a.Ib + n0 + c + e) : 0.f) : __int_as_float(0x7fc00000);  // NaN fails >=
+                    }
+                    if (row_ok) tc_scan_chunk(v, tau, taukey, gid0, a.id_stride, &s_cnt[r], list);
+                }
+            }
+            // release the accumulator stage (the MMA of the next tile proceeds), then prune cooperatively
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            named_bar_sync(1, TC_EPI_WARPS * 32);
+            const bool last = (t + 1 == n_my_tiles);
+            for (int rr = ew; rr < TC_BM; rr += TC_EPI_WARPS) {
+                if (!s_rowok[rr]) continue;
+                const int n_r = s_cnt[rr];
+                if (n_r > prune_at || last) {
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * kCap;
+                    uint64_t thr;
+                    const int nn = warp_prune_list_masked(lp, n_r, s_checked[rr], a.k, lane, &thr, a.excl_indices, s_exlo[rr], s_exhi[rr]);
+                    __syncwarp();
+                    if (lane == 0) {
+                        s_cnt[rr] = nn; s_checked[rr] = nn; s_taukey[rr] = thr;
+                        s_tau[rr] = thr ? key_score(thr) : -INFINITY;
+                    }
+                    if (last && a.n_splits == 1) {
+                        const int64_t orow = (int64_t)(m0 + rr) * a.k;
+                        const float base = s_base[rr];
+                        for (int e = lane; e < a.k; e += 32) {
+                            const uint64_t key = lp[e];
+                            a.out_scores[orow + e] = key ? key_score(key) + base : -INFINITY;
+                            a.out_ids[orow + e] = key_id(key);
                         }
                     }
                 }
             }
-            // release the accumulator stage, then prune (the MMA of the next tile runs meanwhile)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[as]);
-            const bool last = (t + 1 == n_my_tiles);
-            unsigned need = __ballot_sync(kFull, row_ok && (cnt > prune_at || last));
-            while (need) {
-                const int rr = __ffs(need) - 1;
-                need &= need - 1;
-                const int n_r = __shfl_sync(kFull, cnt, rr);
-                const unsigned long long lp = __shfl_sync(kFull, (unsigned long long)list, rr);
-                uint64_t thr;
-                __syncwarp();
-                const int nn = warp_prune_list(reinterpret_cast<uint64_t*>(lp), n_r, a.k, lane, &thr);
-                if (lane == rr) {
-                    cnt = nn;
-                    taukey = thr;
-                    tauf = thr ? key_score(thr) : -INFINITY;
-                }
-                if (last && a.n_splits == 1) {
-                    __syncwarp();
-                    const int64_t orow = (int64_t)(m0 + quarter * 32 + rr) * a.k;
-                    for (int e = lane; e < a.k; e += 32) {
-                        const uint64_t key = reinterpret_cast<uint64_t*>(lp)[e];
-                        a.out_scores[orow + e] = key ? key_score(key) : -INFINITY;
-                        a.out_ids[orow + e] = key_id(key);
-                    }
-                }
-            }
+            named_bar_sync(1, TC_EPI_WARPS * 32);
         }
-        // rows with a bad user index (or an empty split): empty lists / -1 ids
-        if (row < a.Be && !row_ok) {
-            if (a.n_splits == 1) {
-                for (int e = 0; e < a.k; ++e) { a.out_scores[(int64_t)row * a.k + e] = -INFINITY; a.out_ids[(int64_t)row * a.k + e] = -1; }
-            } else {
-                for (int e = 0; e < a.k; ++e) list[e] = 0ull;
+        // rows with a bad user index: empty lists / -1 ids
+        for (int rr = ew; rr < TC_BM; rr += TC_EPI_WARPS) {
+            if (m0 + rr < a.Be && !s_rowok[rr]) {
+                if (a.n_splits == 1) {
+                    for (int e = lane; e < a.k; e += 32) { a.out_scores[(int64_t)(m0 + rr) * a.k + e] = -INFINITY; a.out_ids[(int64_t)(m0 + rr) * a.k + e] = -1; }
+                } else {
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * kCap;
+                    for (int e = lane; e < a.k; e += 32) lp[e] = 0ull;
+                }
             }
         }
     }
@@ -344,7 +390,7 @@ static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split,
     const int nt = (int)((n_local + TC_BN - 1) / TC_BN);
     const int want = sm_count();
     int splits = 1;
-    if (row_tiles < want) splits = (want + row_tiles - 1) / row_tiles;
+    if (row_tiles * 4 < want * 3) splits = (want + row_tiles - 1) / row_tiles;   // >= 75 % of the SMs busy: no split
     const int max_splits = nt / 8 > 0 ? nt / 8 : 1;   // at least 8 item tiles per split
     if (splits > max_splits) splits = max_splits;
     if (splits > 64) splits = 64;
@@ -434,6 +480,6 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc: smem attribute: %s", cudaGetErrorString(e));
     rc = check_launch("hsk_eval_topk_tc");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, Ub, Gb, u_idx, n_users);
     return rc;
 }

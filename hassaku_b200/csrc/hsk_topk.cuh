@@ -76,6 +76,16 @@ __device__ __forceinline__ uint64_t warp_list_at(const uint64_t (&key)[kKeysPerL
     return __shfl_sync(kFull, v, pos & 31);
 }
 
+// membership test in a sorted int32 range [lo, hi) (one CSR row): lower_bound + compare
+__device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int32_t x) {
+    const int64_t end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(idx + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo < end && __ldg(idx + lo) == x;
+}
+
 // Cut a row's candidate list (n <= kCap keys at `list`, global or shared memory) back to its best k, sorted.
 // Returns the new length min(n, k); *thr_key receives the k-th key (0 while the list holds fewer than k).
 __device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int lane, uint64_t* thr_key) {
@@ -95,17 +105,40 @@ __device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int
     return n < k ? n : k;
 }
 
-// membership test in a sorted int32 range [lo, hi) (one CSR row): lower_bound + compare
-__device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int32_t x) {
-    const int64_t end = hi;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(idx + mid) < x) lo = mid + 1; else hi = mid;
+// Same, applying the exclusion mask lazily: entries [n_checked, n) have not been tested against the user's exclusion row
+// yet (the scoring epilogues append raw candidates so that their hot loop has no dependent global loads); an excluded
+// item is re-keyed to score -inf (eval/eval.py:250-251) before the sort.  The 8 binary searches of a lane are
+// independent, so their latencies overlap.
+__device__ __forceinline__ int warp_prune_list_masked(uint64_t* list, int n, int n_checked, int k, int lane, uint64_t* thr_key,
+                                                      const int32_t* __restrict__ excl, int64_t lo, int64_t hi) {
+    uint64_t key[kKeysPerLane];
+#pragma unroll
+    for (int r = 0; r < kKeysPerLane; ++r) {
+        const int e = r * 32 + lane;
+        key[r] = (e < n) ? list[e] : 0ull;
     }
-    return lo < end && __ldg(idx + lo) == x;
+    if (hi > lo) {
+#pragma unroll
+        for (int r = 0; r < kKeysPerLane; ++r) {
+            const int e = r * 32 + lane;
+            if (e >= n_checked && e < n) {
+                const int32_t id = key_id(key[r]);
+                if (csr_contains(excl, lo, hi, id)) key[r] = make_key(-INFINITY, (uint32_t)id);
+            }
+        }
+    }
+    warp_sort_desc(key, lane);
+#pragma unroll
+    for (int r = 0; r < kKeysPerLane; ++r) {
+        const int e = r * 32 + lane;
+        if (e < k) list[e] = key[r];
+    }
+    *thr_key = (n >= k) ? warp_list_at(key, k - 1) : 0ull;
+    return n < k ? n : k;
 }
 
 // hsk_eval.cu: merge of n_lists sorted key lists per row laid out [list][row][kCap] (split plans of the eval kernels)
-int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s);
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
+                      const float* Ub, const float* Gb, const int64_t* u_idx, int64_t n_users);
 
 }  // namespace hsk

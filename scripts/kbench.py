@@ -63,9 +63,47 @@ def train(args):
     print(f'adamw        flushed med {med*1e3:8.1f} us best {best*1e3:8.1f} us -> {ab["adamw"]/med/1e6:8.0f} GB/s (28 B/param)')
 
 
+def evalk(args):
+    """Evaluator scoring kernel alone: one user batch against the whole item table."""
+    import math
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
+    from scipy import sparse as sp
+    U, I, d, B = args.users, args.items, args.dim, args.batch
+    torch.manual_seed(0)
+    model = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn_like(p) * (1.0 / math.sqrt(d) if p.shape[-1] == d else 0.05))
+    model.to('cuda')
+    rng = np.random.RandomState(1)
+    rows = np.repeat(np.arange(U), args.excl)
+    ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+    ex.sum_duplicates(); ex.sort_indices()
+    ex = DeviceCSR(ex, 'cuda')
+    users = torch.arange(B, device='cuda') % U
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for prec in args.variants.split(','):
+        sc = TopKScorer(model, B, 100, prec)
+        fn = lambda: sc(users, ex)
+        for _ in range(2):
+            fn()
+        med, best = time_kernel(fn, args.iters, flush)
+        fl = 2.0 * B * I * d
+        print(f'eval[{prec:4s}] U_b={B} I={I} d={d}: med {med:9.3f} ms best {best:9.3f} ms -> {B/med*1e3:12.0f} users/s '
+              f'{fl/med/1e9:8.1f} TFLOP/s')
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['train'])
+    ap.add_argument('what', choices=['train', 'eval'])
     ap.add_argument('--workload', default='cfg2')
     ap.add_argument('--variants', default='regs,tma')
-    train(ap.parse_args())
+    ap.add_argument('--users', type=int, default=6040)
+    ap.add_argument('--items', type=int, default=3706)
+    ap.add_argument('--dim', type=int, default=402)
+    ap.add_argument('--batch', type=int, default=6040)
+    ap.add_argument('--excl', type=int, default=80)
+    ap.add_argument('--iters', type=int, default=10)
+    a = ap.parse_args()
+    train(a) if a.what == 'train' else evalk(a)
