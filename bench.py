@@ -207,9 +207,115 @@ def cpu_baseline(wl, data, us, its, budget_s=20.0):
                       f'{os.cpu_count()} cpus), {dt:.1f} s'}
 
 
+def run_ours_sharded(args, wl):
+    """N > 1: the item-/user-sharded step (hassaku_b200/sharded.py) with a per-GPU batch of `train_batch_size` samples
+    (weak scaling: global batch = N x 8192), NCCL all-to-all for the row / gradient exchanges."""
+    import torch
+    import torch.distributed as dist
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.data.synthetic import make_named
+    from hassaku_b200.eval.eval import FullEvaluator
+    from hassaku_b200.sharded import ShardedMF
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist.init_process_group('nccl', device_id=dev)
+    name, d, B, N, loss, lr, wd = wl
+    data = make_named(name)
+    U, I = data.n_users, data.n_items
+    K, W = args.steps, max(args.warmup, 0)
+    torch.manual_seed(64)
+    full = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+    smf = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+    smf.load_full_state_dict(full.state_dict())
+    del full
+    shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
+    # local batches: B samples whose user this rank owns
+    import scipy.sparse as sp
+    tr = data.train.tocsr()
+    mine = sp.csr_matrix(tr[np.arange(rank, U, world)])
+    sub = type('D', (), {})()
+    sub.train, sub.n_items = sp.csr_matrix((mine.data, mine.indices, mine.indptr), shape=(mine.shape[0], I)), I
+    us, its = make_batches(sub, B, N, 8, seed=64 + rank)
+    us = [u * world + rank for u in us]                              # local row -> global user id
+    u_dev = [torch.from_numpy(x).to(dev) for x in us]
+    i_dev = [torch.from_numpy(x).to(dev) for x in its]
+    Bg = B * world
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(W):
+        smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        a.record()
+        for s in range(K):
+            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd)
+        b.record()
+        barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    last_loss = smf.pop_loss() / K
+    # e2e: host batches
+    u_pin = [torch.from_numpy(x).pin_memory() for x in us]
+    i_pin = [torch.from_numpy(x).pin_memory() for x in its]
+    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a2.record()
+    for s in range(K):
+        smf.step(u_pin[s % 8].to(dev, non_blocking=True), i_pin[s % 8].to(dev, non_blocking=True), Bg, loss, shift, lr, wd)
+    loss_host = smf.pop_loss()
+    b2.record()
+    barrier()
+    t2 = torch.tensor([a2.elapsed_time(b2)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+    # sharded full-rank evaluation (first sweep warms NCCL's all-gather / all-to-all channels up)
+    u2g = torch.from_numpy(data.user_group).float() if data.user_group is not None else None
+    smf.evaluate(data.val, data.train, FullEvaluator(True, data.n_user_groups, u2g), batch_size=8192)
+    barrier()
+    ev_t0 = time.perf_counter()
+    for _ in range(3):
+        res = smf.evaluate(data.val, data.train, FullEvaluator(True, data.n_user_groups, u2g), batch_size=8192)
+    torch.cuda.synchronize()
+    eval_ms = (time.perf_counter() - ev_t0) * 1e3 / 3
+    if rank == 0:
+        ab = algorithmic_bytes(U, I, d, B, N)
+        peak, peak_src = measured_peaks()
+        triples = Bg * N
+        cfg = workload_config(args.workload, wl, U, I)
+        cfg.update({'parallelism': f'item+user row-sharded x{world}, NCCL all-to-all', 'global_batch': Bg,
+                    'l2': 'not flushed (back to back); tables are L2-resident'})
+        line = {'metric': 'BPR-MF train triples/s', 'value': triples * K / (ms * 1e-3), 'unit': 'triples/s', 'n_gpus': world,
+                'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+                'e2e': {'value': triples * K / (ms_e2e * 1e-3), 'unit': 'triples/s',
+                        'h2d_bytes_per_step': int(us[0].nbytes + its[0].nbytes) * world, 'd2h_bytes_per_step': 8,
+                        'ms_per_step': ms_e2e / K},
+                'gpu_launches': 4 * K * world,
+                'roofline': {'kernel': 'hsk_mf_train_fused_n', 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s',
+                             'frac': None, 'traffic': None, 'peak_source': peak_src,
+                             'step': {'algorithmic_bytes_per_gpu': 2 * ab['A'] + 28 * ab['P'] // world,
+                                      'note': 'per-kernel roofline is reported by the N = 1 run'}},
+                'clocks': clk.summary(),
+                'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
+                         'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U},
+                'final_loss': last_loss}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        return run_ours_sharded(args, wl)
     from hassaku_b200 import _C
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
     from hassaku_b200.data.dataset import FullEvalDataset

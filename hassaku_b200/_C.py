@@ -44,14 +44,17 @@ def _declare(lib):
         'hsk_rec_loss': (i32, [vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
         'hsk_mf_scatter_grads': (i32, [T, T, vp, vp, vp, i32, i32, vp, vp]),
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+        'hsk_mf_train_fused_n': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp]),
+        'hsk_gather_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
+        'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
         'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
         'hsk_eval_topk_scratch_bytes': (i64, [i32, i64, i32]),
-        'hsk_eval_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+        'hsk_eval_topk': (i32, [T, vp, vp, i64, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
         'hsk_eval_tc_kpad': (i32, [i32, i32]),
         'hsk_pack_rows': (i32, [vp, i32, i32, vp, i64, i64, vp, i32, i32, vp, vp]),
         'hsk_eval_topk_tc_scratch_bytes': (i64, [i32, i64, i32]),
-        'hsk_eval_topk_tc': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp,
+        'hsk_eval_topk_tc': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp,
                                    i64, vp, vp]),
         'hsk_topk_merge': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         'hsk_topk_dense': (i32, [vp, i32, i64, i64, i32, vp, vp, vp]),
@@ -156,6 +159,29 @@ def mf_train_fused(tables: MfTables, grads: MfTables, u_idx, i_idx, loss_kind: i
                                     _ptr(status), _stream()), 'hsk_mf_train_fused')
 
 
+def mf_train_fused_n(tables: MfTables, grads: MfTables, u_idx, i_idx, B_global: int, loss_kind: int, neg_shift: float,
+                     loss_accum, status=None):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx'); _req(loss_accum, torch.float64, 'loss_accum')
+    B, N1 = i_idx.shape
+    _check(lib().hsk_mf_train_fused_n(C.byref(tables), C.byref(grads), u_idx.data_ptr(), i_idx.data_ptr(), B, N1, B_global,
+                                      loss_kind, neg_shift, loss_accum.data_ptr(), None, None, _ptr(status), _stream()),
+           'hsk_mf_train_fused_n')
+
+
+def gather_rows(src, idx, dst, status=None):
+    """dst[r, :] = src[idx[r], :]; src/dst 2-D fp32 with the same (padded) leading dimension."""
+    _req(idx, torch.int64, 'idx')
+    _check(lib().hsk_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), idx.numel(), src.shape[0], dst.data_ptr(),
+                                 _ptr(status), _stream()), 'hsk_gather_rows')
+
+
+def scatter_add_rows(dst, idx, src, status=None):
+    """dst[idx[r], :] += src[r, :]."""
+    _req(idx, torch.int64, 'idx')
+    _check(lib().hsk_scatter_add_rows(dst.data_ptr(), dst.stride(0), idx.data_ptr(), idx.numel(), dst.shape[0],
+                                      src.data_ptr(), _ptr(status), _stream()), 'hsk_scatter_add_rows')
+
+
 def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arith: int = 0, adam_l2: bool = False,
                 zero_grad: bool = True):
     for n, t in (('p', p), ('m', m), ('v', v), ('g', g)):
@@ -187,12 +213,15 @@ def eval_topk_scratch_bytes(Be: int, n_local_items: int, k: int) -> int:
 
 
 def eval_topk(tables: MfTables, u_idx, k: int, top_scores, top_ids, scratch, excl_indptr=None, excl_indices=None,
-              id_offset: int = 0, id_stride: int = 1, status=None):
+              id_offset: int = 0, id_stride: int = 1, status=None, u_rows=None, n_users_global: int = 0):
     _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
     if excl_indptr is not None:
         _req(excl_indptr, torch.int64, 'excl_indptr'); _req(excl_indices, torch.int32, 'excl_indices')
     Be = u_idx.numel()
-    _check(lib().hsk_eval_topk(C.byref(tables), u_idx.data_ptr(), Be, id_offset, id_stride, _ptr(excl_indptr),
+    if u_rows is not None:
+        _req(u_rows, torch.int64, 'u_rows')
+    _check(lib().hsk_eval_topk(C.byref(tables), u_idx.data_ptr(), _ptr(u_rows), n_users_global, Be, id_offset, id_stride,
+                               _ptr(excl_indptr),
                                _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(), scratch.data_ptr(),
                                scratch.numel() * scratch.element_size(), _ptr(status), _stream()), 'hsk_eval_topk')
 
@@ -222,11 +251,13 @@ def eval_topk_tc_scratch_bytes(Be: int, n_local_items: int, k: int) -> int:
 
 
 def eval_topk_tc(Uq, Vq, precision: int, u_idx, n_users: int, k: int, top_scores, top_ids, scratch, Ub=None, Ib=None,
-                 Gb=None, excl_indptr=None, excl_indices=None, id_offset: int = 0, id_stride: int = 1, status=None):
+                 Gb=None, excl_indptr=None, excl_indices=None, id_offset: int = 0, id_stride: int = 1, status=None,
+                 u_rows=None):
     _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
     Be, kpad = Uq.shape
     _check(lib().hsk_eval_topk_tc(Uq.data_ptr(), Vq.data_ptr(), kpad, precision, _ptr(Ub), _ptr(Ib), _ptr(Gb),
-                                  u_idx.data_ptr(), Be, n_users, Vq.shape[0], id_offset, id_stride, _ptr(excl_indptr),
+                                  u_idx.data_ptr(), _ptr(u_rows), Be, n_users, Vq.shape[0], id_offset, id_stride,
+                                  _ptr(excl_indptr),
                                   _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(), scratch.data_ptr(),
                                   scratch.numel() * scratch.element_size(), _ptr(status), _stream()), 'hsk_eval_topk_tc')
 

@@ -28,6 +28,8 @@ struct EvalArgs {
     const float* __restrict__ Ib;   // local rows
     const float* __restrict__ Gb;
     const int64_t* __restrict__ u_idx;
+    const int64_t* __restrict__ u_rows;   // row of Uw / Ub per batch entry (null: = u_idx)
+    int64_t n_urows;
     const int64_t* __restrict__ excl_indptr;
     const int32_t* __restrict__ excl_indices;
     int64_t n_users;
@@ -81,12 +83,13 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
         float ub = 0.f;
         if (row < a.Be) {
             const int64_t u = a.u_idx[row];
-            if (bad_index(u, a.n_users)) {
+            const int64_t ur = a.u_rows ? a.u_rows[row] : u;
+            if (bad_index(u, a.n_users) || bad_index(ur, a.n_urows)) {
                 if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
             } else {
-                off = u * a.ld;
+                off = ur * a.ld;
                 if (a.excl_indptr) { lo = a.excl_indptr[u]; hi = a.excl_indptr[u + 1]; }
-                if (a.Ub) ub = a.Ub[u];
+                if (a.Ub) ub = a.Ub[ur];
             }
         }
         s_uoff[tid] = off; s_ex_lo[tid] = lo; s_ex_hi[tid] = hi; s_ubias[tid] = ub;
@@ -428,7 +431,8 @@ extern "C" int64_t hsk_eval_topk_scratch_bytes(int Be, int64_t n_local_items, in
     return (int64_t)ns * (Be > 0 ? Be : 1) * kCap * (int64_t)sizeof(uint64_t);
 }
 
-extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int Be, int64_t id_offset, int64_t id_stride,
+extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const int64_t* u_rows, int64_t n_users_global,
+                             int Be, int64_t id_offset, int64_t id_stride,
                              const int64_t* excl_indptr, const int32_t* excl_indices, int k, float* top_scores,
                              int32_t* top_ids, void* scratch, int64_t scratch_bytes, int32_t* status,
                              hsk_stream_t stream) {
@@ -444,8 +448,8 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int B
     EvalArgs a;
     memset(&a, 0, sizeof(a));
     a.Uw = t->Uw; a.Vw = t->Vw; a.Ub = t->Ub; a.Ib = t->Ib; a.Gb = t->Gb;
-    a.u_idx = u_idx; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
-    a.n_users = t->n_users; a.n_local = t->n_items; a.id_offset = id_offset; a.id_stride = id_stride;
+    a.u_idx = u_idx; a.u_rows = u_rows; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
+    a.n_users = u_rows ? n_users_global : t->n_users; a.n_urows = t->n_users; a.n_local = t->n_items; a.id_offset = id_offset; a.id_stride = id_stride;
     a.ld = t->ld; a.Be = Be; a.k = k;
     eval_plan(Be, t->n_items, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
     const int64_t need = (int64_t)a.n_splits * Be * kCap * (int64_t)sizeof(uint64_t);

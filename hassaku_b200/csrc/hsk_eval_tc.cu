@@ -35,6 +35,7 @@ struct EvalTcArgs {
     const float* __restrict__ Ib;   // local item bias or null
     const float* __restrict__ Gb;
     const int64_t* __restrict__ u_idx;
+    const int64_t* __restrict__ u_rows;   // row of the Ub table per batch entry (null: = u_idx)
     const int64_t* __restrict__ excl_indptr;
     const int32_t* __restrict__ excl_indices;
     int64_t n_users, n_local, id_offset, id_stride;
@@ -168,7 +169,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else {
                 ok = 1;
                 if (a.excl_indptr) { lo = a.excl_indptr[u]; hi = a.excl_indptr[u + 1]; }
-                if (a.Ub) base += a.Ub[u];
+                if (a.Ub) base += a.Ub[a.u_rows ? a.u_rows[row] : u];
             }
         }
         if (a.Gb) base += a.Gb[0];
@@ -434,7 +435,7 @@ extern "C" int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items,
 }
 
 extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
-                                const float* Gb, const int64_t* u_idx, int Be, int64_t n_users, int64_t n_local,
+                                const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users, int64_t n_local,
                                 int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
                                 int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                                 int32_t* status, hsk_stream_t stream) {
@@ -453,7 +454,7 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (Be == 0) return HSK_OK;
     EvalTcArgs a;
     memset(&a, 0, sizeof(a));
-    a.Ub = Ub; a.Ib = Ib; a.Gb = Gb; a.u_idx = u_idx; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
+    a.Ub = Ub; a.Ib = Ib; a.Gb = Gb; a.u_idx = u_idx; a.u_rows = u_rows; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
     a.n_users = n_users; a.n_local = n_local; a.id_offset = id_offset; a.id_stride = id_stride;
     a.Be = Be; a.k = k; a.num_kb = num_kb; a.kelems_per_kb = per_kb;
     tc_plan(Be, n_local, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
@@ -480,6 +481,6 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc: smem attribute: %s", cudaGetErrorString(e));
     rc = check_launch("hsk_eval_topk_tc");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, Ub, Gb, u_idx, n_users);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
     return rc;
 }

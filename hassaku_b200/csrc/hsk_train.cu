@@ -467,7 +467,16 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
                                   const int64_t* i_idx, int B, int N1, int loss_kind, float neg_shift,
                                   double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,
                                   hsk_stream_t stream) {
+    return hsk_mf_train_fused_n(t, g, u_idx, i_idx, B, N1, B, loss_kind, neg_shift, loss_accum, scores_out, dscores_out,
+                                status, stream);
+}
+
+extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx,
+                                    const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind, float neg_shift,
+                                    double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,
+                                    hsk_stream_t stream) {
     TrainArgs a;
+    HSK_REQUIRE(B_global >= B, "hsk_mf_train_fused_n: the global batch cannot be smaller than the local one");
     HSK_REQUIRE(g, "hsk_mf_train_fused: gradient tables are null");
     int rc = fill_args(a, t, g, u_idx, i_idx, B, N1, "hsk_mf_train_fused");
     if (rc) return rc;
@@ -490,7 +499,7 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
     const char* nored = getenv("HSK_DEBUG_NORED");
     a.debug_flags = (nored && nored[0] == '1') ? 1 : 0;
     if (loss_kind == HSK_LOSS_BPR) {
-        a.inv_count = 1.0 / ((double)B * (double)(N1 - 1));
+        a.inv_count = 1.0 / ((double)B_global * (double)(N1 - 1));
         a.j_per_cta = pick_j_per_cta(B, N1 - 1, true);
         if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 - 1 + a.j_per_cta - 1) / a.j_per_cta);
@@ -501,14 +510,14 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
         if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BPR><<<grid, threads, 0, s>>>(a)));
     } else if (loss_kind == HSK_LOSS_BCE) {
-        a.inv_count = 1.0 / ((double)B * (double)N1);
+        a.inv_count = 1.0 / ((double)B_global * (double)N1);
         a.j_per_cta = pick_j_per_cta(B, N1, true);
         if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 + a.j_per_cta - 1) / a.j_per_cta);
         if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BCE><<<grid, threads, 0, s>>>(a)));
     } else {
-        a.inv_count = 1.0 / (double)B;
+        a.inv_count = 1.0 / (double)B_global;
         a.j_per_cta = N1;
         dim3 grid(B, 1);
         const size_t smem = sizeof(float) * (size_t)N1;
@@ -516,4 +525,65 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_SAMPLED_SOFTMAX><<<grid, threads, smem, s>>>(a)));
     }
     return check_launch("hsk_mf_train_fused");
+}
+
+// ---- row gather / scatter-add used by the item-sharded step (hassaku_b200/sharded.py): the rows a peer asked for are
+// packed contiguously before the all-to-all, and the row gradients received back are added into the owner's table ----
+namespace hsk {
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int ld, const int64_t* __restrict__ idx,
+                                                          int64_t n, int64_t n_src, float* __restrict__ dst, int32_t* status) {
+    const int nvec = ld >> 2;
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        const int64_t s = idx[r];
+        if (bad_index(s, n_src)) {
+            if (lane == 0 && status) atomicOr(status, HSK_STATUS_BAD_INDEX);
+            continue;
+        }
+        const float4* sp = reinterpret_cast<const float4*>(src + s * ld);
+        float4* dp = reinterpret_cast<float4*>(dst + r * ld);
+        for (int k = lane; k < nvec; k += 32) dp[k] = __ldg(sp + k);
+    }
+}
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict__ dst, int ld, const int64_t* __restrict__ idx,
+                                                               int64_t n, int64_t n_dst, const float* __restrict__ src, int32_t* status) {
+    const int nvec = ld >> 2;
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (int64_t)gridDim.x * 8) {
+        const int64_t d = idx[r];
+        if (bad_index(d, n_dst)) {
+            if (lane == 0 && status) atomicOr(status, HSK_STATUS_BAD_INDEX);
+            continue;
+        }
+        const float4* sp = reinterpret_cast<const float4*>(src + r * ld);
+        float4* dp = reinterpret_cast<float4*>(dst + d * ld);
+        for (int k = lane; k < nvec; k += 32) atomicAdd(dp + k, sp[k]);
+    }
+}
+}  // namespace hsk
+
+static int rows_args_ok(const float* a, const float* b, int ld, const int64_t* idx, const char* who) {
+    HSK_REQUIRE(a && b && idx, "%s: null pointer", who);
+    HSK_REQUIRE(ld >= 4 && (ld % 4) == 0 && aligned16(a) && aligned16(b), "%s: rows must be 16-byte aligned with ld %% 4 == 0", who);
+    return HSK_OK;
+}
+
+extern "C" int hsk_gather_rows(const float* src, int ld, const int64_t* idx, int64_t n, int64_t n_src, float* dst,
+                               int32_t* status, hsk_stream_t stream) {
+    int rc = rows_args_ok(src, dst, ld, idx, "hsk_gather_rows");
+    if (rc) return rc;
+    if (n <= 0) return HSK_OK;
+    int64_t blocks = (n + 7) / 8, cap = (int64_t)sm_count() * 16;
+    gather_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, ld, idx, n, n_src, dst, status);
+    return check_launch("hsk_gather_rows");
+}
+
+extern "C" int hsk_scatter_add_rows(float* dst, int ld, const int64_t* idx, int64_t n, int64_t n_dst, const float* src,
+                                    int32_t* status, hsk_stream_t stream) {
+    int rc = rows_args_ok(dst, src, ld, idx, "hsk_scatter_add_rows");
+    if (rc) return rc;
+    if (n <= 0) return HSK_OK;
+    int64_t blocks = (n + 7) / 8, cap = (int64_t)sm_count() * 16;
+    scatter_add_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(dst, ld, idx, n, n_dst, src, status);
+    return check_launch("hsk_scatter_add_rows");
 }

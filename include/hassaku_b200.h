@@ -92,6 +92,20 @@ HSK_API int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g, c
                        int B, int N1, int loss_kind, float neg_shift, double* loss_accum,
                        float* scores_out, float* dscores_out, int32_t* status, hsk_stream_t stream);
 
+/* Item-sharded variant: this rank holds B of the B_global samples of the step; the loss / gradient
+ * normalisers stay GLOBAL (1 / (B_global N) for bpr, 1 / B_global for sampled-softmax, 1 / (B_global N1) for bce) so the
+ * sum over ranks equals the single-GPU step on the whole batch.  `t->Vw` is then a compact table of fetched item rows. */
+HSK_API int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx, const int64_t* i_idx,
+                                 int B, int N1, int64_t B_global, int loss_kind, float neg_shift, double* loss_accum,
+                                 float* scores_out, float* dscores_out, int32_t* status, hsk_stream_t stream);
+
+/* Row gather / scatter-add for the all-to-all exchanges of the item-sharded step: dst[r, :] = src[idx[r], :] and
+ * dst[idx[r], :] += src[r, :] (128-bit vector reductions), rows of ld fp32 (ld % 4 == 0, 16-byte aligned). */
+HSK_API int hsk_gather_rows(const float* src, int ld, const int64_t* idx, int64_t n, int64_t n_src, float* dst,
+                            int32_t* status, hsk_stream_t stream);
+HSK_API int hsk_scatter_add_rows(float* dst, int ld, const int64_t* idx, int64_t n, int64_t n_dst, const float* src,
+                                 int32_t* status, hsk_stream_t stream);
+
 /* ---- a8: torch.optim.AdamW(params, lr, weight_decay).step over a flat fp32 range (trainer.py:52-53,147) ---
  * Dense decoupled-decay Adam over ALL n elements, every step (zero-gradient rows included), in one streaming
  * pass: reads p, m, v, g; writes p, m, v and (zero_grad != 0) g = 0, replacing optimizer.zero_grad().
@@ -122,9 +136,12 @@ HSK_API int hsk_sample_negatives(const int64_t* u_idx, const int64_t* pos_idx /*
  * (eval.py:247-248), -inf on every id in the user's exclusion row (CSR, sorted global ids, int32; eval.py:250-251),
  * then the k best: top_scores/top_ids [Be, k], ordered by score descending, ties by item id ascending (torch.topk
  * leaves tie order unspecified).  Slots beyond the number of items get id -1 / score -inf.  The [Be, I] score matrix
- * is never materialised.  `scratch`: hsk_eval_topk_scratch_bytes(Be, t->n_items, k) bytes of device memory. */
+ * is never materialised.  `scratch`: hsk_eval_topk_scratch_bytes(Be, t->n_items, k) bytes of device memory.
+ * u_rows (nullable): when the user rows were gathered from other GPUs (item-sharded evaluation) batch entry r reads row
+ * u_rows[r] of t->Uw / t->Ub while u_idx[r] stays the GLOBAL user id (< n_users_global) that selects the exclusion row. */
 HSK_API int64_t hsk_eval_topk_scratch_bytes(int Be, int64_t n_local_items, int k);
-HSK_API int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, int Be, int64_t id_offset, int64_t id_stride,
+HSK_API int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const int64_t* u_rows /* nullable */,
+                          int64_t n_users_global, int Be, int64_t id_offset, int64_t id_stride,
                           const int64_t* excl_indptr /* [n_users + 1] or NULL */, const int32_t* excl_indices,
                           int k /* <= 128 */, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                           int32_t* status, hsk_stream_t stream);
@@ -140,7 +157,8 @@ HSK_API int hsk_pack_rows(const float* src, int ld, int d, const int64_t* row_id
                           void* dst, int kpad, int precision, int32_t* status, hsk_stream_t stream);
 HSK_API int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items, int k);
 HSK_API int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
-                             const float* Gb, const int64_t* u_idx, int Be, int64_t n_users, int64_t n_local,
+                             const float* Gb, const int64_t* u_idx, const int64_t* u_rows /* nullable: rows of Ub */, int Be,
+                             int64_t n_users, int64_t n_local,
                              int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
                              int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                              int32_t* status, hsk_stream_t stream);

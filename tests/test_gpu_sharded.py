@@ -1,0 +1,86 @@
+"""Multi-GPU (needs >= 2 devices; skipped on the 1-GPU box): the item-/user-sharded train step and evaluation on the real
+kernels over NCCL against the single-GPU path on the union batch."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+        from hassaku_b200.data.dataset import FullEvalDataset
+        from hassaku_b200.data.synthetic import make_interactions
+        from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+        from hassaku_b200.sharded import ShardedMF, partition_batch_by_user_owner
+        from hassaku_b200.train.optim import DenseAdam
+        from hassaku_b200.train.rec_losses import RecBayesianPersonalizedRankingLoss
+        from hassaku_b200.train.trainer_step import FusedMFTrainStep
+        U, I, d, B, N = 1201, 907, 402, 512, 20
+        dev = torch.device('cuda', rank)
+        torch.manual_seed(5)
+        single = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+        with torch.no_grad():
+            for p in single.parameters():
+                p.copy_(torch.randn_like(p) * (1 / math.sqrt(d) if p.shape[-1] == d else 0.1))
+        sd0 = {k: v.clone() for k, v in single.state_dict().items()}
+        single.to(dev)
+        lr, wd = 1e-3, 1e-4
+        opt = DenseAdam(single, lr=lr, weight_decay=wd)
+        step = FusedMFTrainStep(single, RecBayesianPersonalizedRankingLoss(), opt)
+        smf = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+        smf.load_full_state_dict(sd0)
+        rng = np.random.RandomState(9)
+        for s in range(2):
+            u = torch.from_numpy(rng.randint(0, U, B).astype(np.int64))
+            i = torch.from_numpy(rng.randint(0, I, (B, N + 1)).astype(np.int64))
+            step(u, i)
+            ul, il = partition_batch_by_user_owner(u.to(dev), i.to(dev), world, rank)
+            smf.step(ul, il, B, 'bpr', 0.0, lr, wd, exchange='sparse' if s == 0 else 'dense')
+            l_single, l_sh = step.pop_loss_sum(), smf.pop_loss()
+            assert abs(l_single - l_sh) <= 1e-5 * abs(l_single), (l_single, l_sh)
+        sd = smf.full_state_dict()
+        for n, p in single.state_dict().items():
+            a, b = sd[n].double(), p.detach().cpu().double()
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 1e-5 + 2e-3 * lr, (n, err)
+        assert int(smf.status.item()) == 0
+        # sharded evaluation == single-GPU evaluation (ids bit-exact: same fp32 kernel, order-independent merge)
+        data = make_interactions(U, I, 40000, seed=2, n_user_groups=2)
+        ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+
+        class L:
+            dataset, batch_size = ds, 256
+
+        ref = evaluate_recommender_algorithm(single, L, FullEvaluator(True, 2, ds.user_to_user_group), dev)
+        smf.load_full_state_dict({k: v.cpu() for k, v in single.state_dict().items()})
+        got = smf.evaluate(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=200)
+        assert sorted(got) == sorted(ref)
+        for k_, v in ref.items():
+            assert abs(got[k_] - v) <= 1e-9, (k_, got[k_], v)
+        if rank == 0:
+            open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+@pytest.mark.parametrize('world', [2])
+def test_sharded_step_and_eval_match_single_gpu(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()
