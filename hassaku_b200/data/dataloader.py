@@ -97,3 +97,22 @@ class TrainDataLoader:
             i_idxs = self.sample_batch(u_idxs, pos, self.step)
             self.step += 1
             yield u_idxs, i_idxs, self.labels_for(len(sel))
+
+
+class EvalLoader:
+    """Stand-in for `DataLoader(FullEvalDataset(...), batch_size=...)` (data/data_utils.py:348-368): the fused evaluator
+    only needs `.dataset` (its CSR matrices) and `.batch_size`; iterating yields the reference's dense batches
+    `(u_idxs, arange(I), y_true)` for host-side consumers."""
+
+    def __init__(self, dataset, batch_size: int = 64):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+
+    def __len__(self):
+        return math.ceil(len(self.dataset) / self.batch_size)
+
+    def __iter__(self):
+        n, I = len(self.dataset), self.dataset.n_items
+        for s in range(0, n, self.batch_size):
+            u = np.arange(s, min(s + self.batch_size, n))
+            y = self.dataset.iteration_matrix[u].toarray().astype('float32')
+            yield torch.from_numpy(u.astype(np.int64)), torch.arange(I).repeat(len(u), 1), torch.from_numpy(y)

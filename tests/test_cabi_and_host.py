@@ -199,3 +199,40 @@ def test_bench_batches_follow_loader_semantics_and_byte_accounting():
     assert abs(bench.algorithmic_bytes(6040, 3706, 402, 128, 50)['total'] / 1e6 - 131.3) < 0.1
     assert abs(bench.algorithmic_bytes(6040, 3706, 402, 8192, 50)['total'] / 1e6 - 1486.5) < 0.1
     assert abs(bench.algorithmic_bytes(69878, 10677, 128, 8192, 100)['total'] / 1e6 - 1157.9) < 0.1
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/algorithms'), reason='reference tree not mounted')
+def test_install_rebinds_reference_symbols_and_uninstall_restores():
+    """hassaku_b200.install() against the real reference (build container only): the factories and drivers the
+    reference's experiment_helper.py uses resolve to the CUDA implementations."""
+    from oracle import ref_shim
+    ref_shim.load()
+    import hassaku_b200
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization as HMF
+    from hassaku_b200.train.trainer import Trainer as HTrainer
+    from hassaku_b200.train.rec_losses import RecBayesianPersonalizedRankingLoss as HBpr
+    import algorithms.sgd_alg as r_alg
+    import train.rec_losses as r_loss
+    import train.trainer as r_trainer
+    from algorithms.algorithms_utils import AlgorithmsEnum
+    orig_trainer = r_trainer.Trainer
+    try:
+        patched = hassaku_b200.install()
+        assert ('train.trainer', 'Trainer') in patched and r_trainer.Trainer is HTrainer
+
+        class DS:
+            n_users, n_items = 10, 120
+
+        m = AlgorithmsEnum.mf.value.build_from_conf(
+            {'embedding_dim': 8, 'use_user_bias': False, 'use_item_bias': True, 'use_global_bias': False}, DS())
+        assert isinstance(m, HMF)
+        loss = r_loss.RecommenderSystemLossesEnum['bpr'].value.build_from_conf({}, DS())
+        assert isinstance(loss, HBpr)
+        import experiment_helper
+        assert experiment_helper.Trainer is HTrainer
+    finally:
+        hassaku_b200.uninstall()
+    assert r_trainer.Trainer is orig_trainer
+    m2 = AlgorithmsEnum.mf.value.build_from_conf(
+        {'embedding_dim': 8, 'use_user_bias': False, 'use_item_bias': True, 'use_global_bias': False}, DS())
+    assert type(m2) is r_alg.SGDMatrixFactorization
