@@ -414,9 +414,9 @@ static void eval_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_spli
     *n_splits = (nt + tps - 1) / tps;
 }
 
-int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int stride, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
                       const float* Ub, const float* Gb, const int64_t* u_idx, int64_t n_users) {
-    topk_merge_keys_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lists, n_lists, rows, kCap, k, out_scores, out_ids, Ub, Gb, u_idx, n_users);
+    topk_merge_keys_kernel<<<(rows + 7) / 8, 256, 0, s>>>(lists, n_lists, rows, stride, k, out_scores, out_ids, Ub, Gb, u_idx, n_users);
     return check_launch("topk merge");
 }
 
@@ -462,7 +462,7 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const
     eval_topk_f32_kernel<<<grid, kEvalThreads, 0, s>>>(a);
     int rc = check_launch("hsk_eval_topk");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, nullptr, nullptr, nullptr, 0);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, kCap, k, top_scores, top_ids, s, nullptr, nullptr, nullptr, 0);
     return rc;
 }
 

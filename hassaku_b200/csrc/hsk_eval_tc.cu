@@ -15,6 +15,7 @@
 // Operands are packed row-major [rows, kpad] (K-major for both A and B) by hsk_pack_rows: bf16 (round-to-nearest-even)
 // or tf32 (fp32 container, rna-rounded), zero padded to a multiple of 128 bytes of K.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "hsk_topk.cuh"
@@ -24,10 +25,13 @@ namespace hsk {
 constexpr int TC_BM = 128;        // users per CTA tile (UMMA_M)
 constexpr int TC_BN = 128;        // items per tile (UMMA_N)
 constexpr int TC_KB_BYTES = 128;  // bytes of K per k-block (one 128B swizzle atom)
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 10;          // B-tile ring depth is chosen at launch: as many 16 KB stages as fit beside the A tile
 constexpr int TC_TILE_BYTES = TC_BN * TC_KB_BYTES;  // 16 KB per operand tile per k-block
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TC_ACC_STAGES = 4;           // accumulator stages in TMEM: 4 x 128 fp32 columns = all 512 columns
+constexpr int TC_KPL = 16;                 // candidate keys per lane in the epilogue lists
+constexpr int TC_CAP = 32 * TC_KPL;        // 512-entry lists: a cut every ~(512 - 128 - k) appends instead of ~28
 constexpr int TC_MAX_KB = 8;      // kpad * elem_size <= 1024 bytes -> d <= 512 (bf16) / 256 (tf32)
 
 struct EvalTcArgs {
@@ -40,7 +44,9 @@ struct EvalTcArgs {
     const int32_t* __restrict__ excl_indices;
     int64_t n_users, n_local, id_offset, id_stride;
     int Be, k, num_kb, kelems_per_kb;
-    int n_tiles, tiles_per_split, n_splits;
+    int n_tiles, tiles_per_split, n_splits, n_stages;
+    int debug_flags;   // HSK_TC_DEBUG (measurement only): 1 = no candidate scan
+    unsigned long long* prof;   // optional [8] cycle counters of the epilogue phases (hsk_eval_tc_set_profile_buffer)
     uint64_t* cand;
     float* out_scores;
     int32_t* out_ids;
@@ -73,8 +79,7 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t adesc, uint64_t
                      : "memory");
     }
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
         "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -84,10 +89,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
 // start address >> 4 | SBO = 1024 B (8 rows x 128 B) | layout type 2 (SWIZZLE_128B)
@@ -106,17 +109,155 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Epilogue of one 32-column chunk for one row: v[] already holds score' = acc + item bias (the per-row user/global bias
 // does not change the ranking inside a row and is added when the final scores are written).
-__device__ __forceinline__ void tc_scan_chunk(const float (&v)[32], float tau, uint64_t taukey, int64_t gid0, int64_t id_stride,
-                                              int* s_cnt_row, uint64_t* list) {
+// `region` is this thread's PRIVATE half of the row's candidate list (the other column half of the row appends to the
+// other half), so an append is a register increment and a fire-and-forget store: no atomics, no dependent latency
+// (measured: with a shared counter an append cost ~280 cycles of warp time and dominated the epilogue).
+// Two steps: (1) a branch-free 32-bit survivor mask (one FSETP + one bit insert per element); (2) a short loop over the
+// set bits — survivors are rare (~5 per 1024 elements in steady state), so almost every lane runs 0 or 1 iteration.
+// The value of element e is pulled out of the register array with a 5-level select tree (no local memory).  An unrolled
+// `if (...) append` per element made the hot loop ~50 KB of divergent code that thrashed the I-cache (4.5 k cycles/scan).
+__device__ __forceinline__ float tc_pick(const float (&v)[32], int e) {
+    float a16[16], a8[8], a4[4], a2[2];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        if (v[e] >= tau) {
-            const uint64_t key = make_key(v[e], (uint32_t)(gid0 + e * id_stride));
-            if (key > taukey) {
-                const int pos = atomicAdd(s_cnt_row, 1);
-                list[pos] = key;
-            }
+    for (int i = 0; i < 16; ++i) a16[i] = (e & 16) ? v[16 + i] : v[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a8[i] = (e & 8) ? a16[8 + i] : a16[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a4[i] = (e & 4) ? a8[4 + i] : a8[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a2[i] = (e & 2) ? a4[2 + i] : a4[i];
+    return (e & 1) ? a2[1] : a2[0];
+}
+__device__ __forceinline__ void tc_scan_chunk(const float (&v)[32], float tau, uint64_t taukey, uint32_t valid, uint32_t gid0,
+                                              uint32_t id_stride, int& cnt, uint64_t* region) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) mask |= (v[e] >= tau) ? (1u << e) : 0u;
+    mask &= valid;
+    while (mask) {
+        const int e = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint64_t key = make_key(tc_pick(v, e), gid0 + (uint32_t)e * id_stride);
+        if (key > taukey) region[cnt++] = key;
+    }
+}
+
+constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
+
+// Cut a row's two half-lists (cA entries at lp[0..), cB entries at lp[256..)) back to ~k WITHOUT sorting: a radix select
+// on the 16 most significant bits of the keys finds the largest prefix T with count(prefix >= T) >= k; everything
+// below T is dropped, the survivors (k plus the few ties of the T bucket) are compacted and written back split over the
+// two halves.  The new threshold is the lower edge of bucket T — conservative, so no top-k item is ever lost; the exact
+// order is established once, by the final sort.  ~1.5 k cycles instead of ~56 k for the 512-key bitonic network.
+// Entries beyond chkA / chkB are first tested against the user's exclusion row (lock-step binary searches).
+// Returns the number of survivors.
+__device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, int chkB, int k, int lane,
+                                          const int32_t* __restrict__ excl, int64_t lo, int64_t hi, float* new_tau,
+                                          uint64_t* new_taukey, unsigned long long* tprof) {
+    long long t0 = tprof ? clock64() : 0;
+#define HSK_CUT_TICK(i) do { if (tprof) { const long long t1 = clock64(); if (lane == 0) atomicAdd(tprof + (i), (unsigned long long)(t1 - t0)); t0 = t1; } } while (0)
+    uint64_t key[TC_KPL];
+    bool unchecked[TC_KPL];
+#pragma unroll
+    for (int r = 0; r < TC_KPL; ++r) {
+        const int e = r * 32 + lane;
+        const bool inA = e < TC_HALF_CAP;
+        const int idx = inA ? e : e - TC_HALF_CAP;
+        const bool valid = idx < (inA ? cA : cB);
+        key[r] = valid ? lp[e] : 0ull;
+        unchecked[r] = valid && idx >= (inA ? chkA : chkB);
+    }
+    { uint64_t x = 0;
+#pragma unroll
+      for (int r = 0; r < TC_KPL; ++r) x ^= key[r];
+      if (tprof && x == 0x123456789ull) lp[0] = x; }
+    HSK_CUT_TICK(6);
+    if (hi > lo) {
+        int32_t id[TC_KPL];
+        bool found[TC_KPL];
+#pragma unroll
+        for (int r = 0; r < TC_KPL; ++r) id[r] = key_id(key[r]);
+        csr_contains_many<TC_KPL>(excl, lo, hi, id, unchecked, found);
+#pragma unroll
+        for (int r = 0; r < TC_KPL; ++r)
+            if (found[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
+    }
+    HSK_CUT_TICK(7);
+    const int n = cA + cB;
+    uint32_t T = 0;
+    if (n > k) {
+        uint32_t pre[TC_KPL];
+#pragma unroll
+        for (int r = 0; r < TC_KPL; ++r) pre[r] = (uint32_t)(key[r] >> 48);   // empty slots have prefix 0
+#pragma unroll 1
+        for (int b = 15; b >= 0; --b) {
+            const uint32_t cand = T | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < TC_KPL; ++r) c += (pre[r] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= k) T = cand;
         }
+    }
+    HSK_CUT_TICK(8);
+    // compaction: keep keys whose prefix >= T (all valid keys when n <= k)
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < TC_KPL; ++r) mine += (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (total > TC_HALF_CAP - TC_BN / 2) {
+        // degenerate score distribution (a huge tie bucket, e.g. all-equal scores): exact cut by the full sort; ties are
+        // then resolved by the strict key order (lower item id wins), which the scan honours through `taukey`
+        warp_sort_desc<TC_KPL>(key, lane);
+        const int nA2 = (k + 1) >> 1;
+#pragma unroll
+        for (int r = 0; r < TC_KPL; ++r) {
+            const int e = r * 32 + lane;
+            if (e < k) lp[e < nA2 ? e : TC_HALF_CAP + (e - nA2)] = key[r];
+        }
+        const uint64_t thr = warp_list_at<TC_KPL>(key, k - 1);
+        *new_taukey = thr;
+        *new_tau = key_score(thr);
+        return k;
+    }
+    int pos = incl - mine;
+    const int nA = (total + 1) >> 1;
+#pragma unroll
+    for (int r = 0; r < TC_KPL; ++r) {
+        if (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) {
+            lp[pos < nA ? pos : TC_HALF_CAP + (pos - nA)] = key[r];
+            ++pos;
+        }
+    }
+    HSK_CUT_TICK(9);
+    if (tprof && lane == 0) atomicAdd(tprof + 13, 1ull);
+    *new_tau = (n > k) ? from_orderable(T << 16) : -INFINITY;   // lower edge of bucket T (n > k implies T >= 0x007F)
+    *new_taukey = (n > k) ? ((uint64_t)(T << 16) << 32) : 0ull;
+    return total;
+}
+
+// Final, exact: the (already cut and exclusion-checked) halves nA entries at lp[0..) and nB at lp[256..), nA, nB <= 128,
+// are sorted with the 256-key network and the best k written to lp[0..k) / returned in key[] (element e = r * 32 + lane).
+__device__ __noinline__ void tc_final_sort(uint64_t* lp, int nA, int nB, int k, int lane, uint64_t (&key)[kKeysPerLane]) {
+#pragma unroll
+    for (int r = 0; r < kKeysPerLane; ++r) {
+        const int e = r * 32 + lane;
+        const bool inA = e < 128;
+        const int idx = inA ? e : e - 128;
+        key[r] = (idx < (inA ? nA : nB)) ? lp[inA ? idx : TC_HALF_CAP + idx] : 0ull;
+    }
+    warp_sort_desc<kKeysPerLane>(key, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kKeysPerLane; ++r) {
+        const int e = r * 32 + lane;
+        if (e < k) lp[e] = key[r];
     }
 }
 
@@ -124,15 +265,16 @@ template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_a, bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[TC_ACC_STAGES], bar_tempty[TC_ACC_STAGES];
     __shared__ uint32_t s_tmem_base;
     // per-row top-k state shared by the two epilogue warps of a row (column halves)
     __shared__ float s_tau[TC_BM];
     __shared__ uint64_t s_taukey[TC_BM];
-    __shared__ int s_cnt[TC_BM], s_checked[TC_BM];
+    __shared__ int s_cnt2[2][TC_BM], s_chk2[2][TC_BM];   // per column half: entries / exclusion-checked entries
     __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
     __shared__ float s_base[TC_BM];
     __shared__ int s_rowok[TC_BM];
+    __shared__ __align__(16) float s_ib[4][2][TC_BN];   // per pair: item-bias tile, double buffered with the accumulator stages
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
@@ -144,16 +286,16 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* smA = smem;                                        // num_kb x 16 KB, resident
-    unsigned char* smB = smem + (size_t)a.num_kb * TC_TILE_BYTES;     // TC_STAGES x 16 KB
+    unsigned char* smB = smem + (size_t)a.num_kb * TC_TILE_BYTES;     // n_stages x 16 KB
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_a, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], TC_EPI_WARPS); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], TC_EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == 1) {  // TMEM: 2 accumulator stages x 128 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "n"(TC_ACC_STAGES * TC_BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_BM) {  // per-row state
@@ -174,7 +316,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (a.Gb) base += a.Gb[0];
         s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
-        s_tau[r] = -INFINITY; s_taukey[r] = 0ull; s_cnt[r] = 0; s_checked[r] = 0;
+        s_tau[r] = -INFINITY; s_taukey[r] = 0ull;
+        s_cnt2[0][r] = s_cnt2[1][r] = 0; s_chk2[0][r] = s_chk2[1][r] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -196,7 +339,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&bar_empty[s], ph ^ 1u);
                     mbar_expect_tx(&bar_full[s], TC_TILE_BYTES);
                     tma_load_2d(smB + (size_t)s * TC_TILE_BYTES, &tmB, kb * a.kelems_per_kb, n0, &bar_full[s]);
-                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -211,8 +354,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int s = 0;
             uint32_t ph = 0;
             for (int t = 0; t < n_my_tiles; ++t) {
-                const int as = t & 1;
-                mbar_wait(&bar_tempty[as], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                const int as = t % TC_ACC_STAGES;
+                mbar_wait(&bar_tempty[as], (((uint32_t)t / TC_ACC_STAGES) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_c = tmem_base + (uint32_t)as * TC_BN;
                 for (int kb = 0; kb < a.num_kb; ++kb) {
@@ -224,101 +367,169 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k = 0; k < TC_KB_BYTES / 32; ++k)  // 32 bytes of K per MMA: advance the start address by 2 (x16 B)
                         tc_mma<TF32>(tmem_c, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                     tc_commit(&bar_empty[s]);
-                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(&bar_tfull[as]);
             }
         }
     } else {
-        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4.  The two warps of a quarter
+        // (a "pair", 64 threads) own the 32 rows of that quarter and synchronise only with each other. =====
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int half = ew >> 2;
         const int r = quarter * 32 + lane;   // row within the tile == TMEM lane
         const bool row_ok = s_rowok[r] != 0;
-        uint64_t* list = a.cand + ((int64_t)split * a.Be + min(m0 + r, a.Be - 1)) * kCap;
-        const int prune_at = kCap - TC_BN;
-        const bool ib_vec = a.Ib != nullptr && ((reinterpret_cast<uintptr_t>(a.Ib) & 15) == 0);
+        uint64_t* list = a.cand + ((int64_t)split * a.Be + min(m0 + r, a.Be - 1)) * TC_CAP;
+        const int prune_at = TC_HALF_CAP - TC_BN / 2;   // a tile appends at most 64 keys per column half
+        uint64_t* region = list + half * TC_HALF_CAP;
+        int cnt = 0;
+        float* ib_pair = &s_ib[quarter][0][0];
+        const int pt = half * 32 + lane;     // thread index within the pair (0..63)
+        const int bar_id = 1 + quarter;
 
+        // item-bias tile of the first tile -> shared memory (each pair keeps its own copy: no CTA-wide sync needed)
+        {
+            const int64_t n0 = (int64_t)t_begin * TC_BN;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t n = n0 + pt + 64 * h;
+                ib_pair[pt + 64 * h] = (a.Ib && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
+            }
+        }
+        named_bar_sync(bar_id, 64);
+
+        unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
+        unsigned long long n_app = 0, n_scan_lane = 0, n_scan_warp = 0;
+        long long tk = clock64();
+#define HSK_TICK(i) do { if (a.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } } while (0)
         for (int t = 0; t < n_my_tiles; ++t) {
-            const int as = t & 1;
+            const int as = t % TC_ACC_STAGES;
+            const int ibs = t & 1;
             const int64_t n0 = (int64_t)(t_begin + t) * TC_BN;
             const int ncols = (int)min((int64_t)TC_BN, a.n_local - n0);
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
-            mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN;
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = half * 64 + cc * 32;
-                float v[32];
-                tc_ld32(taddr + (uint32_t)c, v);
-                if (c >= ncols) continue;
-                const int64_t gid0 = a.id_offset + (n0 + c) * a.id_stride;
-                if (c + 32 <= ncols) {
-                    float mx = -INFINITY;
-                    if (ib_vec) {
-                        const float4* ibp = reinterpret_cast<const float4*>(a.Ib + n0 + c);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b4 = __ldg(ibp + q);
-                            v[4 * q + 0] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-                        }
-                    } else if (a.Ib) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] += __ldg(a.Ib + n0 + c + e);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(v[e], v[e + 1]));
-                    if (row_ok && mx >= tau) tc_scan_chunk(v, tau, taukey, gid0, a.id_stride, &s_cnt[r], list);
-                } else {  // the ragged last tile: out-of-range columns never become candidates
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const bool in = c + e < ncols;
-                        v[e] = in ? v[e] + (a.Ib ? __ldg(a.Ib + n0 + c + e) : 0.f) : __int_as_float(0x7fc00000);  // NaN fails >=
-                    }
-                    if (row_ok) tc_scan_chunk(v, tau, taukey, gid0, a.id_stride, &s_cnt[r], list);
-                }
+            const float* ibt = ib_pair + ibs * TC_BN;
+            // prefetch the next tile's bias values into registers (stored to the other smem stage after the scan)
+            float ibn0 = 0.f, ibn1 = 0.f;
+            if (t + 1 < n_my_tiles && a.Ib) {
+                const int64_t nn = n0 + TC_BN + pt;
+                if (nn < a.n_local) ibn0 = __ldg(a.Ib + nn);
+                if (nn + 64 < a.n_local) ibn1 = __ldg(a.Ib + nn + 64);
             }
-            // release the accumulator stage (the MMA of the next tile proceeds), then prune cooperatively
+            mbar_wait(&bar_tfull[as], ((uint32_t)t / TC_ACC_STAGES) & 1u);
+            tc_fence_after();
+            HSK_TICK(0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN + (uint32_t)(half * 64);
+            uint32_t raw0[32], raw1[32];
+            tc_ld32_issue(taddr, raw0);
+            tc_ld32_issue(taddr + 32u, raw1);
+            tc_ld_wait();
+            // both chunks are in registers: release the accumulator stage right away (MMA of tile t+2 may start)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[as]);
-            named_bar_sync(1, TC_EPI_WARPS * 32);
-            const bool last = (t + 1 == n_my_tiles);
-            for (int rr = ew; rr < TC_BM; rr += TC_EPI_WARPS) {
-                if (!s_rowok[rr]) continue;
-                const int n_r = s_cnt[rr];
-                if (n_r > prune_at || last) {
-                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * kCap;
-                    uint64_t thr;
-                    const int nn = warp_prune_list_masked(lp, n_r, s_checked[rr], a.k, lane, &thr, a.excl_indices, s_exlo[rr], s_exhi[rr]);
-                    __syncwarp();
-                    if (lane == 0) {
-                        s_cnt[rr] = nn; s_checked[rr] = nn; s_taukey[rr] = thr;
-                        s_tau[rr] = thr ? key_score(thr) : -INFINITY;
+            HSK_TICK(1);
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {   // one code instance for both chunks (keeps the hot loop inside the I-cache)
+                const int c = half * 64 + cc * 32;
+                if (c < ncols) {
+                    float v[32];
+                    const float4* ib4 = reinterpret_cast<const float4*>(ibt + c);
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b4 = ib4[q];
+                        v[4 * q + 0] = __uint_as_float(raw0[4 * q + 0]) + b4.x;
+                        v[4 * q + 1] = __uint_as_float(raw0[4 * q + 1]) + b4.y;
+                        v[4 * q + 2] = __uint_as_float(raw0[4 * q + 2]) + b4.z;
+                        v[4 * q + 3] = __uint_as_float(raw0[4 * q + 3]) + b4.w;
+                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q + 0], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
                     }
-                    if (last && a.n_splits == 1) {
+                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
+                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
+                    if (row_ok && mx >= tau && !(a.debug_flags & 1)) {
+                        const int c0 = cnt;
+                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
+                                      cnt, region);
+                        if (a.prof) { n_app += cnt - c0; n_scan_lane += 1; }
+                    }
+                    if (a.prof && __any_sync(kFull, row_ok && mx >= tau)) n_scan_warp += 1;
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) raw0[e] = raw1[e];
+            }
+            ib_pair[(ibs ^ 1) * TC_BN + pt] = ibn0;
+            ib_pair[(ibs ^ 1) * TC_BN + pt + 64] = ibn1;
+            s_cnt2[half][r] = cnt;
+            HSK_TICK(2);
+            named_bar_sync(bar_id, 64);
+            HSK_TICK(3);
+            // cut back the lists of this pair's rows that may overflow on the next tile (16 rows per warp)
+            const bool last = (t + 1 == n_my_tiles);
+            int my_a = 0, my_b = 0;
+            bool my_need = false;
+            if (lane < 16) {   // lane j looks at row j of this warp's 16 rows: two shared-memory reads, then a ballot
+                const int rj = quarter * 32 + half * 16 + lane;
+                my_a = s_cnt2[0][rj];
+                my_b = s_cnt2[1][rj];
+                my_need = s_rowok[rj] && (my_a > prune_at || my_b > prune_at || last);
+            }
+            unsigned need = __ballot_sync(kFull, my_need);
+            while (need) {
+                const int j = __ffs(need) - 1;
+                need &= need - 1;
+                const int rr = quarter * 32 + half * 16 + j;
+                const int cA = __shfl_sync(kFull, my_a, j), cB = __shfl_sync(kFull, my_b, j);
+                uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
+                float ntau;
+                uint64_t ntaukey;
+                // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors)
+                const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
+                                             s_exhi[rr], &ntau, &ntaukey, a.prof);
+                __syncwarp();
+                const int nA = (total + 1) >> 1;
+                if (lane == 0) {
+                    s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA; s_chk2[0][rr] = nA; s_chk2[1][rr] = total - nA;
+                    s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
+                }
+                if (last) {
+                    uint64_t keys[kKeysPerLane];
+                    tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
+                    if (a.n_splits == 1) {
                         const int64_t orow = (int64_t)(m0 + rr) * a.k;
                         const float base = s_base[rr];
-                        for (int e = lane; e < a.k; e += 32) {
-                            const uint64_t key = lp[e];
-                            a.out_scores[orow + e] = key ? key_score(key) + base : -INFINITY;
-                            a.out_ids[orow + e] = key_id(key);
+#pragma unroll
+                        for (int q = 0; q < kKeysPerLane; ++q) {
+                            const int e = q * 32 + lane;
+                            if (e < a.k) {
+                                a.out_scores[orow + e] = keys[q] ? key_score(keys[q]) + base : -INFINITY;
+                                a.out_ids[orow + e] = key_id(keys[q]);
+                            }
                         }
                     }
                 }
             }
-            named_bar_sync(1, TC_EPI_WARPS * 32);
+            HSK_TICK(4);
+            named_bar_sync(bar_id, 64);
+            cnt = s_cnt2[half][r];
+            HSK_TICK(5);
         }
+        if (a.prof && lane == 0) {
+            for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, pc[i]);
+            atomicAdd(a.prof + 12, n_scan_warp);
+        }
+        if (a.prof) { atomicAdd(a.prof + 10, n_app); atomicAdd(a.prof + 11, n_scan_lane); }
         // rows with a bad user index: empty lists / -1 ids
-        for (int rr = ew; rr < TC_BM; rr += TC_EPI_WARPS) {
+        for (int j = 0; j < 16; ++j) {
+            const int rr = quarter * 32 + half * 16 + j;
             if (m0 + rr < a.Be && !s_rowok[rr]) {
                 if (a.n_splits == 1) {
                     for (int e = lane; e < a.k; e += 32) { a.out_scores[(int64_t)(m0 + rr) * a.k + e] = -INFINITY; a.out_ids[(int64_t)(m0 + rr) * a.k + e] = -1; }
                 } else {
-                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * kCap;
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
                     for (int e = lane; e < a.k; e += 32) lp[e] = 0ull;
                 }
             }
@@ -328,7 +539,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TC_ACC_STAGES * TC_BN));
     }
 }
 
@@ -405,6 +616,9 @@ static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split,
 
 using namespace hsk;
 
+static unsigned long long* g_tc_prof = nullptr;   // measurement hook, not part of the public header
+extern "C" __attribute__((visibility("default"))) void hsk_debug_eval_tc_profile(unsigned long long* dev_counters) { g_tc_prof = dev_counters; }
+
 extern "C" int hsk_eval_tc_kpad(int d, int precision) {
     const int per_kb = (precision == HSK_PREC_TF32) ? 32 : 64;
     return ((d + per_kb - 1) / per_kb) * per_kb;
@@ -431,7 +645,7 @@ extern "C" int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items,
     (void)k;
     int nt, tps, ns;
     tc_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, &nt, &tps, &ns);
-    return (int64_t)ns * (Be > 0 ? Be : 1) * kCap * (int64_t)sizeof(uint64_t);
+    return (int64_t)ns * (Be > 0 ? Be : 1) * TC_CAP * (int64_t)sizeof(uint64_t);
 }
 
 extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
@@ -458,7 +672,7 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     a.n_users = n_users; a.n_local = n_local; a.id_offset = id_offset; a.id_stride = id_stride;
     a.Be = Be; a.k = k; a.num_kb = num_kb; a.kelems_per_kb = per_kb;
     tc_plan(Be, n_local, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
-    const int64_t need = (int64_t)a.n_splits * Be * kCap * (int64_t)sizeof(uint64_t);
+    const int64_t need = (int64_t)a.n_splits * Be * TC_CAP * (int64_t)sizeof(uint64_t);
     HSK_REQUIRE(scratch && scratch_bytes >= need, "hsk_eval_topk_tc: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
     a.cand = reinterpret_cast<uint64_t*>(scratch);
     a.out_scores = top_scores; a.out_ids = top_ids; a.status = status;
@@ -467,7 +681,13 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (rc) return rc;
     rc = make_map(&tmB, Vq, tf32, kpad, n_local, per_kb);
     if (rc) return rc;
-    const size_t smem = (size_t)(num_kb + TC_STAGES) * TC_TILE_BYTES + 1024;
+    int n_stages = (200 * 1024 - num_kb * TC_TILE_BYTES) / TC_TILE_BYTES;   // ~200 KB of the 227 KB for operands
+    if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
+    if (n_stages < 2) n_stages = 2;
+    a.n_stages = n_stages;
+    { const char* dbg = getenv("HSK_TC_DEBUG"); a.debug_flags = dbg ? atoi(dbg) : 0; }
+    a.prof = g_tc_prof;
+    const size_t smem = (size_t)(num_kb + n_stages) * TC_TILE_BYTES + 1024;
     cudaStream_t s = as_stream(stream);
     dim3 grid((Be + TC_BM - 1) / TC_BM, a.n_splits);
     cudaError_t e;
@@ -481,6 +701,6 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc: smem attribute: %s", cudaGetErrorString(e));
     rc = check_launch("hsk_eval_topk_tc");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, TC_CAP, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
     return rc;
 }

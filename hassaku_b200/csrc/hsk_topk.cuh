@@ -32,35 +32,43 @@ __device__ __forceinline__ int32_t key_id(uint64_t key) {
     return key == 0 ? -1 : static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFu));
 }
 
-// Sort 256 keys held by a warp (element e = r * 32 + lane lives in key[r] of `lane`) in DESCENDING order.
-__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[kKeysPerLane], int lane) {
+// Sort 32 * KPL keys held by a warp (element e = r * 32 + lane lives in key[r] of `lane`) in DESCENDING order.
+template <int KPL>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[KPL], int lane) {
+    // log2-indexed unit-stride loops: nvcc fully unrolls them, so key[] stays in registers (with shift-stepped loops it
+    // did not, and the network ran out of local memory: ~130 k cycles per 512-key sort, measured)
+    constexpr int LOGN = (KPL == 1 ? 5 : KPL == 2 ? 6 : KPL == 4 ? 7 : KPL == 8 ? 8 : 9);
+    static_assert((32 * KPL) == (1 << LOGN), "KPL must be a power of two <= 16");
 #pragma unroll
-    for (int k = 2; k <= kCap; k <<= 1) {
+    for (int lk = 1; lk <= LOGN; ++lk) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int jr = j >> 5;
+        for (int lj = LOGN - 1; lj >= 0; --lj) {
+            if (lj < lk) {
+                const int k = 1 << lk, j = 1 << lj;
+                if (lj >= 5) {
+                    const int jr = j >> 5;
 #pragma unroll
-                for (int r = 0; r < kKeysPerLane; ++r) {
-                    const int rp = r ^ jr;
-                    if (rp > r) {
-                        const bool desc = (((r * 32 + lane) & k) == 0);
-                        const uint64_t a = key[r], b = key[rp];
-                        const bool sw = desc ? (a < b) : (a > b);
-                        key[r] = sw ? b : a;
-                        key[rp] = sw ? a : b;
+                    for (int r = 0; r < KPL; ++r) {
+                        if ((r & jr) == 0) {
+                            const int rp = r | jr;
+                            const bool desc = (((r * 32 + lane) & k) == 0);
+                            const uint64_t a = key[r], b = key[rp];
+                            const bool sw = desc ? (a < b) : (a > b);
+                            key[r] = sw ? b : a;
+                            key[rp] = sw ? a : b;
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int r = 0; r < kKeysPerLane; ++r) {
-                    const uint64_t other = __shfl_xor_sync(kFull, key[r], j);
-                    const bool lower = (lane & j) == 0;
-                    const bool desc = (((r * 32 + lane) & k) == 0);
-                    const bool keep_max = (lower == desc);
-                    const uint64_t mx = key[r] > other ? key[r] : other;
-                    const uint64_t mn = key[r] > other ? other : key[r];
-                    key[r] = keep_max ? mx : mn;
+                    for (int r = 0; r < KPL; ++r) {
+                        const uint64_t other = __shfl_xor_sync(kFull, key[r], j);
+                        const bool lower = (lane & j) == 0;
+                        const bool desc = (((r * 32 + lane) & k) == 0);
+                        const bool keep_max = (lower == desc);
+                        const uint64_t mx = key[r] > other ? key[r] : other;
+                        const uint64_t mn = key[r] > other ? other : key[r];
+                        key[r] = keep_max ? mx : mn;
+                    }
                 }
             }
         }
@@ -68,10 +76,11 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[kKeysPerLane], in
 }
 
 // element #pos (0 <= pos < 256) of a warp-held sorted list, broadcast to every lane
-__device__ __forceinline__ uint64_t warp_list_at(const uint64_t (&key)[kKeysPerLane], int pos) {
+template <int KPL>
+__device__ __forceinline__ uint64_t warp_list_at(const uint64_t (&key)[KPL], int pos) {
     uint64_t v = 0;
 #pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r)
+    for (int r = 0; r < KPL; ++r)
         if (r == (pos >> 5)) v = key[r];
     return __shfl_sync(kFull, v, pos & 31);
 }
@@ -86,22 +95,47 @@ __device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ idx, in
     return lo < end && __ldg(idx + lo) == x;
 }
 
+// KPL membership tests in lock-step: every step of the binary search issues KPL independent loads per lane, so the
+// latencies of the searches overlap (one after the other they cost KPL x log2(len) dependent global-memory round trips —
+// measured 125 k cycles per list cut in the tensor-core evaluator).  found[r] = id[r] is in the sorted row [lo, hi).
+template <int KPL>
+__device__ __forceinline__ void csr_contains_many(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, const int32_t (&id)[KPL],
+                                                  const bool (&active)[KPL], bool (&found)[KPL]) {
+    const int len = (int)(hi - lo);
+    const int32_t* row = idx + lo;
+    int pos[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) pos[r] = 0;
+    int step = 1;
+    while (step * 2 <= len) step *= 2;
+    for (; step > 0; step >>= 1) {
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const int probe = pos[r] + step;
+            if (active[r] && probe <= len && __ldg(row + probe - 1) < id[r]) pos[r] = probe;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) found[r] = active[r] && pos[r] < len && __ldg(row + pos[r]) == id[r];
+}
+
 // Cut a row's candidate list (n <= kCap keys at `list`, global or shared memory) back to its best k, sorted.
 // Returns the new length min(n, k); *thr_key receives the k-th key (0 while the list holds fewer than k).
+template <int KPL = kKeysPerLane>
 __device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int lane, uint64_t* thr_key) {
-    uint64_t key[kKeysPerLane];
+    uint64_t key[KPL];
 #pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
+    for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
         key[r] = (e < n) ? list[e] : 0ull;
     }
-    warp_sort_desc(key, lane);
+    warp_sort_desc<KPL>(key, lane);
 #pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
+    for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
         if (e < k) list[e] = key[r];
     }
-    *thr_key = (n >= k) ? warp_list_at(key, k - 1) : 0ull;
+    *thr_key = (n >= k) ? warp_list_at<KPL>(key, k - 1) : 0ull;
     return n < k ? n : k;
 }
 
@@ -109,36 +143,47 @@ __device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int
 // yet (the scoring epilogues append raw candidates so that their hot loop has no dependent global loads); an excluded
 // item is re-keyed to score -inf (eval/eval.py:250-251) before the sort.  The 8 binary searches of a lane are
 // independent, so their latencies overlap.
+template <int KPL = kKeysPerLane>
 __device__ __forceinline__ int warp_prune_list_masked(uint64_t* list, int n, int n_checked, int k, int lane, uint64_t* thr_key,
-                                                      const int32_t* __restrict__ excl, int64_t lo, int64_t hi) {
-    uint64_t key[kKeysPerLane];
+                                                      const int32_t* __restrict__ excl, int64_t lo, int64_t hi,
+                                                      unsigned long long* tprof = nullptr) {
+    long long t0 = tprof ? clock64() : 0;
+    uint64_t key[KPL];
 #pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
+    for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
         key[r] = (e < n) ? list[e] : 0ull;
     }
+    if (tprof) { uint64_t x = 0; for (int r = 0; r < KPL; ++r) x ^= key[r]; if (x == 0x1234567ull) list[0] = x; const long long t1 = clock64(); tprof[0] += t1 - t0; t0 = t1; }
     if (hi > lo) {
+        int32_t id[KPL];
+        bool active[KPL], found[KPL];
 #pragma unroll
-        for (int r = 0; r < kKeysPerLane; ++r) {
+        for (int r = 0; r < KPL; ++r) {
             const int e = r * 32 + lane;
-            if (e >= n_checked && e < n) {
-                const int32_t id = key_id(key[r]);
-                if (csr_contains(excl, lo, hi, id)) key[r] = make_key(-INFINITY, (uint32_t)id);
-            }
+            active[r] = e >= n_checked && e < n;
+            id[r] = key_id(key[r]);
         }
-    }
-    warp_sort_desc(key, lane);
+        csr_contains_many<KPL>(excl, lo, hi, id, active, found);
 #pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
+        for (int r = 0; r < KPL; ++r)
+            if (found[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
+    }
+    if (tprof) { uint64_t x = 0; for (int r = 0; r < KPL; ++r) x ^= key[r]; if (x == 0x1234567ull) list[0] = x; const long long t1 = clock64(); tprof[1] += t1 - t0; t0 = t1; }
+    warp_sort_desc<KPL>(key, lane);
+    if (tprof) { uint64_t x = 0; for (int r = 0; r < KPL; ++r) x ^= key[r]; if (x == 0x1234567ull) list[0] = x; const long long t1 = clock64(); tprof[2] += t1 - t0; t0 = t1; }
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
         if (e < k) list[e] = key[r];
     }
-    *thr_key = (n >= k) ? warp_list_at(key, k - 1) : 0ull;
+    if (tprof) { const long long t1 = clock64(); tprof[3] += t1 - t0; tprof[4] += 1; }
+    *thr_key = (n >= k) ? warp_list_at<KPL>(key, k - 1) : 0ull;
     return n < k ? n : k;
 }
 
-// hsk_eval.cu: merge of n_lists sorted key lists per row laid out [list][row][kCap] (split plans of the eval kernels)
-int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
+// hsk_eval.cu: merge of n_lists sorted key lists per row laid out [list][row][stride] (split plans of the eval kernels)
+int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int stride, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
                       const float* Ub, const float* Gb, const int64_t* u_idx, int64_t n_users);
 
 }  // namespace hsk

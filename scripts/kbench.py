@@ -89,6 +89,22 @@ def evalk(args):
         for _ in range(2):
             fn()
         med, best = time_kernel(fn, args.iters, flush)
+        if os.environ.get('HSK_TC_PROFILE') and prec != 'fp32':
+            import ctypes
+            from hassaku_b200 import _C
+            cnt = torch.zeros(16, dtype=torch.int64, device='cuda')
+            _C.lib().hsk_debug_eval_tc_profile(ctypes.c_void_p(cnt.data_ptr()))
+            fn(); torch.cuda.synchronize()
+            _C.lib().hsk_debug_eval_tc_profile(None)
+            call = cnt.cpu().numpy().astype(float)
+            c = call[:6]
+            pr = call[6:11]
+            nw = (B + 127) // 128 * 8
+            names = ['wait_tfull', 'tmem_ld', 'bias+max+scan', 'pair_bar1', 'prune', 'pair_bar2']
+            print('   epilogue cycles per warp (k): ' + ', '.join(f'{n}={v/nw/1e3:.0f}' for n, v in zip(names, c)) + f'  total={c.sum()/nw/1e3:.0f}')
+            print(f'   per warp: appends={call[10]/nw:.0f} lane-scans={call[11]/nw:.0f} warp-scans={call[12]/nw:.0f} (of {2*((I+127)//128)} chunks)')
+            nc = max(call[13], 1)
+            print(f'   cuts/warp={call[13]/nw:.0f}; cycles per cut: load={call[6]/nc:.0f} excl={call[7]/nc:.0f} select={call[8]/nc:.0f} compact+store={call[9]/nc:.0f}')
         fl = 2.0 * B * I * d
         print(f'eval[{prec:4s}] U_b={B} I={I} d={d}: med {med:9.3f} ms best {best:9.3f} ms -> {B/med*1e3:12.0f} users/s '
               f'{fl/med/1e9:8.1f} TFLOP/s')
