@@ -207,6 +207,84 @@ def cpu_baseline(wl, data, us, its, budget_s=20.0):
                       f'{os.cpu_count()} cpus), {dt:.1f} s'}
 
 
+def run_extras(dev, flush):
+    """Kernel-level measurements at the shapes of BASELINE configs 4 and 5 that do not fit the cfg2 step (reported next to
+    the headline, never instead of it):
+      adamw_cfg4      hsk_adamw_dense over P = 385 M parameters (2 M users x 1 M items, d 128): the genuinely HBM-bound
+                      kernel of the path (28 B / parameter + 4 B gradient zeroing), GB/s vs the measured copy bandwidth
+      eval_tc_cfg5    hsk_eval_topk_tc, one batch of 18 944 users (148 CTAs x 128) against 1 M items, d 256, BF16 and
+                      TF32: users/s, TFLOP/s vs the measured sustained bf16 GEMM peak (tensor-pipe roofline)"""
+    import torch
+    from hassaku_b200 import _C
+    out = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        peaks = {'hbm_gbs': 6650.0, 'bf16_tflops_sustained': 1400.0, 'bf16_tflops': 1590.0}
+
+    def timed(fn, iters):
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    try:
+        P = (2_000_000 + 1_000_000) * 128 + 1_000_000
+        p = torch.zeros(P, device=dev); m = torch.zeros_like(p); v = torch.zeros_like(p)
+        g = torch.full((P,), 1e-3, device=dev)
+        k = [0]
+
+        def adam():
+            k[0] += 1
+            _C.adamw_dense(p, m, v, g, 3e-4, 0.9, 0.999, 1e-8, 4e-5, k[0], zero_grad=True)
+        adam()
+        ms = timed(adam, 5)
+        gbs = 32.0 * P / (ms * 1e-3) / 1e9   # 16 B read + 16 B written per parameter (g zeroed in the same pass)
+        out['adamw_cfg4'] = {'params': P, 'ms': ms, 'bytes_per_param': 32, 'achieved_gbs': gbs, 'peak_gbs': peaks['hbm_gbs'],
+                             'frac': gbs / peaks['hbm_gbs']}
+        del p, m, v, g
+    except Exception as ex:
+        out['adamw_cfg4'] = {'error': repr(ex)}
+    try:
+        import math
+        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+        from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
+        from scipy import sparse as sp
+        U, I, d, B = 18944, 1_000_000, 256, 18944
+        torch.manual_seed(0)
+        model = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+        with torch.no_grad():
+            for q in model.parameters():
+                q.copy_(torch.randn_like(q) * (1.0 / math.sqrt(d) if q.shape[-1] == d else 0.05))
+        model.to(dev)
+        rng = np.random.RandomState(1)
+        rows = np.repeat(np.arange(U), 80)
+        ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+        ex.sum_duplicates(); ex.sort_indices()
+        ex = DeviceCSR(ex, dev)
+        users = torch.arange(B, device=dev)
+        fl = 2.0 * B * I * d
+        for prec in ('bf16', 'tf32'):
+            sc = TopKScorer(model, B, 100, prec)
+            fn = lambda: sc(users, ex)
+            fn(); fn()
+            ms = timed(fn, 3)
+            out[f'eval_tc_cfg5_{prec}'] = {'users': B, 'items': I, 'd': d, 'k': 100, 'ms_per_batch': ms, 'users_per_s': B / (ms * 1e-3),
+                                           'tflops': fl / (ms * 1e-3) / 1e12, 'peak_tflops_sustained_bf16': peaks['bf16_tflops_sustained'],
+                                           'frac_of_bf16_peak': fl / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
+                                           'includes': 'user-row pack + tcgen05 scoring + mask + top-100'}
+            del sc
+        del model
+    except Exception as ex:
+        out['eval_tc_cfg5'] = {'error': repr(ex)}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours_sharded(args, wl):
     """N > 1: the item-/user-sharded step (hassaku_b200/sharded.py) with a per-GPU batch of `train_batch_size` samples
     (weak scaling: global batch = N x 8192), NCCL all-to-all for the row / gradient exchanges."""
@@ -462,6 +540,9 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     eval_ms = (time.perf_counter() - t0) * 1e3 / n_eval
 
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras = run_extras(dev, flush)
     if rank != 0:
         return
     ab = algorithmic_bytes(U, I, d, B, N)
@@ -495,6 +576,7 @@ def run_ours(args, wl):
                  'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U, 'timing': 'host wall clock incl. the '
                  'single D2H sync of the sweep'},
         'final_loss': last_loss,
+        'extras': extras,
     }
     if not args.no_cpu_baseline:
         try:
@@ -514,6 +596,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the cfg4 / cfg5-shaped kernel measurements')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

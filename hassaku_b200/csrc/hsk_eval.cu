@@ -20,6 +20,8 @@ constexpr int TN = 128;    // items per tile
 constexpr int KC = 16;     // K chunk
 constexpr int KP = 20;     // padded smem row (floats): conflict-free 128-bit reads for the strided thread map
 constexpr int kEvalThreads = 256;
+constexpr int EV_KPL = 16;            // candidate keys per lane: 512-entry lists (a 256-entry list with k = 100 left only
+constexpr int EV_CAP = 32 * EV_KPL;   // 28 entries of slack per 128-item tile and was re-sorted at almost every tile)
 
 struct EvalArgs {
     const float* __restrict__ Uw;
@@ -37,7 +39,7 @@ struct EvalArgs {
     int64_t id_offset, id_stride;   // global item id of local row j = id_offset + j * id_stride
     int ld, Be, k;
     int n_tiles, tiles_per_split, n_splits;
-    uint64_t* cand;          // [n_splits, Be, kCap]
+    uint64_t* cand;          // [n_splits, Be, EV_CAP]
     float* out_scores;       // [Be, k]  (written directly when n_splits == 1)
     int32_t* out_ids;
     int32_t* status;
@@ -57,6 +59,17 @@ __device__ __forceinline__ void write_topk_row(const uint64_t* list, int k, floa
         out_s[e] = key ? key_score(key) : -INFINITY;
         out_i[e] = key_id(key);
     }
+}
+
+// out-of-line: the list cut (radix select + fallback sort network) is rare and large; inlined into the tile loop it also
+// made the compiler's unroller explode
+__device__ __noinline__ int ev_cut(uint64_t* list, int n, int n_checked, int k, int lane, const int32_t* __restrict__ excl,
+                                   int64_t lo, int64_t hi, float* new_tau, uint64_t* new_taukey) {
+    return warp_cut_list<EV_KPL>(list, n, n_checked, k, kCap - TN, lane, excl, lo, hi, new_tau, new_taukey);
+}
+__device__ __noinline__ void ev_final_sort(uint64_t* list, int n, int k, int lane) {
+    uint64_t thr;
+    warp_prune_list<kKeysPerLane>(list, n, k, lane, &thr);
 }
 
 __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs a) {
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
 
     const float gb = a.Gb ? a.Gb[0] : 0.f;
     const int nk = (a.ld + KC - 1) / KC;
-    const int prune_at = kCap - TN;  // a tile appends at most TN keys per row
+    const int prune_at = EV_CAP - TN;  // a tile appends at most TN keys per row
 
     for (int t = t_begin; t < t_end; ++t) {
         const int64_t n0 = (int64_t)t * TN;
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
             if (s_uoff[r] < 0) continue;
             const float tauf = s_tauf[r];
             const float ub = s_ubias[r];
-            uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * kCap;
+            uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * EV_CAP;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int64_t n = n0 + tx + 16 * j;
@@ -186,26 +199,30 @@ __global__ void __launch_bounds__(kEvalThreads, 2) eval_topk_f32_kernel(EvalArgs
         for (int r = warp; r < TM; r += kEvalThreads / 32) {
             if (s_uoff[r] < 0) {  // bad user index: leave an empty list for the merge
                 if (last && a.n_splits > 1 && m0 + r < a.Be) {
-                    uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * kCap;
+                    uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * EV_CAP;
                     for (int e = lane; e < a.k; e += 32) list[e] = 0ull;
                 }
                 continue;
             }
             const int n = s_cnt[r];
             if (n > prune_at || last) {
-                uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * kCap;
-                uint64_t thr;
-                const int nn = warp_prune_list_masked(list, n, s_checked[r], a.k, lane, &thr, a.excl_indices, s_ex_lo[r], s_ex_hi[r]);
+                uint64_t* list = a.cand + ((int64_t)split * a.Be + (m0 + r)) * EV_CAP;
+                float ntau;
+                uint64_t ntaukey;
+                const int total = ev_cut(list, n, s_checked[r], a.k, lane, a.excl_indices, s_ex_lo[r], s_ex_hi[r], &ntau, &ntaukey);
                 __syncwarp();
                 if (lane == 0) {
-                    s_cnt[r] = nn;
-                    s_checked[r] = nn;
-                    s_taukey[r] = thr;
-                    s_tauf[r] = thr ? key_score(thr) : -INFINITY;
+                    s_cnt[r] = total;
+                    s_checked[r] = total;
+                    s_taukey[r] = ntaukey;
+                    s_tauf[r] = ntau;
                 }
-                if (last && a.n_splits == 1) {
-                    __syncwarp();
-                    write_topk_row(list, a.k, a.out_scores + (int64_t)(m0 + r) * a.k, a.out_ids + (int64_t)(m0 + r) * a.k, lane);
+                if (last) {   // exact order, once: the <= 256 survivors through the 256-key network
+                    ev_final_sort(list, total, a.k, lane);
+                    if (a.n_splits == 1) {
+                        __syncwarp();
+                        write_topk_row(list, a.k, a.out_scores + (int64_t)(m0 + r) * a.k, a.out_ids + (int64_t)(m0 + r) * a.k, lane);
+                    }
                 }
             }
         }
@@ -405,7 +422,8 @@ static void eval_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_spli
     const int want = sm_count() * 2;
     int splits = 1;
     if (row_tiles < want) splits = (want + row_tiles - 1) / row_tiles;
-    const int max_splits = nt / 4 > 0 ? nt / 4 : 1;   // at least 4 item tiles per split
+    const int max_splits = nt / 16 > 0 ? nt / 16 : 1;   // at least 16 item tiles per split: every split re-pays the warm-up
+                                                        // of its running thresholds (the first ~3 tiles keep everything)
     if (splits > max_splits) splits = max_splits;
     if (splits > 64) splits = 64;
     const int tps = (nt + splits - 1) / splits;
@@ -428,7 +446,7 @@ extern "C" int64_t hsk_eval_topk_scratch_bytes(int Be, int64_t n_local_items, in
     (void)k;
     int nt, tps, ns;
     eval_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, &nt, &tps, &ns);
-    return (int64_t)ns * (Be > 0 ? Be : 1) * kCap * (int64_t)sizeof(uint64_t);
+    return (int64_t)ns * (Be > 0 ? Be : 1) * EV_CAP * (int64_t)sizeof(uint64_t);
 }
 
 extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const int64_t* u_rows, int64_t n_users_global,
@@ -452,7 +470,7 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const
     a.n_users = u_rows ? n_users_global : t->n_users; a.n_urows = t->n_users; a.n_local = t->n_items; a.id_offset = id_offset; a.id_stride = id_stride;
     a.ld = t->ld; a.Be = Be; a.k = k;
     eval_plan(Be, t->n_items, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
-    const int64_t need = (int64_t)a.n_splits * Be * kCap * (int64_t)sizeof(uint64_t);
+    const int64_t need = (int64_t)a.n_splits * Be * EV_CAP * (int64_t)sizeof(uint64_t);
     HSK_REQUIRE(scratch && scratch_bytes >= need, "hsk_eval_topk: scratch too small (%lld < %lld bytes)",
                 (long long)scratch_bytes, (long long)need);
     a.cand = reinterpret_cast<uint64_t*>(scratch);
@@ -462,7 +480,7 @@ extern "C" int hsk_eval_topk(const hsk_mf_tables* t, const int64_t* u_idx, const
     eval_topk_f32_kernel<<<grid, kEvalThreads, 0, s>>>(a);
     int rc = check_launch("hsk_eval_topk");
     if (rc) return rc;
-    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, kCap, k, top_scores, top_ids, s, nullptr, nullptr, nullptr, 0);
+    if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, EV_CAP, k, top_scores, top_ids, s, nullptr, nullptr, nullptr, 0);
     return rc;
 }
 

@@ -182,6 +182,80 @@ __device__ __forceinline__ int warp_prune_list_masked(uint64_t* list, int n, int
     return n < k ? n : k;
 }
 
+// Cut a CONTIGUOUS candidate list (n <= 32 * KPL keys) back to ~k without sorting: exclusion test of the entries beyond
+// n_checked (lock-step binary searches), radix select on the 16 most significant key bits for the largest prefix T with
+// count(prefix >= T) >= k, compaction of the survivors (k plus the ties of bucket T) to list[0..total).  The new
+// threshold is the lower edge of bucket T — conservative, the exact order is established once by the final sort.
+// If the tie bucket is huge (degenerate scores) the cut falls back to the exact sort and keeps exactly k, with the
+// exact k-th key as threshold.  Returns the number of survivors (<= max_keep).
+template <int KPL>
+__device__ __forceinline__ int warp_cut_list(uint64_t* list, int n, int n_checked, int k, int max_keep, int lane,
+                                             const int32_t* __restrict__ excl, int64_t lo, int64_t hi, float* new_tau,
+                                             uint64_t* new_taukey) {
+    uint64_t key[KPL];
+    bool unchecked[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int e = r * 32 + lane;
+        key[r] = (e < n) ? list[e] : 0ull;
+        unchecked[r] = e >= n_checked && e < n;
+    }
+    if (hi > lo) {
+        int32_t id[KPL];
+        bool found[KPL];
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) id[r] = key_id(key[r]);
+        csr_contains_many<KPL>(excl, lo, hi, id, unchecked, found);
+#pragma unroll
+        for (int r = 0; r < KPL; ++r)
+            if (found[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
+    }
+    uint32_t T = 0;
+    if (n > k) {
+        uint32_t pre[KPL];
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) pre[r] = (uint32_t)(key[r] >> 48);
+#pragma unroll 1
+        for (int b = 15; b >= 0; --b) {
+            const uint32_t cand = T | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) c += (pre[r] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= k) T = cand;
+        }
+    }
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) mine += (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (total > max_keep) {
+        warp_sort_desc<KPL>(key, lane);
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+            const int e = r * 32 + lane;
+            if (e < k) list[e] = key[r];
+        }
+        const uint64_t thr = warp_list_at<KPL>(key, k - 1);
+        *new_taukey = thr;
+        *new_tau = key_score(thr);
+        return k;
+    }
+    int pos = incl - mine;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r)
+        if (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) list[pos++] = key[r];
+    *new_tau = (n > k) ? from_orderable(T << 16) : -INFINITY;
+    *new_taukey = (n > k) ? ((uint64_t)(T << 16) << 32) : 0ull;
+    return total;
+}
+
 // hsk_eval.cu: merge of n_lists sorted key lists per row laid out [list][row][stride] (split plans of the eval kernels)
 int launch_merge_keys(const uint64_t* lists, int n_lists, int rows, int stride, int k, float* out_scores, int32_t* out_ids, cudaStream_t s,
                       const float* Ub, const float* Gb, const int64_t* u_idx, int64_t n_users);
