@@ -327,13 +327,13 @@ def run_ours_sharded(args, wl):
         torch.cuda.synchronize()
 
     for s in range(W):
-        smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd)
+        smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as clk:
         a.record()
         for s in range(K):
-            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd)
+            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
         b.record()
         barrier()
     t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -347,7 +347,8 @@ def run_ours_sharded(args, wl):
     barrier()
     a2.record()
     for s in range(K):
-        smf.step(u_pin[s % 8].to(dev, non_blocking=True), i_pin[s % 8].to(dev, non_blocking=True), Bg, loss, shift, lr, wd)
+        smf.step(u_pin[s % 8].to(dev, non_blocking=True), i_pin[s % 8].to(dev, non_blocking=True), Bg, loss, shift, lr, wd,
+                 exchange=args.exchange)
     loss_host = smf.pop_loss()
     b2.record()
     barrier()
@@ -368,7 +369,7 @@ def run_ours_sharded(args, wl):
         peak, peak_src = measured_peaks()
         triples = Bg * N
         cfg = workload_config(args.workload, wl, U, I)
-        cfg.update({'parallelism': f'item+user row-sharded x{world}, NCCL all-to-all', 'global_batch': Bg,
+        cfg.update({'parallelism': f'item+user row-sharded x{world}, NCCL ({args.exchange} exchange)', 'global_batch': Bg,
                     'l2': 'not flushed (back to back); tables are L2-resident'})
         line = {'metric': 'BPR-MF train triples/s', 'value': triples * K / (ms * 1e-3), 'unit': 'triples/s', 'n_gpus': world,
                 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
@@ -385,7 +386,9 @@ def run_ours_sharded(args, wl):
                 'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
                          'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U},
                 'final_loss': last_loss}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    smf.close()
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -600,6 +603,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
+    ap.add_argument('--exchange', default='dense_graph', choices=['auto', 'dense', 'dense_graph', 'sparse'],
+                    help='N > 1: item-row exchange of the sharded step')
     ap.add_argument('--no-extras', action='store_true', help='skip the cfg4 / cfg5-shaped kernel measurements')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

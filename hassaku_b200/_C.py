@@ -49,6 +49,9 @@ def _declare(lib):
         'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
         'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
+        'hsk_debug_eval_tc_profile': (None, [vp]),
+        'hsk_adamw_consts': (i32, [f64, f64, f64, f64, f64, i64, vp]),
+        'hsk_adamw_dense_graph': (i32, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]),
         'hsk_eval_topk_scratch_bytes': (i64, [i32, i64, i32]),
         'hsk_eval_topk': (i32, [T, vp, vp, i64, i32, i64, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
         'hsk_eval_tc_kpad': (i32, [i32, i32]),
@@ -191,6 +194,21 @@ def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arit
         raise HskError('adamw_dense: p, m, v, g must have the same number of elements')
     _check(lib().hsk_adamw_dense(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, lr, beta1, beta2, eps,
                                  weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')
+
+
+def adamw_consts(lr, beta1, beta2, eps, weight_decay, step: int, out_host: torch.Tensor):
+    """Fill the 8 fp32 step scalars into a (pinned) HOST tensor."""
+    if out_host.is_cuda or out_host.dtype != torch.float32 or out_host.numel() < 8:
+        raise HskError('adamw_consts: out_host must be a host fp32 tensor with >= 8 elements')
+    _check(lib().hsk_adamw_consts(lr, beta1, beta2, eps, weight_decay, step, out_host.data_ptr()), 'hsk_adamw_consts')
+
+
+def adamw_dense_graph(p, m, v, g, consts_dev, decoupled: bool = True, adam_l2: bool = False, zero_grad: bool = True):
+    for n, t in (('p', p), ('m', m), ('v', v), ('g', g), ('consts_dev', consts_dev)):
+        _req(t, torch.float32, n)
+    _check(lib().hsk_adamw_dense_graph(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), p.numel(),
+                                       consts_dev.data_ptr(), int(decoupled), int(adam_l2), int(zero_grad), _stream()),
+           'hsk_adamw_dense_graph')
 
 
 def sample_negatives(u_idx, pos_idx, n_neg: int, n_items: int, n_users: int, csr_indptr, csr_indices, seed: int,

@@ -82,7 +82,81 @@ __global__ void __launch_bounds__(256) adamw_dense_kernel(float* __restrict__ p,
     }
 }
 
+// Same update with the step-dependent scalars read from DEVICE memory, so that the launch can be captured once in a CUDA
+// graph and replayed for every step (the host rewrites the 8 floats before each replay).
+template <int ARITH, bool L2, bool DECAY, bool ZERO>
+__global__ void __launch_bounds__(256) adamw_dense_devc_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                               float* __restrict__ v, float* __restrict__ g, int64_t n,
+                                                               const AdamConsts* __restrict__ cp) {
+    const AdamConsts c = *cp;
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P = p4[i], M = m4[i], V = v4[i], G = __ldcs(g4 + i);
+        adam_elem<ARITH, L2, DECAY>(P.x, M.x, V.x, G.x, c);
+        adam_elem<ARITH, L2, DECAY>(P.y, M.y, V.y, G.y, c);
+        adam_elem<ARITH, L2, DECAY>(P.z, M.z, V.z, G.z, c);
+        adam_elem<ARITH, L2, DECAY>(P.w, M.w, V.w, G.w, c);
+        p4[i] = P; m4[i] = M; v4[i] = V;
+        if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float P = p[t], M = m[t], V = v[t], G = g[t];
+        adam_elem<ARITH, L2, DECAY>(P, M, V, G, c);
+        p[t] = P; m[t] = M; v[t] = V;
+        if (ZERO) g[t] = 0.f;
+    }
+}
+
+static void fill_consts(AdamConsts& c, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step) {
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    c.decay = (float)(1.0 - lr * weight_decay);
+    c.wd = (float)weight_decay;
+    c.w1 = (float)(1.0 - beta1);
+    c.beta2 = (float)beta2;
+    c.w2 = (float)(1.0 - beta2);
+    c.sqrt_bc2 = (float)sqrt(bc2);
+    c.eps = (float)eps;
+    c.step_size = (float)(-(lr / bc1));
+}
+
 }  // namespace hsk
+
+// host helper: the 8 fp32 scalars of one step (what hsk_adamw_dense computes internally), for hsk_adamw_dense_graph
+extern "C" int hsk_adamw_consts(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                                float* out8 /* HOST */) {
+    HSK_REQUIRE(out8 && step >= 1, "hsk_adamw_consts: bad arguments");
+    hsk::AdamConsts c;
+    hsk::fill_consts(c, lr, beta1, beta2, eps, weight_decay, step);
+    memcpy(out8, &c, sizeof(c));
+    return HSK_OK;
+}
+
+extern "C" int hsk_adamw_dense_graph(float* p, float* m, float* v, float* g, int64_t n, const float* consts_dev,
+                                     int decoupled_decay, int adam_l2, int zero_grad, hsk_stream_t stream) {
+    using namespace hsk;
+    HSK_REQUIRE(p && m && v && g && consts_dev, "hsk_adamw_dense_graph: null pointer");
+    HSK_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g) && aligned16(consts_dev), "hsk_adamw_dense_graph: pointers must be 16-byte aligned");
+    if (n <= 0) return HSK_OK;
+    const int threads = 256;
+    int64_t want = ((n >> 2) + threads - 1) / threads;
+    if (want < 1) want = 1;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const int blocks = (int)(want < cap ? want : cap);
+    cudaStream_t s = as_stream(stream);
+    const AdamConsts* cp = reinterpret_cast<const AdamConsts*>(consts_dev);
+#define HSK_LAUNCH_ADAMG(L, D, Z) adamw_dense_devc_kernel<0, L, D, Z><<<blocks, threads, 0, s>>>(p, m, v, g, n, cp)
+    if (adam_l2) { if (zero_grad) HSK_LAUNCH_ADAMG(true, false, true); else HSK_LAUNCH_ADAMG(true, false, false); }
+    else if (decoupled_decay) { if (zero_grad) HSK_LAUNCH_ADAMG(false, true, true); else HSK_LAUNCH_ADAMG(false, true, false); }
+    else { if (zero_grad) HSK_LAUNCH_ADAMG(false, false, true); else HSK_LAUNCH_ADAMG(false, false, false); }
+    return check_launch("hsk_adamw_dense_graph");
+}
 
 extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, double lr, double beta1,
                                double beta2, double eps, double weight_decay, int64_t step, int arith, int adam_l2,
@@ -95,17 +169,8 @@ extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n
     HSK_REQUIRE(arith == 0 || arith == 1, "hsk_adamw_dense: arith must be 0 (cuda foreach) or 1 (cpu single-tensor)");
     if (n == 0) return HSK_OK;
     // python-double scalar bookkeeping exactly as torch/optim/adam.py does it, then one rounding to fp32
-    const double bc1 = 1.0 - pow(beta1, (double)step);
-    const double bc2 = 1.0 - pow(beta2, (double)step);
     AdamConsts c;
-    c.decay = (float)(1.0 - lr * weight_decay);
-    c.wd = (float)weight_decay;
-    c.w1 = (float)(1.0 - beta1);
-    c.beta2 = (float)beta2;
-    c.w2 = (float)(1.0 - beta2);
-    c.sqrt_bc2 = (float)sqrt(bc2);
-    c.eps = (float)eps;
-    c.step_size = (float)(-(lr / bc1));
+    fill_consts(c, lr, beta1, beta2, eps, weight_decay, step);
     const bool l2 = adam_l2 != 0 && weight_decay != 0.0;
     const bool decay = adam_l2 == 0 && weight_decay != 0.0;
     const int threads = 256;

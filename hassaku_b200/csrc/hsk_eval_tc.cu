@@ -617,7 +617,7 @@ static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split,
 using namespace hsk;
 
 static unsigned long long* g_tc_prof = nullptr;   // measurement hook, not part of the public header
-extern "C" __attribute__((visibility("default"))) void hsk_debug_eval_tc_profile(unsigned long long* dev_counters) { g_tc_prof = dev_counters; }
+extern "C" void hsk_debug_eval_tc_profile(unsigned long long* dev_counters) { g_tc_prof = dev_counters; }
 
 extern "C" int hsk_eval_tc_kpad(int d, int precision) {
     const int per_kb = (precision == HSK_PREC_TF32) ? 32 : 64;

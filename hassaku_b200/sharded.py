@@ -254,11 +254,95 @@ class ShardedMF:
         self.t += 1
         self.ops.adamw(self.arena, self.m, self.v, self.g, lr, wd, self.t, decoupled)
 
+    # ---- the dense step as ONE CUDA graph (fixed shapes): removes ~20 launches / collectives worth of host latency ----
+    CONST_TABLE_STEPS = 4096
+
+    def _dense_body(self, u_global, i_global, B_global, loss_kind, neg_shift, consts_dev, decoupled):
+        """train_step_dense with the AdamW scalars read from device memory (capturable)."""
+        G, lay = self.spec.world, self.layout
+        ld, nl = lay.ld, lay.n_items
+        D = self._dense_buffers()
+        cap = D['cap']
+        _, _, _, Ib, _ = lay.views(self.arena)
+        D['Vpad'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
+        dist.all_gather_into_tensor(D['V'], D['Vpad'], group=self.group)
+        if Ib is not None:
+            D['Ibpad'][:nl] = Ib.view(-1)
+            dist.all_gather_into_tensor(D['Ib'], D['Ibpad'], group=self.group)
+        rows = (i_global % G) * cap + torch.div(i_global, G, rounding_mode='floor')
+        u_local = torch.div(u_global, G, rounding_mode='floor')
+        D['gV'].zero_()
+        D['gIb'].zero_()
+        self.ops.train_fused(lay, self.arena, self.g, D['V'], D['Ib'] if Ib is not None else None, D['gV'],
+                             D['gIb'] if Ib is not None else None, u_local, rows.contiguous(), B_global,
+                             _C.LOSS_KINDS[loss_kind], neg_shift, self.loss_accum)
+        self._reduce_scatter(D['gVpad'], D['gV'])
+        self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['gVpad'][:nl])
+        if Ib is not None:
+            self._reduce_scatter(D['gIbpad'], D['gIb'])
+            lay.views(self.g)[3].view(-1).add_(D['gIbpad'][:nl])
+        gGb = lay.views(self.g)[4]
+        if gGb is not None:
+            dist.all_reduce(gGb, group=self.group)
+        _C.adamw_dense_graph(self.arena, self.m, self.v, self.g, consts_dev, decoupled=decoupled, adam_l2=not decoupled)
+
+    def _fill_const_table(self, gs, lr, wd):
+        host = torch.empty((self.CONST_TABLE_STEPS, 8), dtype=torch.float32).pin_memory()
+        for j in range(self.CONST_TABLE_STEPS):
+            _C.adamw_consts(lr, 0.9, 0.999, 1e-8, wd, self.t + 1 + j, host[j])
+        gs['table'].copy_(host)
+        gs['step_idx'].zero_()
+        gs['table_base_t'] = self.t
+
+    def train_step_dense_graphed(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled=True):
+        """train_step_dense captured once per (batch shape, hyper-parameters) and replayed.  The per-step AdamW scalars
+        come from a device table of the next CONST_TABLE_STEPS steps indexed by a device-side step counter, so a replay
+        needs no host-computed kernel argument."""
+        key = (tuple(i_global.shape), B_global, loss_kind, float(neg_shift), float(lr), float(wd), bool(decoupled))
+        gs = getattr(self, '_graph_state', None)
+        if gs is None or gs['key'] != key:
+            dev = self.device
+            gs = {'key': key, 'u': torch.empty_like(u_global, device=dev), 'i': torch.empty_like(i_global, device=dev),
+                  'table': torch.empty((self.CONST_TABLE_STEPS, 8), dtype=torch.float32, device=dev),
+                  'consts': torch.empty(8, dtype=torch.float32, device=dev),
+                  'step_idx': torch.zeros(1, dtype=torch.int64, device=dev)}
+            self._fill_const_table(gs, lr, wd)
+            # NCCL channels for these collectives must exist before capture: warm them up on scratch buffers
+            D = self._dense_buffers()
+            dist.all_gather_into_tensor(D['gV'], D['gVpad'], group=self.group)
+            self._reduce_scatter(D['gVpad'], D['gV'])
+            dist.all_gather_into_tensor(D['gIb'], D['gIbpad'], group=self.group)
+            self._reduce_scatter(D['gIbpad'], D['gIb'])
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                torch.index_select(gs['table'], 0, gs['step_idx'], out=gs['consts'].view(1, 8))
+                self._dense_body(gs['u'], gs['i'], B_global, loss_kind, neg_shift, gs['consts'], decoupled)
+                gs['step_idx'].add_(1)
+            gs['graph'] = graph
+            self._graph_state = gs
+        if self.t - gs['table_base_t'] >= self.CONST_TABLE_STEPS:
+            torch.cuda.current_stream().synchronize()
+            self._fill_const_table(gs, lr, wd)
+        gs['u'].copy_(u_global, non_blocking=True)
+        gs['i'].copy_(i_global, non_blocking=True)
+        gs['graph'].replay()
+        self.t += 1
+
+    def close(self):
+        """Drop the captured CUDA graphs (they hold NCCL work): call before dist.destroy_process_group(), which
+        otherwise blocks."""
+        torch.cuda.synchronize()
+        self._graph_state = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def step(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled=True, exchange='auto'):
         """Dispatch on the expected fraction of distinct items: dense exchange when the batch covers the item table."""
         if exchange == 'auto':
             exchange = 'dense' if i_global.numel() >= 2 * self.spec.n_items // self.spec.world else 'sparse'
-        fn = self.train_step_dense if exchange == 'dense' else self.train_step
+        fn = {'dense': self.train_step_dense, 'dense_graph': self.train_step_dense_graphed, 'sparse': self.train_step}[exchange]
         return fn(u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled)
 
     def pop_loss(self) -> float:

@@ -189,6 +189,19 @@ HSK_API int hsk_rank_metrics_dense(const int32_t* top_ids, int Be, int k_max, co
                                    const int32_t* user_group, int n_groups, const float* discount, float* per_user,
                                    double* sums, int64_t* counts, hsk_stream_t stream);
 
+/* ---- measurement hook (scripts/kbench.py): if set to a device array of 16 uint64, hsk_eval_topk_tc adds the cycle counts
+ * of its epilogue phases and list-cut sub-phases to it; NULL (default) disables the counters. */
+HSK_API void hsk_debug_eval_tc_profile(unsigned long long* dev_counters);
+
+/* ---- CUDA-graph friendly AdamW: the step-dependent scalars live in device memory --------------------------------------
+ * hsk_adamw_consts fills 8 fp32 (HOST) for step `step`; the caller copies them to `consts_dev` (captured as a memcpy
+ * node from pinned memory) and hsk_adamw_dense_graph applies exactly the arithmetic of hsk_adamw_dense(arith = 0) with
+ * them, so one captured graph serves every step.  decoupled_decay / adam_l2 select AdamW / Adam(L2) / plain Adam. */
+HSK_API int hsk_adamw_consts(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                             float* out8 /* host */);
+HSK_API int hsk_adamw_dense_graph(float* p, float* m, float* v, float* g, int64_t n, const float* consts_dev,
+                                  int decoupled_decay, int adam_l2, int zero_grad, hsk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,12 +46,12 @@ def _worker(rank, world, port, out_dir):
         smf = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
         smf.load_full_state_dict(sd0)
         rng = np.random.RandomState(9)
-        for s in range(2):
+        for s in range(4):
             u = torch.from_numpy(rng.randint(0, U, B).astype(np.int64))
             i = torch.from_numpy(rng.randint(0, I, (B, N + 1)).astype(np.int64))
             step(u, i)
             ul, il = partition_batch_by_user_owner(u.to(dev), i.to(dev), world, rank)
-            smf.step(ul, il, B, 'bpr', 0.0, lr, wd, exchange='sparse' if s == 0 else 'dense')
+            smf.step(ul, il, B, 'bpr', 0.0, lr, wd, exchange=('sparse', 'dense', 'dense', 'dense')[s])
             l_single, l_sh = step.pop_loss_sum(), smf.pop_loss()
             assert abs(l_single - l_sh) <= 1e-5 * abs(l_single), (l_single, l_sh)
         sd = smf.full_state_dict()
@@ -83,4 +83,47 @@ def _worker(rank, world, port, out_dir):
 @pytest.mark.parametrize('world', [2])
 def test_sharded_step_and_eval_match_single_gpu(world, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()
+
+
+def _worker_graph(rank, world, port, out_dir):
+    """The CUDA-graph replay of the dense step equals the eager dense step (fixed local batch shape)."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+        from hassaku_b200.sharded import ShardedMF
+        U, I, d, B, N = 801, 507, 128, 256, 10
+        dev = torch.device('cuda', rank)
+        torch.manual_seed(5)
+        full = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+        with torch.no_grad():
+            for p in full.parameters():
+                p.copy_(torch.randn_like(p) * (1 / math.sqrt(d) if p.shape[-1] == d else 0.1))
+        a = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+        b = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+        a.load_full_state_dict(full.state_dict()); b.load_full_state_dict(full.state_dict())
+        rng = np.random.RandomState(rank)
+        for s in range(5):
+            u = torch.from_numpy((rng.randint(0, (U - rank + world - 1) // world, B) * world + rank).astype(np.int64)).to(dev)
+            i = torch.from_numpy(rng.randint(0, I, (B, N + 1)).astype(np.int64)).to(dev)
+            a.step(u, i, B * world, 'bpr', 0.0, 1e-3, 1e-4, exchange='dense')
+            b.step(u, i, B * world, 'bpr', 0.0, 1e-3, 1e-4, exchange='dense_graph')
+        torch.cuda.synchronize()
+        assert a.t == b.t == 5
+        assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v)
+        err = float((a.arena - b.arena).abs().max() / a.arena.abs().max())
+        assert err < 1e-6, err     # atomics order differs run to run; the arithmetic is identical
+        assert abs(a.pop_loss() - b.pop_loss()) < 1e-9
+        b.close()
+        if rank == 0:
+            open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+def test_graphed_dense_step_matches_eager(tmp_path):
+    mp.spawn(_worker_graph, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / 'ok').exists()
