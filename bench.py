@@ -249,6 +249,48 @@ def run_extras(dev, flush):
         del p, m, v, g
     except Exception as ex:
         out['adamw_cfg4'] = {'error': repr(ex)}
+    try:   # cfg4-shaped train step on one GPU: dense (torch-faithful) vs lazy (row-sparse) AdamW, reported separately
+        from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+        from hassaku_b200.train.optim import DenseAdam
+        U4, I4, d4, B4, N4 = 2_000_000, 1_000_000, 128, 8192, 50
+
+        class _M:   # arena-only stand-in for the model (random-init weights of the cfg4 architecture, built on the device)
+            pass
+        mdl = _M()
+        mdl.layout = ArenaLayout(U4, I4, d4, False, True, False)
+        mdl.arena = torch.randn(mdl.layout.n_total, device=dev) * (0.1 / d4)
+        mdl.parameters = lambda: [torch.nn.Parameter(mdl.arena[:4])]
+        tabs = mdl.layout.tables(mdl.arena)
+        gen = torch.Generator(device=dev); gen.manual_seed(0)
+        ub = [torch.randint(0, U4, (B4,), device=dev, generator=gen) for _ in range(4)]
+        ib = [torch.randint(0, I4, (B4, N4 + 1), device=dev, generator=gen) for _ in range(4)]
+        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        res4 = {}
+        for mode in ('dense', 'lazy'):
+            opt4 = DenseAdam(mdl, lr=3e-4, weight_decay=4e-5, mode=mode)
+            kk = [0]
+
+            def st():
+                j = kk[0] % 4
+                kk[0] += 1
+                _C.mf_train_fused(tabs, opt4.grad_tables, ub[j], ib[j], 0, 0.0, acc)
+                if mode == 'lazy':
+                    opt4.mark(ub[j], ib[j])
+                opt4.step_fused()
+            st(); st()
+            ms = timed(st, 6)
+            ab4 = algorithmic_bytes(U4, I4, d4, B4, N4)
+            res4[mode] = {'ms_per_step': ms, 'triples_per_s': B4 * N4 / (ms * 1e-3)}
+            if mode == 'dense':
+                res4[mode].update({'algorithmic_bytes': ab4['total'], 'achieved_gbs': ab4['total'] / (ms * 1e-3) / 1e9,
+                                   'frac_of_hbm_peak': ab4['total'] / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']})
+            del opt4
+        out['train_cfg4_1gpu'] = dict(res4, shape={'n_users': U4, 'n_items': I4, 'd': d4, 'B': B4, 'N': N4},
+                                      note='lazy = row-sparse AdamW (different trajectory from torch.optim.AdamW), reported separately')
+        del mdl, tabs
+    except Exception as ex:
+        out['train_cfg4_1gpu'] = {'error': repr(ex)}
+    torch.cuda.empty_cache()
     try:
         import math
         from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization

@@ -49,6 +49,8 @@ def _declare(lib):
         'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
         'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
+        'hsk_mark_touched': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, vp]),
+        'hsk_adamw_rows_lazy': (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, f64, f64, f64, f64, f64, i64, vp]),
         'hsk_debug_eval_tc_profile': (None, [vp]),
         'hsk_adamw_consts': (i32, [f64, f64, f64, f64, f64, i64, vp]),
         'hsk_adamw_dense_graph': (i32, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]),
@@ -194,6 +196,23 @@ def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arit
         raise HskError('adamw_dense: p, m, v, g must have the same number of elements')
     _check(lib().hsk_adamw_dense(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, lr, beta1, beta2, eps,
                                  weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')
+
+
+def mark_touched(u_idx, i_idx, n_users: int, n_items: int, touched_users, touched_items):
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx')
+    _req(touched_users, torch.uint8, 'touched_users'); _req(touched_items, torch.uint8, 'touched_items')
+    B, N1 = i_idx.shape
+    _check(lib().hsk_mark_touched(u_idx.data_ptr(), i_idx.data_ptr(), B, N1, n_users, n_items, touched_users.data_ptr(),
+                                  touched_items.data_ptr(), _stream()), 'hsk_mark_touched')
+
+
+def adamw_rows_lazy(p2d, m2d, v2d, g2d, touched, lr, beta1, beta2, eps, weight_decay, step: int, bias=None):
+    """p2d/m2d/v2d/g2d: [rows, ld] fp32 views with the same padded leading dimension; bias: optional (p, m, v, g) vectors."""
+    _req(touched, torch.uint8, 'touched')
+    pb, mb, vb, gb = bias if bias is not None else (None, None, None, None)
+    _check(lib().hsk_adamw_rows_lazy(p2d.data_ptr(), m2d.data_ptr(), v2d.data_ptr(), g2d.data_ptr(), p2d.shape[0],
+                                     p2d.stride(0), _ptr(pb), _ptr(mb), _ptr(vb), _ptr(gb), touched.data_ptr(), lr, beta1,
+                                     beta2, eps, weight_decay, step, _stream()), 'hsk_adamw_rows_lazy')
 
 
 def adamw_consts(lr, beta1, beta2, eps, weight_decay, step: int, out_host: torch.Tensor):

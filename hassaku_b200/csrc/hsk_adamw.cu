@@ -189,3 +189,91 @@ extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n
     if (arith == 0) { HSK_ADAM_LD(0) } else { HSK_ADAM_LD(1) }
     return check_launch("hsk_adamw_dense");
 }
+
+// ---- row-sparse "lazy" AdamW (north_star item 2, reported separately from the dense, torch-faithful mode) ------------
+// Only rows that received a gradient in this step are updated (p, m, v) — the semantics of torch.optim.SparseAdam plus
+// decoupled weight decay on the touched rows; untouched rows keep p, m, v unchanged (no decay, no momentum tail), which
+// is a different trajectory from dense AdamW.  Bytes: 28 B per TOUCHED element + 1 flag byte per row,
+// instead of 28 B per parameter: at cfg4 (2 M x 1 M x 128) a step touches ~0.35 M of 3 M rows.
+namespace hsk {
+
+__global__ void __launch_bounds__(256) mark_touched_kernel(const int64_t* __restrict__ u_idx, const int64_t* __restrict__ i_idx,
+                                                           int64_t B, int64_t BN1, int64_t n_users, int64_t n_items,
+                                                           uint8_t* __restrict__ tu, uint8_t* __restrict__ ti) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < BN1; e += stride) {
+        const int64_t it = i_idx[e];
+        if (!bad_index(it, n_items)) ti[it] = 1;
+        if (e < B) {
+            const int64_t u = u_idx[e];
+            if (!bad_index(u, n_users)) tu[u] = 1;
+        }
+    }
+}
+
+// one warp per row; bias (nullable) is the length-n_rows vector that shares the row index (item_bias / user_bias)
+template <bool DECAY>
+__global__ void __launch_bounds__(256) adamw_rows_lazy_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                              float* __restrict__ g, int64_t n_rows, int ld,
+                                                              float* __restrict__ pb, float* __restrict__ mb, float* __restrict__ vb,
+                                                              float* __restrict__ gb, uint8_t* __restrict__ touched, AdamConsts c) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = ld >> 2;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * 8) {
+        if (!touched[r]) continue;
+        float4* p4 = reinterpret_cast<float4*>(p + r * ld);
+        float4* m4 = reinterpret_cast<float4*>(m + r * ld);
+        float4* v4 = reinterpret_cast<float4*>(v + r * ld);
+        float4* g4 = reinterpret_cast<float4*>(g + r * ld);
+        for (int k = lane; k < nvec; k += 32) {
+            float4 P = p4[k], M = m4[k], V = v4[k], G = g4[k];
+            adam_elem<0, false, DECAY>(P.x, M.x, V.x, G.x, c);
+            adam_elem<0, false, DECAY>(P.y, M.y, V.y, G.y, c);
+            adam_elem<0, false, DECAY>(P.z, M.z, V.z, G.z, c);
+            adam_elem<0, false, DECAY>(P.w, M.w, V.w, G.w, c);
+            p4[k] = P; m4[k] = M; v4[k] = V;
+            g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pb && lane == 0) {
+            float P = pb[r], M = mb[r], V = vb[r], G = gb[r];
+            adam_elem<0, false, DECAY>(P, M, V, G, c);
+            pb[r] = P; mb[r] = M; vb[r] = V; gb[r] = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) touched[r] = 0;
+    }
+}
+
+}  // namespace hsk
+
+extern "C" int hsk_mark_touched(const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t n_users, int64_t n_items,
+                                uint8_t* touched_users, uint8_t* touched_items, hsk_stream_t stream) {
+    HSK_REQUIRE(u_idx && i_idx && touched_users && touched_items, "hsk_mark_touched: null pointer");
+    if (B <= 0) return HSK_OK;
+    const int64_t n = (int64_t)B * N1;
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)hsk::sm_count() * 8;
+    hsk::mark_touched_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, hsk::as_stream(stream)>>>(u_idx, i_idx, B, n, n_users, n_items,
+                                                                                                 touched_users, touched_items);
+    return hsk::check_launch("hsk_mark_touched");
+}
+
+extern "C" int hsk_adamw_rows_lazy(float* p, float* m, float* v, float* g, int64_t n_rows, int ld, float* p_bias, float* m_bias,
+                                   float* v_bias, float* g_bias, uint8_t* touched, double lr, double beta1, double beta2,
+                                   double eps, double weight_decay, int64_t step, hsk_stream_t stream) {
+    using namespace hsk;
+    HSK_REQUIRE(p && m && v && g && touched, "hsk_adamw_rows_lazy: null pointer");
+    HSK_REQUIRE(ld >= 4 && (ld % 4) == 0 && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), "hsk_adamw_rows_lazy: rows must be 16-byte aligned with ld %% 4 == 0");
+    HSK_REQUIRE(step >= 1 && n_rows >= 0, "hsk_adamw_rows_lazy: bad step / row count");
+    HSK_REQUIRE((p_bias == nullptr) == (m_bias == nullptr) && (p_bias == nullptr) == (v_bias == nullptr) && (p_bias == nullptr) == (g_bias == nullptr),
+                "hsk_adamw_rows_lazy: bias p/m/v/g must be given together");
+    if (n_rows == 0) return HSK_OK;
+    AdamConsts c;
+    fill_consts(c, lr, beta1, beta2, eps, weight_decay, step);
+    int64_t blocks = (n_rows + 7) / 8, cap = (int64_t)sm_count() * 16;
+    const int nb = (int)(blocks < cap ? blocks : cap);
+    if (weight_decay != 0.0)
+        adamw_rows_lazy_kernel<true><<<nb, 256, 0, as_stream(stream)>>>(p, m, v, g, n_rows, ld, p_bias, m_bias, v_bias, g_bias, touched, c);
+    else
+        adamw_rows_lazy_kernel<false><<<nb, 256, 0, as_stream(stream)>>>(p, m, v, g, n_rows, ld, p_bias, m_bias, v_bias, g_bias, touched, c);
+    return check_launch("hsk_adamw_rows_lazy");
+}

@@ -12,11 +12,16 @@ class DenseAdam(torch.optim.Optimizer):
     (the reference always passes conf['wd'])."""
 
     def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
-                 decoupled: bool = True, arith: int = 0):
+                 decoupled: bool = True, arith: int = 0, mode: str = 'dense'):
         self.model = model
         super().__init__(list(model.parameters()),
                          dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, decoupled=decoupled))
         self.arith = arith
+        if mode not in ('dense', 'lazy'):
+            raise ValueError("optimizer_mode must be 'dense' (torch-faithful) or 'lazy' (row-sparse)")
+        if mode == 'lazy' and not decoupled:
+            raise ValueError('lazy mode is defined for AdamW (decoupled decay) only')
+        self.mode = mode
         self.t = 0
         self._alloc()
 
@@ -28,16 +33,49 @@ class DenseAdam(torch.optim.Optimizer):
         self.v = torch.zeros_like(arena)
         self.g = torch.zeros_like(arena)
         self.grad_tables = self.model.layout.tables(self.g)
+        if self.mode == 'lazy':
+            lay = self.model.layout
+            self.touched_users = torch.zeros(lay.n_users, dtype=torch.uint8, device=arena.device)
+            self.touched_items = torch.zeros(lay.n_items, dtype=torch.uint8, device=arena.device)
 
     @property
     def grad_views(self):
         """(gU, gV, gUb, gIb, gGb) views of the dense gradient arena, shaped like the parameters."""
         return self.model.layout.views(self.g)
 
+    def mark(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor):
+        """lazy mode: remember which rows this batch touches (call before step_fused)."""
+        lay = self.model.layout
+        _C.mark_touched(u_idxs, i_idxs, lay.n_users, lay.n_items, self.touched_users, self.touched_items)
+
+    def _step_lazy(self, grp):
+        lay, arena = self.model.layout, self.model.arena
+
+        def t2d(a, off, rows):
+            return a[off:off + rows * lay.ld].view(rows, lay.ld)
+
+        def vec(a, off, rows):
+            return a[off:off + rows] if off >= 0 else None
+
+        for off_t, off_b, rows, touched in ((lay.off_U, lay.off_Ub, lay.n_users, self.touched_users),
+                                            (lay.off_V, lay.off_Ib, lay.n_items, self.touched_items)):
+            bias = None
+            if off_b >= 0:
+                bias = tuple(vec(a, off_b, rows) for a in (arena, self.m, self.v, self.g))
+            _C.adamw_rows_lazy(t2d(arena, off_t, rows), t2d(self.m, off_t, rows), t2d(self.v, off_t, rows),
+                               t2d(self.g, off_t, rows), touched, grp['lr'], grp['betas'][0], grp['betas'][1], grp['eps'],
+                               grp['weight_decay'], self.t, bias=bias)
+        if lay.off_Gb >= 0:   # the global bias is touched by every sample: plain dense update of that one element
+            sl = slice(lay.off_Gb, lay.off_Gb + 4)
+            _C.adamw_dense(arena[sl], self.m[sl], self.v[sl], self.g[sl], grp['lr'], grp['betas'][0], grp['betas'][1],
+                           grp['eps'], grp['weight_decay'], self.t, arith=self.arith, zero_grad=True)
+
     def step_fused(self):
         """One optimizer step consuming the gradient arena `self.g` (filled by hsk_mf_train_fused)."""
         grp = self.param_groups[0]
         self.t += 1
+        if self.mode == 'lazy':
+            return self._step_lazy(grp)
         _C.adamw_dense(self.model.arena, self.m, self.v, self.g, grp['lr'], grp['betas'][0], grp['betas'][1],
                        grp['eps'], grp['weight_decay'], self.t, arith=self.arith, adam_l2=not grp['decoupled'],
                        zero_grad=True)

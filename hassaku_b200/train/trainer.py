@@ -46,8 +46,9 @@ class Trainer:
         self.lr, self.wd = conf['lr'], conf['wd']
         if conf['optimizer'] not in self._OPTIMIZERS:
             raise ValueError(f"Optimizer {conf['optimizer']} not yet implemented")
+        # optional extra key (default reproduces the reference): optimizer_mode: dense | lazy (row-sparse AdamW)
         self.optimizer = DenseAdam(self.model, lr=self.lr, weight_decay=self.wd,
-                                   decoupled=self._OPTIMIZERS[conf['optimizer']])
+                                   decoupled=self._OPTIMIZERS[conf['optimizer']], mode=conf.get('optimizer_mode', 'dense'))
         self.train_step = FusedMFTrainStep(self.model, self.rec_loss, self.optimizer)
 
         self.n_epochs = conf['n_epochs']

@@ -189,6 +189,17 @@ HSK_API int hsk_rank_metrics_dense(const int32_t* top_ids, int Be, int k_max, co
                                    const int32_t* user_group, int n_groups, const float* discount, float* per_user,
                                    double* sums, int64_t* counts, hsk_stream_t stream);
 
+/* ---- row-sparse "lazy" AdamW (reported separately: NOT torch.optim.AdamW's trajectory) ------------------------------
+ * hsk_mark_touched sets touched_users[u] = touched_items[i] = 1 for every index of the batch; hsk_adamw_rows_lazy then
+ * updates p, m, v (and zeroes g) ONLY for rows whose flag is set and clears the flag — torch.optim.SparseAdam semantics
+ * (global step count for the bias corrections) plus decoupled weight decay on the touched rows.  `*_bias` (nullable)
+ * are the length-n_rows vectors sharing the row index (item_bias with the item table, user_bias with the user table). */
+HSK_API int hsk_mark_touched(const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t n_users, int64_t n_items,
+                             uint8_t* touched_users, uint8_t* touched_items, hsk_stream_t stream);
+HSK_API int hsk_adamw_rows_lazy(float* p, float* m, float* v, float* g, int64_t n_rows, int ld, float* p_bias, float* m_bias,
+                                float* v_bias, float* g_bias, uint8_t* touched, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, int64_t step, hsk_stream_t stream);
+
 /* ---- measurement hook (scripts/kbench.py): if set to a device array of 16 uint64, hsk_eval_topk_tc adds the cycle counts
  * of its epilogue phases and list-cut sub-phases to it; NULL (default) disables the counters. */
 HSK_API void hsk_debug_eval_tc_profile(unsigned long long* dev_counters);

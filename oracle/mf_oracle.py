@@ -334,3 +334,38 @@ def metrics_from_topk(topk_ids: np.ndarray, users: np.ndarray, labels_csr, k_val
             out[f'recall@{k}'][r] = h.sum() / npos if npos > 0 else 0.
             out[f'ndcg@{k}'][r] = min(1., (h * w[:k]).sum() / cw[min(k, npos)]) if npos > 0 else 0.
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# row-sparse "lazy" AdamW — NOT in the reference (which always runs dense torch.optim.AdamW); this restates the
+# documented semantics of hsk_adamw_rows_lazy (= torch.optim.SparseAdam's masked update with the global step count, plus
+# decoupled weight decay on the touched rows) so that the CUDA kernel has a checker.
+# --------------------------------------------------------------------------------------------
+class OracleLazyAdamW:
+    def __init__(self, model: nn.Module, lr: float, wd: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model, self.lr, self.wd, self.betas, self.eps, self.t = model, lr, wd, betas, eps, 0
+        self.state = {n: (torch.zeros_like(p), torch.zeros_like(p)) for n, p in model.named_parameters()}
+
+    @torch.no_grad()
+    def step(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor):
+        """Consumes p.grad of every parameter; rows not indexed by this batch are left untouched."""
+        self.t += 1
+        b1, b2 = self.betas
+        bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
+        rows_u, rows_i = torch.unique(u_idxs), torch.unique(i_idxs)
+        for n, p in self.model.named_parameters():
+            m, v = self.state[n]
+            if n.startswith('user_'):
+                sel = rows_u
+            elif n.startswith('item_'):
+                sel = rows_i
+            else:
+                sel = torch.arange(p.shape[0])
+            g = p.grad[sel]
+            pp = p[sel] * (1 - self.lr * self.wd)
+            mm = torch.lerp(m[sel], g, 1 - b1)
+            vv = v[sel] * b2 + (1 - b2) * g * g
+            denom = vv.sqrt() / math.sqrt(bc2) + self.eps
+            pp = pp - (self.lr / bc1) * mm / denom
+            p[sel], m[sel], v[sel] = pp, mm, vv
+            p.grad = None

@@ -259,3 +259,50 @@ def test_state_dict_roundtrip_matches_reference_names_and_shapes():
     u = torch.arange(50, device='cuda')
     i = torch.randint(0, 120, (50, 5), device='cuda')
     assert torch.equal(m(u, i), m2(u, i))
+
+
+def test_lazy_row_sparse_adamw_vs_oracle():
+    """optimizer_mode='lazy': only the rows a batch touches move (p, m, v); checked against the oracle's restatement of
+    the documented semantics over 3 free-running steps with partially overlapping batches."""
+    from oracle import mf_oracle as O
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.train.optim import DenseAdam
+    from hassaku_b200.train.rec_losses import RecBayesianPersonalizedRankingLoss
+    from hassaku_b200.train.trainer_step import FusedMFTrainStep
+    U, I, d, B, N = 400, 900, 36, 64, 6
+    torch.manual_seed(4)
+    ref = O.OracleMF(U, I, d, use_item_bias=True)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(torch.randn_like(p) * (1.0 / math.sqrt(d) if p.shape[-1] == d else 0.1))
+    model = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+    model.load_state_dict(ref.state_dict())
+    model.to('cuda')
+    lr, wd = 1e-3, 1e-2
+    opt = DenseAdam(model, lr=lr, weight_decay=wd, mode='lazy')
+    step = FusedMFTrainStep(model, RecBayesianPersonalizedRankingLoss(), opt)
+    oopt = O.OracleLazyAdamW(ref, lr, wd)
+    rng = np.random.RandomState(0)
+    p0 = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    touched_u, touched_i = set(), set()
+    for s in range(3):
+        u = torch.from_numpy(rng.randint(0, U // 2, B).astype(np.int64))
+        i = torch.from_numpy(rng.randint(0, I // 2, (B, N + 1)).astype(np.int64))
+        touched_u |= set(u.tolist()); touched_i |= set(i.flatten().tolist())
+        loss = O.bpr_loss(ref(u, i), O.make_labels(B, N + 1))
+        loss.backward()
+        oopt.step(u, i)
+        step(u, i)
+        assert abs(step.pop_loss_sum() - float(loss)) <= RTOL * abs(float(loss))
+        for n, pr in ref.named_parameters():
+            got = dict(model.named_parameters())[n].detach().cpu().numpy()
+            err = np.abs(got.astype(np.float64) - pr.detach().numpy()).max()
+            assert err < RTOL * np.abs(pr.detach().numpy()).max() + 2e-3 * lr, (s, n, err)
+    # rows never touched are bit-identical to the initial weights (no decay, no momentum tail), unlike dense AdamW
+    Uw = model.user_embeddings.weight.detach().cpu()
+    untouched = sorted(set(range(U)) - touched_u)
+    assert len(untouched) > 0 and torch.equal(Uw[untouched], p0['user_embeddings.weight'][untouched])
+    Vw = model.item_embeddings.weight.detach().cpu()
+    untouched_i = sorted(set(range(I)) - touched_i)
+    assert torch.equal(Vw[untouched_i], p0['item_embeddings.weight'][untouched_i])
+    assert float(opt.g.abs().max()) == 0.0 and int(opt.touched_items.sum()) == 0 and int(opt.touched_users.sum()) == 0
