@@ -13,49 +13,99 @@ namespace hsk {
 
 // Shared-memory row slots are NV * 512 bytes: the TMA writes ld * 4 bytes, the tail [ld * 4, NV * 512) is zeroed once
 // per CTA and never written again, so the dot / axpy loops need no bounds checks (the zero tail contributes nothing).
-template <int NV>
+// TAILS: the last of the NV rounds is a SCALAR round (one float per lane) instead of a masked float4 round — used when
+// at most 32 floats remain after the full rounds (d = 402: 3 full rounds + 20 floats), which saves the 3/4-empty fourth
+// float4 round in every dot / axpy / reduction.
+template <int NV, bool TAILS>
 __device__ __forceinline__ void row_from_smem(Row<NV>& r, const float4* p, int lane) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) r.v[k] = p[lane + 32 * k];
+    for (int k = 0; k < NV; ++k) {
+        if (TAILS && k == NV - 1) r.v[k] = make_float4(reinterpret_cast<const float*>(p)[128 * k + lane], 0.f, 0.f, 0.f);
+        else r.v[k] = p[lane + 32 * k];
+    }
 }
-template <int NV>
+template <int NV, bool TAILS>
 __device__ __forceinline__ float dot_smem(const Row<NV>& u, const float4* p, int lane) {
     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const float4 v = p[lane + 32 * k];
-        acc0 = fmaf(u.v[k].x, v.x, acc0);
-        acc1 = fmaf(u.v[k].y, v.y, acc1);
-        acc0 = fmaf(u.v[k].z, v.z, acc0);
-        acc1 = fmaf(u.v[k].w, v.w, acc1);
+        if (TAILS && k == NV - 1) {
+            acc0 = fmaf(u.v[k].x, reinterpret_cast<const float*>(p)[128 * k + lane], acc0);
+        } else {
+            const float4 v = p[lane + 32 * k];
+            acc0 = fmaf(u.v[k].x, v.x, acc0);
+            acc1 = fmaf(u.v[k].y, v.y, acc1);
+            acc0 = fmaf(u.v[k].z, v.z, acc0);
+            acc1 = fmaf(u.v[k].w, v.w, acc1);
+        }
     }
     return acc0 + acc1;
 }
-template <int NV>
+template <int NV, bool TAILS>
 __device__ __forceinline__ void axpy_smem(Row<NV>& g, float a, const float4* p, int lane) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const float4 v = p[lane + 32 * k];
-        g.v[k].x = fmaf(a, v.x, g.v[k].x);
-        g.v[k].y = fmaf(a, v.y, g.v[k].y);
-        g.v[k].z = fmaf(a, v.z, g.v[k].z);
-        g.v[k].w = fmaf(a, v.w, g.v[k].w);
+        if (TAILS && k == NV - 1) {
+            g.v[k].x = fmaf(a, reinterpret_cast<const float*>(p)[128 * k + lane], g.v[k].x);
+        } else {
+            const float4 v = p[lane + 32 * k];
+            g.v[k].x = fmaf(a, v.x, g.v[k].x);
+            g.v[k].y = fmaf(a, v.y, g.v[k].y);
+            g.v[k].z = fmaf(a, v.z, g.v[k].z);
+            g.v[k].w = fmaf(a, v.w, g.v[k].w);
+        }
     }
 }
 // dst += a * u: full rounds unguarded, only the last round is bounds-checked
-template <int NV>
+template <int NV, bool TAILS>
 __device__ __forceinline__ void red_row(const Row<NV>& u, float* __restrict__ dst, float a, int nvec, int lane) {
     float4* p = reinterpret_cast<float4*>(dst) + lane;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        if (k < NV - 1 || lane + 32 * k < nvec)
+        if (TAILS && k == NV - 1) {
+            if (128 * k + lane < nvec * 4) atomicAdd(dst + 128 * k + lane, a * u.v[k].x);
+        } else if (k < NV - 1 || lane + 32 * k < nvec) {
             atomicAdd(p + 32 * k, make_float4(a * u.v[k].x, a * u.v[k].y, a * u.v[k].z, a * u.v[k].w));
+        }
+    }
+}
+
+template <int NV, bool TAILS>
+__device__ __forceinline__ float dot_smem_a(const Row<NV>& u, uint32_t base) {   // base already includes lane * 16
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (TAILS && k == NV - 1) {
+            acc0 = fmaf(u.v[k].x, lds32(base - (threadIdx.x & 31) * 12 + 512 * k), acc0);
+        } else {
+            const float4 v = lds128(base + 512 * k);
+            acc0 = fmaf(u.v[k].x, v.x, acc0);
+            acc1 = fmaf(u.v[k].y, v.y, acc1);
+            acc0 = fmaf(u.v[k].z, v.z, acc0);
+            acc1 = fmaf(u.v[k].w, v.w, acc1);
+        }
+    }
+    return acc0 + acc1;
+}
+template <int NV, bool TAILS>
+__device__ __forceinline__ void axpy_smem_a(Row<NV>& g, float a, uint32_t base) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (TAILS && k == NV - 1) {
+            g.v[k].x = fmaf(a, lds32(base - (threadIdx.x & 31) * 12 + 512 * k), g.v[k].x);
+        } else {
+            const float4 v = lds128(base + 512 * k);
+            g.v[k].x = fmaf(a, v.x, g.v[k].x);
+            g.v[k].y = fmaf(a, v.y, g.v[k].y);
+            g.v[k].z = fmaf(a, v.z, g.v[k].z);
+            g.v[k].w = fmaf(a, v.w, g.v[k].w);
+        }
     }
 }
 
 constexpr int min_blocks_for(int nv) { return nv <= 4 ? 7 : (nv <= 6 ? 5 : 4); }
 
-template <int NV, int LOSS, int STAGES>
+template <int NV, int LOSS, int STAGES, bool TAILS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_train_fused_tma_kernel(TrainArgs a) {
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ uint64_t bar_u, bar_v0;
@@ -120,17 +170,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
     const float* __restrict__ Vw = a.Vw;
     float* __restrict__ gV = a.gV;
 
+    // shared-memory addresses of this warp's ring and barriers, advanced incrementally (no multiplies in the loop)
+    const uint32_t ring_a = smem_u32(ring), bars_a = smem_u32(&bars[warp][0]);
+    const uint32_t lane16 = (uint32_t)lane * 16u;
     uint32_t to_issue = valid, to_consume = valid;
-    int issue_stage = 0;
+    uint32_t iss_slot = ring_a, iss_bar = bars_a;
     auto issue_next = [&]() {
         const int t = __ffs(to_issue) - 1;
         to_issue &= to_issue - 1;
         const int64_t it = __shfl_sync(kFull, my_idx, t);
         if (lane == 0) {
-            mbar_expect_tx(&bars[warp][issue_stage], row_bytes);
-            bulk_g2s(ring + issue_stage * kSlot, Vw + it * ld, row_bytes, &bars[warp][issue_stage]);
+            mbar_expect_tx_a(iss_bar, row_bytes);
+            bulk_g2s_a(iss_slot, Vw + it * ld, row_bytes, iss_bar);
         }
-        issue_stage = (issue_stage + 1 == STAGES) ? 0 : issue_stage + 1;
+        iss_slot += kSlot; iss_bar += 8;
+        if (iss_bar == bars_a + 8 * STAGES) { iss_slot = ring_a; iss_bar = bars_a; }
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s)
@@ -139,12 +193,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
     Row<NV> ur, gu;
     gu.zero();
     mbar_wait(&bar_u, 0);
-    row_from_smem(ur, reinterpret_cast<const float4*>(slot_u), lane);
+    row_from_smem<NV, TAILS>(ur, reinterpret_cast<const float4*>(slot_u), lane);
 
     float s0 = 0.f;
     if (LOSS == HSK_LOSS_BPR) {
         mbar_wait(&bar_v0, 0);
-        s0 = warp_sum(dot_smem(ur, reinterpret_cast<const float4*>(slot_v0), lane));
+        s0 = warp_sum(dot_smem<NV, TAILS>(ur, reinterpret_cast<const float4*>(slot_v0), lane));
         if (a.Ub) s0 += a.Ub[u];
         if (a.Ib) s0 += __ldg(a.Ib + i0);
         if (a.Gb) s0 += a.Gb[0];
@@ -156,8 +210,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
     const float invf = (float)a.inv_count;
     const bool write_scores = a.scores_out != nullptr, write_ds = a.dscores_out != nullptr;
     const bool do_red = !(a.debug_flags & 1);
+    float* __restrict__ gIb = a.gIb;
     const int64_t rowoff = (int64_t)b * N1;
-    int stage = 0;
+    uint32_t cur_slot = ring_a + lane16, cur_bar = bars_a;
     uint32_t parity = 0;
     while (to_consume) {
         if (to_issue) issue_next();
@@ -165,9 +220,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
         to_consume &= to_consume - 1;
         const int64_t it = __shfl_sync(kFull, my_idx, t);
         const float ib = __shfl_sync(kFull, my_ib, t);
-        mbar_wait(&bars[warp][stage], parity);
-        const float4* vp = reinterpret_cast<const float4*>(ring + stage * kSlot);
-        float sj = warp_sum(dot_smem(ur, vp, lane));
+        mbar_wait_a(cur_bar, parity);
+        float sj = warp_sum(dot_smem_a<NV, TAILS>(ur, cur_slot));
         if (has_ub) sj += ubv;     // sgd_alg.py:173-178 order
         if (has_ib) sj += ib;
         if (has_gb) sj += gbv;
@@ -175,32 +229,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
         if (LOSS == HSK_LOSS_BPR) {
             const float x = s0 - sj;
             // sigma(x) - 1 = -1 / (1 + e^x); one exp serves the gradient and the loss:
-            //   x >= 0: e = e^-x, sig-1 = -e/(1+e), -logsig = log1p(e)
-            //   x <  0: e = e^x,  sig-1 = -1/(1+e), -logsig = log1p(e) - x
+            //   x >= 0: e = e^-x, sig-1 = -e/(1+e), -logsig = log(1+e)
+            //   x <  0: e = e^x,  sig-1 = -1/(1+e), -logsig = log(1+e) - x
             const float e = expf(-fabsf(x));
-            const float r = 1.f / (1.f + e);
+            const float r = __frcp_rn(1.f + e);
             const float dx = -(x >= 0.f ? e * r : r) * invf;  // dL/dx = (sigma(x) - 1) / (B N)
             dsj = -dx;
             ds0 += dx;
-            loss_local += (log1pf(e) - fminf(x, 0.f)) * invf;
+            // the reported loss only (not the gradient): log(1+e) by the fast log, absolute error ~1e-7 per term
+            loss_local += (__logf(1.f + e) - fminf(x, 0.f)) * invf;
         } else {
             const float y = (warp + kWarpsPerCta * t + jbase == 0) ? 1.f : 0.f;
             const float e = expf(-fabsf(sj));
-            const float r = 1.f / (1.f + e);
+            const float r = __frcp_rn(1.f + e);
             const float sig = sj >= 0.f ? r : e * r;
             dsj = (sig - y) * invf;
-            loss_local += ((1.f - y) * sj + log1pf(e) - fminf(sj, 0.f)) * invf;
+            loss_local += ((1.f - y) * sj + __logf(1.f + e) - fminf(sj, 0.f)) * invf;
         }
         dsum += dsj;
-        axpy_smem(gu, dsj, vp, lane);
-        if (do_red) red_row(ur, gV + it * ld, dsj, nvec, lane);
+        axpy_smem_a<NV, TAILS>(gu, dsj, cur_slot);
+        if (do_red) red_row<NV, TAILS>(ur, gV + it * ld, dsj, nvec, lane);
         if (lane == 0) {
-            if (a.gIb) atomicAdd(a.gIb + it, dsj);
-            const int j = jbase + warp + kWarpsPerCta * t;
-            if (write_scores) a.scores_out[rowoff + j] = sj;
-            if (write_ds) a.dscores_out[rowoff + j] = dsj;
+            if (gIb) atomicAdd(gIb + it, dsj);
+            if (write_scores | write_ds) {
+                const int j = jbase + warp + kWarpsPerCta * t;
+                if (write_scores) a.scores_out[rowoff + j] = sj;
+                if (write_ds) a.dscores_out[rowoff + j] = dsj;
+            }
         }
-        if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+        cur_slot += kSlot; cur_bar += 8;
+        if (cur_bar == bars_a + 8 * STAGES) { cur_slot = ring_a + lane16; cur_bar = bars_a; parity ^= 1u; }
         __syncwarp();
     }
 
@@ -225,10 +283,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_blocks_for(NV)) mf_trai
             }
         }
         if (LOSS == HSK_LOSS_BPR) {
-            axpy_smem(gu, d0, reinterpret_cast<const float4*>(slot_v0), lane);
-            if (do_red) red_row(ur, gV + i0 * ld, d0, nvec, lane);
+            axpy_smem<NV, TAILS>(gu, d0, reinterpret_cast<const float4*>(slot_v0), lane);
+            if (do_red) red_row<NV, TAILS>(ur, gV + i0 * ld, d0, nvec, lane);
         }
-        red_row(gu, a.gU + u * ld, 1.0f, nvec, lane);
+        red_row<NV, TAILS>(gu, a.gU + u * ld, 1.0f, nvec, lane);
         if (lane == 0) {
             if (LOSS == HSK_LOSS_BPR) {
                 if (a.gIb) atomicAdd(a.gIb + i0, d0);
@@ -247,7 +305,9 @@ template <int NV, int LOSS, int STAGES>
 static int launch_one(const TrainArgs& a, dim3 grid, int row_pad, cudaStream_t s) {
     (void)row_pad;
     const size_t smem = (size_t)NV * 512 * (2 + kWarpsPerCta * STAGES);
-    auto kern = mf_train_fused_tma_kernel<NV, LOSS, STAGES>;
+    // scalar tail round when at most 32 floats (8 float4) remain after NV - 1 full rounds
+    const bool tails = (a.nvec - 32 * (NV - 1)) <= 8;
+    auto kern = tails ? mf_train_fused_tma_kernel<NV, LOSS, STAGES, true> : mf_train_fused_tma_kernel<NV, LOSS, STAGES, false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_mf_train_fused: smem attribute: %s", cudaGetErrorString(e));
