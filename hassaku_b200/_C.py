@@ -48,7 +48,8 @@ def _declare(lib):
         'hsk_gather_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
-        'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp]),
+        'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp, vp]),
+        'hsk_adagrad_dense': (i32, [vp, vp, vp, i64, f64, f64, f64, i32, vp]),
         'hsk_mark_touched': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, vp]),
         'hsk_adamw_rows_lazy': (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, f64, f64, f64, f64, f64, i64, vp]),
         'hsk_debug_eval_tc_profile': (None, [vp]),
@@ -198,6 +199,13 @@ def adamw_dense(p, m, v, g, lr, beta1, beta2, eps, weight_decay, step: int, arit
                                  weight_decay, step, arith, int(adam_l2), int(zero_grad), _stream()), 'hsk_adamw_dense')
 
 
+def adagrad_dense(p, state_sum, g, lr, eps=1e-10, weight_decay=0.0, zero_grad=True):
+    for n, t in (('p', p), ('state_sum', state_sum), ('g', g)):
+        _req(t, torch.float32, n)
+    _check(lib().hsk_adagrad_dense(p.data_ptr(), state_sum.data_ptr(), g.data_ptr(), p.numel(), lr, eps, weight_decay,
+                                   int(zero_grad), _stream()), 'hsk_adagrad_dense')
+
+
 def mark_touched(u_idx, i_idx, n_users: int, n_items: int, touched_users, touched_items):
     _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx')
     _req(touched_users, torch.uint8, 'touched_users'); _req(touched_items, torch.uint8, 'touched_items')
@@ -231,7 +239,7 @@ def adamw_dense_graph(p, m, v, g, consts_dev, decoupled: bool = True, adam_l2: b
 
 
 def sample_negatives(u_idx, pos_idx, n_neg: int, n_items: int, n_users: int, csr_indptr, csr_indices, seed: int,
-                     step: int, i_idx, distinct_in_row: bool = True, status=None):
+                     step: int, i_idx, distinct_in_row: bool = True, status=None, pop_cdf=None):
     _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx')
     _req(csr_indptr, torch.int64, 'csr_indptr'); _req(csr_indices, torch.int32, 'csr_indices')
     if pos_idx is not None:
@@ -241,7 +249,7 @@ def sample_negatives(u_idx, pos_idx, n_neg: int, n_items: int, n_users: int, csr
         raise HskError(f'i_idx must be [{B}, {n_neg + 1}]')
     _check(lib().hsk_sample_negatives(u_idx.data_ptr(), _ptr(pos_idx), B, n_neg, n_items, n_users, csr_indptr.data_ptr(),
                                       csr_indices.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, step, int(distinct_in_row),
-                                      i_idx.data_ptr(), _ptr(status), _stream()), 'hsk_sample_negatives')
+                                      _ptr(pop_cdf), i_idx.data_ptr(), _ptr(status), _stream()), 'hsk_sample_negatives')
 
 
 # ---- evaluator ----

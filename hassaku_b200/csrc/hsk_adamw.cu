@@ -277,3 +277,45 @@ extern "C" int hsk_adamw_rows_lazy(float* p, float* m, float* v, float* g, int64
         adamw_rows_lazy_kernel<false><<<nb, 256, 0, as_stream(stream)>>>(p, m, v, g, n_rows, ld, p_bias, m_bias, v_bias, g_bias, touched, c);
     return check_launch("hsk_adamw_rows_lazy");
 }
+
+// ---- torch.optim.Adagrad(params, lr, weight_decay) (train/trainer.py:50-51), dense, one streaming pass ----------------
+// Op order of torch's CUDA `_multi_tensor_adagrad` (lr_decay = 0, initial_accumulator_value = 0, eps = 1e-10):
+//   g = fma(f(wd), p, g)            _foreach_add(grads, params, alpha = wd)          (only if wd != 0)
+//   s = fma(g, g, s)                _foreach_addcmul_(state_sums, grads, grads, 1)   (value 1 is folded away)
+//   std = sqrt(s) + f(eps)          _foreach_sqrt, _foreach_add_
+//   p = p + (g * f(-lr)) / std      _foreach_mul_(grads, -clr), _foreach_addcdiv_(params, grads, std)
+namespace hsk {
+template <bool L2, bool ZERO>
+__global__ void __launch_bounds__(256) adagrad_dense_kernel(float* __restrict__ p, float* __restrict__ s, float* __restrict__ g,
+                                                            int64_t n, float wd, float neg_lr, float eps) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float P = p[i], S = s[i], G = g[i];
+        if (L2) G = __fmaf_rn(wd, P, G);
+        S = __fmaf_rn(G, G, S);   // value = 1 is folded: a single rounding (verified bitwise against torch on the GPU)
+        const float sd = __fadd_rn(__fsqrt_rn(S), eps);
+        P = __fmaf_rn(1.0f, __fdiv_rn(__fmul_rn(G, neg_lr), sd), P);
+        p[i] = P; s[i] = S;
+        if (ZERO) g[i] = 0.f;
+    }
+}
+}  // namespace hsk
+
+extern "C" int hsk_adagrad_dense(float* p, float* state_sum, float* g, int64_t n, double lr, double eps, double weight_decay,
+                                 int zero_grad, hsk_stream_t stream) {
+    using namespace hsk;
+    HSK_REQUIRE(p && state_sum && g && n >= 0, "hsk_adagrad_dense: bad arguments");
+    if (n == 0) return HSK_OK;
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 32;
+    const int nb = (int)(blocks < cap ? blocks : cap);
+    cudaStream_t st = as_stream(stream);
+    const float wd = (float)weight_decay, nlr = (float)(-lr), e = (float)eps;
+    if (weight_decay != 0.0) {
+        if (zero_grad) adagrad_dense_kernel<true, true><<<nb, 256, 0, st>>>(p, state_sum, g, n, wd, nlr, e);
+        else adagrad_dense_kernel<true, false><<<nb, 256, 0, st>>>(p, state_sum, g, n, wd, nlr, e);
+    } else {
+        if (zero_grad) adagrad_dense_kernel<false, true><<<nb, 256, 0, st>>>(p, state_sum, g, n, wd, nlr, e);
+        else adagrad_dense_kernel<false, false><<<nb, 256, 0, st>>>(p, state_sum, g, n, wd, nlr, e);
+    }
+    return check_launch("hsk_adagrad_dense");
+}

@@ -30,6 +30,28 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// 'popular' strategy (data/dataloader.py:59-64): item ~ pop^alpha.  The caller passes the distribution as a 64-bit
+// fixed-point CDF (cdf[i] = floor(2^64 * sum_{t <= i} p_t), last entry 2^64 - 1); a draw takes two Philox words r64 and
+// returns the first i with cdf[i] > r64 — integer arithmetic only, so the numpy oracle reproduces it bit for bit.
+__device__ __forceinline__ uint32_t draw_item_cdf(uint32_t b, uint32_t j, uint32_t& q, uint32_t step_lo, uint32_t k0, uint32_t k1,
+                                                  const uint64_t* __restrict__ cdf, uint32_t n_items) {
+    uint32_t w[4];
+    uint32_t hi, lo;
+    philox4x32_10(b, j, q >> 2, step_lo, k0, k1, w);
+    hi = w[q & 3u];
+    ++q;
+    if ((q & 3u) == 0u) philox4x32_10(b, j, q >> 2, step_lo, k0, k1, w);
+    lo = w[q & 3u];
+    ++q;
+    const uint64_t r = ((uint64_t)hi << 32) | lo;
+    uint32_t a = 0, n = n_items;   // upper_bound
+    while (n > 0) {
+        const uint32_t half = n >> 1;
+        if (__ldg(cdf + a + half) <= r) { a += half + 1; n -= half + 1; } else { n = half; }
+    }
+    return a < n_items ? a : n_items - 1;
+}
+
 // next uniform item of slot (b, j); q = words consumed so far (updated)
 __device__ __forceinline__ uint32_t draw_item(uint32_t b, uint32_t j, uint32_t& q, uint32_t step_lo, uint32_t k0, uint32_t k1,
                                               uint32_t n_items) {
@@ -47,7 +69,7 @@ __device__ __forceinline__ uint32_t draw_item(uint32_t b, uint32_t j, uint32_t& 
 __global__ void __launch_bounds__(kSamplerWarps * 32) sample_negatives_kernel(
     const int64_t* __restrict__ u_idx, const int64_t* __restrict__ pos_idx, int B, int N, uint32_t n_items, int64_t n_users,
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, uint32_t k0, uint32_t k1, uint32_t step_lo,
-    int distinct, int64_t* __restrict__ i_idx, int32_t* status) {
+    int distinct, const uint64_t* __restrict__ cdf, int64_t* __restrict__ i_idx, int32_t* status) {
     extern __shared__ uint32_t sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kSamplerWarps + warp;
@@ -69,7 +91,8 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_negatives_kernel(
         for (int j = lane; j < N; j += 32) {
             if (round == 0 || (cnt[j] & 0x80000000u)) {
                 uint32_t q = cnt[j] & 0x7FFFFFFFu;
-                const uint32_t it = draw_item((uint32_t)b, (uint32_t)j, q, step_lo, k0, k1, n_items);
+                const uint32_t it = cdf ? draw_item_cdf((uint32_t)b, (uint32_t)j, q, step_lo, k0, k1, cdf, n_items)
+                                        : draw_item((uint32_t)b, (uint32_t)j, q, step_lo, k0, k1, n_items);
                 val[j] = it;
                 cnt[j] = q | 0x40000000u;  // bit 30 = "drawn this round"
             }
@@ -101,7 +124,7 @@ using namespace hsk;
 
 extern "C" int hsk_sample_negatives(const int64_t* u_idx, const int64_t* pos_idx, int B, int N, int64_t n_items,
                                     int64_t n_users, const int64_t* csr_indptr, const int32_t* csr_indices, uint64_t seed,
-                                    uint64_t step, int distinct_in_row, int64_t* i_idx, int32_t* status,
+                                    uint64_t step, int distinct_in_row, const uint64_t* pop_cdf, int64_t* i_idx, int32_t* status,
                                     hsk_stream_t stream) {
     HSK_REQUIRE(u_idx && csr_indptr && csr_indices && i_idx, "hsk_sample_negatives: null pointer");
     HSK_REQUIRE(B >= 0 && N >= 1 && N <= kSamplerMaxN, "hsk_sample_negatives: need 1 <= N <= %d (N=%d)", kSamplerMaxN, N);
@@ -111,6 +134,6 @@ extern "C" int hsk_sample_negatives(const int64_t* u_idx, const int64_t* pos_idx
     const size_t smem = (size_t)kSamplerWarps * 2 * N * sizeof(uint32_t);
     sample_negatives_kernel<<<(B + kSamplerWarps - 1) / kSamplerWarps, kSamplerWarps * 32, smem, as_stream(stream)>>>(
         u_idx, pos_idx, B, N, (uint32_t)n_items, n_users, csr_indptr, csr_indices, k0, k1, (uint32_t)step, distinct_in_row,
-        i_idx, status);
+        pop_cdf, i_idx, status);
     return check_launch("hsk_sample_negatives");
 }

@@ -18,7 +18,7 @@ class InteractionSampler:
 
 
 class NegativeSampler(InteractionSampler):
-    """data/dataloader.py:17-64: parameters of the negative sampling ('uniform'; 'popular' is not built yet)."""
+    """data/dataloader.py:17-64: parameters of the negative sampling: 'uniform' or 'popular' (item ~ pop^alpha)."""
 
     def __init__(self, train_dataset: TrainRecDataset, n_neg: int = 10, neg_sampling_strategy: str = 'uniform',
                  squashing_factor_pop_sampling: float = 1., distinct_in_row: bool = True):
@@ -26,9 +26,6 @@ class NegativeSampler(InteractionSampler):
         assert neg_sampling_strategy in ['uniform', 'popular'], \
             f'<{neg_sampling_strategy}> is not a valid negative sampling strategy!'
         assert squashing_factor_pop_sampling >= 0, 'Squashing factor for popularity sampling should be positive!'
-        if neg_sampling_strategy != 'uniform':
-            raise NotImplementedError("hassaku_b200 implements the 'uniform' strategy on the device; 'popular' is a "
-                                      "next-row item (SURVEY §8f)")
         self.dataset = train_dataset
         self.n_neg = n_neg
         self.neg_sampling_strategy = neg_sampling_strategy
@@ -37,6 +34,16 @@ class NegativeSampler(InteractionSampler):
         self.n_items = train_dataset.n_items
         self.pop_distribution = train_dataset.pop_distribution.copy()
         self.name = 'NegativeSampler'
+
+    def popularity_cdf(self) -> np.ndarray:
+        """64-bit fixed-point CDF of pop^alpha (what hsk_sample_negatives consumes for the 'popular' strategy)."""
+        p = np.power(np.asarray(self.pop_distribution, dtype=np.float64), self.squashing_factor_pop_sampling)
+        p = p / p.sum()
+        c = np.cumsum(p)
+        c = c / c[-1]
+        out = np.array([min(int(x * 18446744073709551616.0), 18446744073709551615) for x in c], dtype=np.uint64)
+        out[-1] = np.uint64(18446744073709551615)
+        return out
         logging.info(f'Built {self.name} module: n_neg={n_neg}, strategy={neg_sampling_strategy}')
 
 
@@ -65,6 +72,9 @@ class TrainDataLoader:
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.step = 0
         self._labels = {}
+        self.pop_cdf = None
+        if interaction_sampler.neg_sampling_strategy == 'popular':
+            self.pop_cdf = torch.from_numpy(interaction_sampler.popularity_cdf().view(np.int64)).to(self.device)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(self.seed)
 
@@ -84,7 +94,7 @@ class TrainDataLoader:
         s = self.interaction_sampler
         i_idxs = torch.empty((len(u_idxs), s.n_neg + 1), dtype=torch.int64, device=self.device)
         _C.sample_negatives(u_idxs, pos_idxs, s.n_neg, self.dataset.n_items, self.dataset.n_users, self.indptr,
-                            self.indices, self.seed, step, i_idxs, s.distinct_in_row, self.status)
+                            self.indices, self.seed, step, i_idxs, s.distinct_in_row, self.status, pop_cdf=self.pop_cdf)
         return i_idxs
 
     def __iter__(self):

@@ -96,3 +96,35 @@ class DenseAdam(torch.optim.Optimizer):
                 gview.add_(p.grad.view_as(gview))
         self.step_fused()
         return loss
+
+
+class DenseAdagrad(torch.optim.Optimizer):
+    """torch.optim.Adagrad(lr, weight_decay) (train/trainer.py:50-51) over the flat arena in one streaming kernel."""
+    mode = 'dense'
+
+    def __init__(self, model, lr: float = 1e-2, weight_decay: float = 0.0, eps: float = 1e-10):
+        self.model = model
+        super().__init__(list(model.parameters()), dict(lr=lr, weight_decay=weight_decay, eps=eps))
+        arena = model.arena
+        if not arena.is_cuda:
+            raise _C.HskError('DenseAdagrad needs the model on a CUDA device (no CPU path)')
+        self.state_sum = torch.zeros_like(arena)
+        self.g = torch.zeros_like(arena)
+        self.grad_tables = model.layout.tables(self.g)
+        self.t = 0
+
+    def step_fused(self):
+        grp = self.param_groups[0]
+        self.t += 1
+        _C.adagrad_dense(self.model.arena, self.state_sum, self.g, grp['lr'], grp['eps'], grp['weight_decay'], zero_grad=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        names = ('user_embeddings.weight', 'item_embeddings.weight', 'user_bias.weight', 'item_bias.weight', 'global_bias')
+        params = dict(self.model.named_parameters())
+        for name, gview in zip(names, self.model.layout.views(self.g)):
+            if gview is not None and params[name].grad is not None:
+                gview.add_(params[name].grad.view_as(gview))
+        self.step_fused()
+        return loss

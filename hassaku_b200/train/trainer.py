@@ -18,7 +18,7 @@ from tqdm import trange, tqdm
 from hassaku_b200 import _C
 from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
 from hassaku_b200.eval.eval import evaluate_recommender_algorithm, FullEvaluator
-from hassaku_b200.train.optim import DenseAdam
+from hassaku_b200.train.optim import DenseAdagrad, DenseAdam
 from hassaku_b200.train.rec_losses import RecommenderSystemLoss
 from hassaku_b200.train.trainer_step import FusedMFTrainStep
 
@@ -27,7 +27,7 @@ class Trainer:
     """Same surface as the reference `Trainer` (train/trainer.py:15-200): constructor arguments, the attributes
     `best_value / best_metrics / best_epoch / pointer_to_model / optimizer`, `fit()` and `val()`."""
 
-    _OPTIMIZERS = {'adamw': True, 'adam': False}  # name -> decoupled weight decay? (trainer.py:48-53)
+    _OPTIMIZERS = {'adamw': True, 'adam': False, 'adagrad': None}  # name -> decoupled weight decay? (trainer.py:48-53)
 
     def __init__(self, model: SGDMatrixFactorization, train_loader: data.DataLoader, val_loader: data.DataLoader,
                  rec_loss: RecommenderSystemLoss, conf: dict):
@@ -47,8 +47,11 @@ class Trainer:
         if conf['optimizer'] not in self._OPTIMIZERS:
             raise ValueError(f"Optimizer {conf['optimizer']} not yet implemented")
         # optional extra key (default reproduces the reference): optimizer_mode: dense | lazy (row-sparse AdamW)
-        self.optimizer = DenseAdam(self.model, lr=self.lr, weight_decay=self.wd,
-                                   decoupled=self._OPTIMIZERS[conf['optimizer']], mode=conf.get('optimizer_mode', 'dense'))
+        if conf['optimizer'] == 'adagrad':
+            self.optimizer = DenseAdagrad(self.model, lr=self.lr, weight_decay=self.wd)
+        else:
+            self.optimizer = DenseAdam(self.model, lr=self.lr, weight_decay=self.wd,
+                                       decoupled=self._OPTIMIZERS[conf['optimizer']], mode=conf.get('optimizer_mode', 'dense'))
         self.train_step = FusedMFTrainStep(self.model, self.rec_loss, self.optimizer)
 
         self.n_epochs = conf['n_epochs']

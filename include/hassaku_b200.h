@@ -123,10 +123,13 @@ HSK_API int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, d
  * [n_users + 1], indices int32 sorted per row), redrawing flagged slots until the row is clean — the reference's
  * collate loop.  distinct_in_row != 0 additionally redraws a slot when a higher slot of the row holds the same item
  * (numpy's assume_unique sort path; the reference's common case).  Stream: Philox4x32-10 keyed by (seed, step), a
- * pure function of (seed, step, b, slot) — restated bit-exactly by oracle/philox.py.  i_idx is [B, 1 + N] int64. */
+ * pure function of (seed, step, b, slot) — restated bit-exactly by oracle/philox.py.  i_idx is [B, 1 + N] int64.
+ * pop_cdf (nullable): 'popular' strategy (data/dataloader.py:59-64, item ~ pop^alpha): a 64-bit fixed-point CDF over the
+ * items, cdf[i] = floor(2^64 * sum_{t<=i} p_t) with cdf[n_items-1] = 2^64 - 1; NULL = uniform. */
 HSK_API int hsk_sample_negatives(const int64_t* u_idx, const int64_t* pos_idx /* nullable */, int B, int N, int64_t n_items,
                                  int64_t n_users, const int64_t* csr_indptr, const int32_t* csr_indices, uint64_t seed,
-                                 uint64_t step, int distinct_in_row, int64_t* i_idx, int32_t* status, hsk_stream_t stream);
+                                 uint64_t step, int distinct_in_row, const uint64_t* pop_cdf /* nullable */, int64_t* i_idx,
+                                 int32_t* status, hsk_stream_t stream);
 
 /* ==== full-rank evaluator (eval/eval.py:54-99, 101-118, 237-253; eval/metrics.py:4-105) ========================= */
 
@@ -188,6 +191,11 @@ HSK_API int hsk_rank_metrics_dense(const int32_t* top_ids, int Be, int k_max, co
                                    const int64_t* u_idx, const float* y_true, int64_t n_items,
                                    const int32_t* user_group, int n_groups, const float* discount, float* per_user,
                                    double* sums, int64_t* counts, hsk_stream_t stream);
+
+/* ---- torch.optim.Adagrad(params, lr, weight_decay).step (train/trainer.py:50-51), dense, op order of torch's CUDA foreach
+ * path (lr_decay 0, eps default 1e-10): g += wd p; sum += g g; p -= lr g / (sqrt(sum) + eps); g zeroed if zero_grad. */
+HSK_API int hsk_adagrad_dense(float* p, float* state_sum, float* g, int64_t n, double lr, double eps, double weight_decay,
+                              int zero_grad, hsk_stream_t stream);
 
 /* ---- row-sparse "lazy" AdamW (reported separately: NOT torch.optim.AdamW's trajectory) ------------------------------
  * hsk_mark_touched sets touched_users[u] = touched_items[i] = 1 for every index of the batch; hsk_adamw_rows_lazy then

@@ -44,7 +44,30 @@ def _draw(b, j, q, step_lo, k0, k1, n_items):
             return m >> 32, q
 
 
-def sample_negatives(u_idx, n_neg, n_items, indptr, indices, seed, step, distinct_in_row=True, max_rounds=256):
+def popularity_cdf_u64(pop_distribution, squashing_factor=1.0):
+    """data/dataloader.py:59-64: p = pop^alpha / sum -> 64-bit fixed-point CDF (the array both the kernel and this oracle
+    consume).  Computed in Python integers from the float64 probabilities, so it is deterministic."""
+    p = np.power(np.asarray(pop_distribution, dtype=np.float64), squashing_factor)
+    p = p / p.sum()
+    c = np.cumsum(p)
+    c = c / c[-1]
+    out = np.array([min(int(x * 18446744073709551616.0), 18446744073709551615) for x in c], dtype=np.uint64)
+    out[-1] = np.uint64(18446744073709551615)
+    return out
+
+
+def _draw_cdf(b, j, q, step_lo, k0, k1, cdf):
+    words = []
+    for _ in range(2):
+        w = philox4x32_10(np.array([b, j, q >> 2, step_lo], dtype=np.uint32), np.array([k0, k1], dtype=np.uint32))
+        words.append(int(w[q & 3]))
+        q += 1
+    r = (words[0] << 32) | words[1]
+    i = int(np.searchsorted(cdf, np.uint64(r), side='right'))
+    return min(i, len(cdf) - 1), q
+
+
+def sample_negatives(u_idx, n_neg, n_items, indptr, indices, seed, step, distinct_in_row=True, max_rounds=256, pop_cdf=None):
     """The device sampler's contract, row by row.  Returns int64 [B, n_neg]."""
     k0 = seed & 0xFFFFFFFF
     k1 = ((seed >> 32) ^ (step >> 32)) & 0xFFFFFFFF
@@ -59,7 +82,10 @@ def sample_negatives(u_idx, n_neg, n_items, indptr, indices, seed, step, distinc
         for _ in range(max_rounds):
             drawn = flagged.copy()
             for j in np.nonzero(flagged)[0]:
-                val[j], q[j] = _draw(b, int(j), int(q[j]), step_lo, k0, k1, n_items)
+                if pop_cdf is None:
+                    val[j], q[j] = _draw(b, int(j), int(q[j]), step_lo, k0, k1, n_items)
+                else:
+                    val[j], q[j] = _draw_cdf(b, int(j), int(q[j]), step_lo, k0, k1, pop_cdf)
             flagged = np.zeros(n_neg, dtype=bool)
             flagged[drawn] = np.isin(val[drawn], row)
             if distinct_in_row:

@@ -87,3 +87,23 @@ def test_rejects_misaligned_and_bad_args():
         _C.adamw_dense(p[1:33], p[:32].clone(), p[:32].clone(), p[:32].clone(), 1e-3, .9, .999, 1e-8, 0., 1)
     with pytest.raises(_C.HskError):
         _C.adamw_dense(p, p.clone(), p.clone(), p.clone(), 1e-3, .9, .999, 1e-8, 0., 0)
+
+
+@pytest.mark.parametrize('lr,wd', [(1e-2, 0.0), (5e-3, 1e-4)])
+def test_adagrad_bitwise_vs_torch_cuda(lr, wd):
+    from hassaku_b200 import _C
+    n = 4 * 3000 + 2
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=gen) * 0.01
+    grads = _grads(n, 5, 11)
+    p = torch.nn.Parameter(p0.clone().cuda())
+    opt = torch.optim.Adagrad([p], lr=lr, weight_decay=wd)
+    q, ssum = p0.clone().cuda(), torch.zeros(n, device='cuda')
+    for g in grads:
+        p.grad = g.clone().cuda()
+        opt.step()
+        gg = g.clone().cuda()
+        _C.adagrad_dense(q, ssum, gg, lr, 1e-10, wd)
+        assert float(gg.abs().max()) == 0.0
+        assert torch.equal(q, p.detach()), f'{(q != p.detach()).sum().item()} / {n} differ'
+        assert torch.equal(ssum, opt.state[p]['sum'])

@@ -173,3 +173,52 @@ def test_trainer_with_device_loader_learns_and_stops_on_patience():
         m2.load_model_from_path(tmp)
         tr2 = Trainer(m2, dl, _EvalLoader(ds, 300), loss, _conf(tmp))
         assert abs(tr2.val()['ndcg@10'] - best['ndcg@10']) < 1e-7
+
+
+def test_popular_sampler_bit_exact_vs_oracle_and_distribution():
+    from oracle import philox as P
+    from hassaku_b200 import _C
+    from hassaku_b200.data.dataset import TrainRecDataset
+    from hassaku_b200.data.dataloader import NegativeSampler, TrainDataLoader
+    data = _tiny()
+    ds = TrainRecDataset.from_interactions(data.train)
+    sampler = NegativeSampler(ds, n_neg=12, neg_sampling_strategy='popular', squashing_factor_pop_sampling=0.75)
+    cdf = sampler.popularity_cdf()
+    np.testing.assert_array_equal(cdf, P.popularity_cdf_u64(ds.pop_distribution, 0.75))
+    assert cdf[-1] == np.uint64(2 ** 64 - 1) and (np.diff(cdf.astype(np.float64)) >= 0).all()
+    dl = TrainDataLoader(sampler, ds, batch_size=64, shuffle=False, seed=5)
+    u, i, _ = next(iter(dl))
+    ref = P.sample_negatives(u.cpu().numpy(), 12, 200, data.train.indptr, data.train.indices, 5, 0, True, pop_cdf=cdf)
+    np.testing.assert_array_equal(i.cpu().numpy()[:, 1:], ref)
+    # marginal follows pop^alpha over the allowed items (coarsely: popular items are drawn more often)
+    sampler2 = NegativeSampler(ds, n_neg=50, neg_sampling_strategy='popular', distinct_in_row=False)
+    dl2 = TrainDataLoader(sampler2, ds, batch_size=2048, shuffle=True, seed=1)
+    cnt = np.zeros(200)
+    for b, (u, i, _) in enumerate(dl2):
+        cnt += np.bincount(i[:, 1:].flatten().cpu().numpy(), minlength=200)
+        if b == 1:
+            break
+    pop = ds.pop_distribution
+    top, bottom = np.argsort(-pop)[:20], np.argsort(-pop)[-60:]
+    assert cnt[top].mean() > 2 * cnt[bottom].mean()
+
+
+def test_trainer_adagrad_option_runs_on_the_fused_path():
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.dataloader import NegativeSampler, TrainDataLoader
+    from hassaku_b200.data.dataset import FullEvalDataset, TrainRecDataset
+    from hassaku_b200.train.optim import DenseAdagrad
+    from hassaku_b200.train.rec_losses import RecBinaryCrossEntropy
+    from hassaku_b200.train.trainer import Trainer
+    data = _tiny()
+    tds = TrainRecDataset.from_interactions(data.train, data.user_group, 2)
+    dl = TrainDataLoader(NegativeSampler(tds, n_neg=8), tds, batch_size=256, shuffle=True)
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+    torch.manual_seed(2)
+    model = SGDMatrixFactorization(300, 200, 16, use_item_bias=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        tr = Trainer(model, dl, _EvalLoader(ds, 300), RecBinaryCrossEntropy(), _conf(tmp, optimizer='adagrad', lr=5e-2, n_epochs=4))
+        assert isinstance(tr.optimizer, DenseAdagrad)
+        first = tr.val()['ndcg@10']
+        best = tr.fit()
+        assert best['ndcg@10'] >= first
