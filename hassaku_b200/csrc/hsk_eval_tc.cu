@@ -152,8 +152,12 @@ constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
 // Entries beyond chkA / chkB are first tested against the user's exclusion row (lock-step binary searches).
 // Returns the number of survivors.
 __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, int chkB, int k, int lane,
-                                          const int32_t* __restrict__ excl, int64_t lo, int64_t hi, float* new_tau,
-                                          uint64_t* new_taukey, unsigned long long* tprof) {
+                                          const int32_t* __restrict__ excl, int64_t lo, int64_t hi, bool check, int max_keep,
+                                          float* new_tau, uint64_t* new_taukey, unsigned long long* tprof) {
+    // check == false: the exclusion test is postponed to the final cut.  At most n_excl = hi - lo excluded items can sit
+    // in the list, so selecting the (k + n_excl)-th largest RAW key is still a conservative threshold; it saves the
+    // ~11 k cycles of binary searches that made every cut stall the MMA pipeline.
+    if (!check) k += (int)(hi - lo);
     long long t0 = tprof ? clock64() : 0;
 #define HSK_CUT_TICK(i) do { if (tprof) { const long long t1 = clock64(); if (lane == 0) atomicAdd(tprof + (i), (unsigned long long)(t1 - t0)); t0 = t1; } } while (0)
     uint64_t key[TC_KPL];
@@ -172,15 +176,16 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
       for (int r = 0; r < TC_KPL; ++r) x ^= key[r];
       if (tprof && x == 0x123456789ull) lp[0] = x; }
     HSK_CUT_TICK(6);
-    if (hi > lo) {
+    if (check && hi > lo) {
         int32_t id[TC_KPL];
         bool found[TC_KPL];
 #pragma unroll
-        for (int r = 0; r < TC_KPL; ++r) id[r] = key_id(key[r]);
-        csr_contains_many<TC_KPL>(excl, lo, hi, id, unchecked, found);
+        for (int r = 0; r < TC_KPL; ++r) id[r] = key[r] ? key_id(key[r]) : -1;
+        if (hi - lo <= 384) csr_contains_bcast<TC_KPL>(excl, lo, hi, id, found, lane);   // short row: one coalesced pass
+        else csr_contains_many<TC_KPL>(excl, lo, hi, id, unchecked, found);             // long row: lock-step searches
 #pragma unroll
         for (int r = 0; r < TC_KPL; ++r)
-            if (found[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
+            if (found[r] && key[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
     }
     HSK_CUT_TICK(7);
     const int n = cA + cB;
@@ -211,7 +216,7 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
         if (lane >= o) incl += up;
     }
     const int total = __shfl_sync(kFull, incl, 31);
-    if (total > TC_HALF_CAP - TC_BN / 2) {
+    if (total > max_keep) {
         // degenerate score distribution (a huge tie bucket, e.g. all-equal scores): exact cut by the full sort; ties are
         // then resolved by the strict key order (lower item id wins), which the scan honours through `taukey`
         warp_sort_desc<TC_KPL>(key, lane);
@@ -274,6 +279,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
     __shared__ float s_base[TC_BM];
     __shared__ int s_rowok[TC_BM];
+    __shared__ int s_need[4][2][2];   // per pair / column half / tile parity: a list of this warp may overflow
     __shared__ __align__(16) float s_ib[4][2][TC_BN];   // per pair: item-bias tile, double buffered with the accumulator stages
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,59 +469,71 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             ib_pair[(ibs ^ 1) * TC_BN + pt] = ibn0;
             ib_pair[(ibs ^ 1) * TC_BN + pt + 64] = ibn1;
-            s_cnt2[half][r] = cnt;
+            // Does any row of this pair need its list cut before the next tile?  Common case: no -> one flag store, one
+            // pair barrier, one flag load per tile.  Only when a list may overflow (or at the last tile) do the two warps
+            // exchange their counts and run the cut protocol (two more pair barriers).
+            const bool last = (t + 1 == n_my_tiles);
+            const bool warp_need = __any_sync(kFull, row_ok && cnt > prune_at) || last;
+            if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
             HSK_TICK(2);
             named_bar_sync(bar_id, 64);
             HSK_TICK(3);
-            // cut back the lists of this pair's rows that may overflow on the next tile (16 rows per warp)
-            const bool last = (t + 1 == n_my_tiles);
-            int my_a = 0, my_b = 0;
-            bool my_need = false;
-            if (lane < 16) {   // lane j looks at row j of this warp's 16 rows: two shared-memory reads, then a ballot
-                const int rj = quarter * 32 + half * 16 + lane;
-                my_a = s_cnt2[0][rj];
-                my_b = s_cnt2[1][rj];
-                my_need = s_rowok[rj] && (my_a > prune_at || my_b > prune_at || last);
-            }
-            unsigned need = __ballot_sync(kFull, my_need);
-            while (need) {
-                const int j = __ffs(need) - 1;
-                need &= need - 1;
-                const int rr = quarter * 32 + half * 16 + j;
-                const int cA = __shfl_sync(kFull, my_a, j), cB = __shfl_sync(kFull, my_b, j);
-                uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
-                float ntau;
-                uint64_t ntaukey;
-                // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors)
-                const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
-                                             s_exhi[rr], &ntau, &ntaukey, a.prof);
-                __syncwarp();
-                const int nA = (total + 1) >> 1;
-                if (lane == 0) {
-                    s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA; s_chk2[0][rr] = nA; s_chk2[1][rr] = total - nA;
-                    s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
+            const bool pair_need = (s_need[quarter][0][t & 1] | s_need[quarter][1][t & 1]) != 0;
+            if (pair_need) {
+                s_cnt2[half][r] = cnt;
+                named_bar_sync(bar_id, 64);
+                int my_a = 0, my_b = 0;
+                bool my_need = false;
+                if (lane < 16) {   // lane j looks at row j of this warp's 16 rows
+                    const int rj = quarter * 32 + half * 16 + lane;
+                    my_a = s_cnt2[0][rj];
+                    my_b = s_cnt2[1][rj];
+                    my_need = s_rowok[rj] && (my_a > prune_at || my_b > prune_at || last);
                 }
-                if (last) {
-                    uint64_t keys[kKeysPerLane];
-                    tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
-                    if (a.n_splits == 1) {
-                        const int64_t orow = (int64_t)(m0 + rr) * a.k;
-                        const float base = s_base[rr];
+                unsigned need = __ballot_sync(kFull, my_need);
+                while (need) {
+                    const int j = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int rr = quarter * 32 + half * 16 + j;
+                    const int cA = __shfl_sync(kFull, my_a, j), cB = __shfl_sync(kFull, my_b, j);
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
+                    float ntau;
+                    uint64_t ntaukey;
+                    // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors)
+                    // no exclusion test in the intermediate cuts when k + n_excl raw keys still fit comfortably (each half
+                    // keeps total / 2 <= 160 of its 256 slots); the last cut always tests and keeps <= 192 for the final sort
+                    const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > 288;
+                    const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
+                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey, a.prof);
+                    __syncwarp();
+                    const int nA = (total + 1) >> 1;
+                    if (lane == 0) {
+                        s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA;
+                        s_chk2[0][rr] = check ? nA : 0; s_chk2[1][rr] = check ? total - nA : 0;
+                        s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
+                    }
+                    if (last) {
+                        uint64_t keys[kKeysPerLane];
+                        tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
+                        if (a.n_splits == 1) {
+                            const int64_t orow = (int64_t)(m0 + rr) * a.k;
+                            const float base = s_base[rr];
 #pragma unroll
-                        for (int q = 0; q < kKeysPerLane; ++q) {
-                            const int e = q * 32 + lane;
-                            if (e < a.k) {
-                                a.out_scores[orow + e] = keys[q] ? key_score(keys[q]) + base : -INFINITY;
-                                a.out_ids[orow + e] = key_id(keys[q]);
+                            for (int q = 0; q < kKeysPerLane; ++q) {
+                                const int e = q * 32 + lane;
+                                if (e < a.k) {
+                                    a.out_scores[orow + e] = keys[q] ? key_score(keys[q]) + base : -INFINITY;
+                                    a.out_ids[orow + e] = key_id(keys[q]);
+                                }
                             }
                         }
                     }
                 }
+                HSK_TICK(4);
+                named_bar_sync(bar_id, 64);
+                cnt = s_cnt2[half][r];
+                HSK_TICK(5);
             }
-            HSK_TICK(4);
-            named_bar_sync(bar_id, 64);
-            cnt = s_cnt2[half][r];
-            HSK_TICK(5);
         }
         if (a.prof && lane == 0) {
             for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, pc[i]);

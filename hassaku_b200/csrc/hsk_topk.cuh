@@ -119,6 +119,26 @@ __device__ __forceinline__ void csr_contains_many(const int32_t* __restrict__ id
     for (int r = 0; r < KPL; ++r) found[r] = active[r] && pos[r] < len && __ldg(row + pos[r]) == id[r];
 }
 
+// Membership of KPL ids per lane in a SHORT sorted row the other way round: the row is read once, coalesced (32 ids per
+// round), and every id of it is broadcast to the warp and compared with the lane's KPL register-resident candidates —
+// len * KPL compares per lane but a single global-memory round trip per 32 row entries, instead of log2(len) dependent
+// round trips per candidate.  Use for rows up to a few hundred entries.
+template <int KPL>
+__device__ __forceinline__ void csr_contains_bcast(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, const int32_t (&id)[KPL],
+                                                   bool (&found)[KPL], int lane) {
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) found[r] = false;
+    for (int64_t base = lo; base < hi; base += 32) {
+        const int32_t x = (base + lane < hi) ? __ldg(idx + base + lane) : -2;
+        const int cntr = (int)min((int64_t)32, hi - base);
+        for (int j = 0; j < cntr; ++j) {
+            const int32_t xj = __shfl_sync(kFull, x, j);
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) found[r] |= (id[r] == xj);
+        }
+    }
+}
+
 // Cut a row's candidate list (n <= kCap keys at `list`, global or shared memory) back to its best k, sorted.
 // Returns the new length min(n, k); *thr_key receives the k-th key (0 while the list holds fewer than k).
 template <int KPL = kKeysPerLane>
