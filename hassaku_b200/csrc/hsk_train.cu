@@ -498,6 +498,15 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
     const bool use_tma = !(variant && strcmp(variant, "regs") == 0);
     const char* nored = getenv("HSK_DEBUG_NORED");
     a.debug_flags = (nored && nored[0] == '1') ? 1 : 0;
+    const bool use_q = !variant || strcmp(variant, "q") == 0;   // default; "regs" / "tma" force the warp-per-row kernels
+    if (use_q) {
+        if (variant) a.debug_flags |= 4;   // HSK_TRAIN_FUSED=q: take the quarter-warp kernel whatever the batch size (tests)
+        a.inv_count = loss_kind == HSK_LOSS_BPR ? 1.0 / ((double)B_global * (double)(N1 - 1))
+                    : loss_kind == HSK_LOSS_BCE ? 1.0 / ((double)B_global * (double)N1) : 1.0 / (double)B_global;
+        a.j_per_cta = N1;
+        const int rc = launch_train_fused_q(a, loss_kind, s);
+        if (rc != 1) return rc;
+    }
     if (loss_kind == HSK_LOSS_BPR) {
         a.inv_count = 1.0 / ((double)B_global * (double)(N1 - 1));
         a.j_per_cta = pick_j_per_cta(B, N1 - 1, true);

@@ -30,11 +30,14 @@ struct TrainArgs {
     float* dscores_out;
     const float* __restrict__ dscores_in;
     int32_t* status;
-    int debug_flags;  // bit 0: skip item-gradient reductions (HSK_DEBUG_NORED=1, measurement only)
+    int debug_flags;  // bit 0: skip item-gradient reductions (HSK_DEBUG_NORED=1, measurement only); bit 2: force the quarter-warp kernel
 };
 
 
 // hsk_train_tma.cu: the bulk-copy (TMA) pipelined fused step for bpr / bce; returns HSK_OK or an error code
 int launch_train_fused_tma(const TrainArgs& a, int loss_kind, cudaStream_t s);
+// hsk_train_q.cu: quarter-warp-per-sample fused step for rows of at most 128 floats; returns 1 (no launch) when the
+// shape is outside its range and the caller should use the warp-per-row kernels
+int launch_train_fused_q(const TrainArgs& a, int loss_kind, cudaStream_t s);
 
 }  // namespace hsk

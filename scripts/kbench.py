@@ -63,6 +63,37 @@ def train(args):
     print(f'adamw        flushed med {med*1e3:8.1f} us best {best*1e3:8.1f} us -> {ab["adamw"]/med/1e6:8.0f} GB/s (28 B/param)')
 
 
+def trainraw(args):
+    """fused step kernel alone on random tables / uniform indices of any shape (cfg4: --users 2000000 --items 1000000 --dim 128)"""
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    U, I, d, B, N = args.users, args.items, args.dim, args.batch, args.neg
+    lay = ArenaLayout(U, I, d, False, True, False)
+    arena = torch.randn(lay.n_total, device='cuda') * 0.05
+    g = torch.zeros_like(arena)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    u = [torch.randint(0, U, (B,), device='cuda', generator=gen) for _ in range(4)]
+    i = [torch.randint(0, I, (B, N + 1), device='cuda', generator=gen) for _ in range(4)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    kind = _C.LOSS_KINDS[args.loss]
+    shift = float(np.log(I / N)) if args.loss == 'sampled_softmax' else 0.0
+    ab = 4 * d * B * (N + 2)
+    for v in args.variants.split(','):
+        os.environ['HSK_TRAIN_FUSED'] = v
+        k = [0]
+
+        def fn():
+            _C.mf_train_fused(lay.tables(arena), lay.tables(g), u[k[0] % 4], i[k[0] % 4], kind, shift, acc)
+            k[0] += 1
+        for _ in range(3):
+            fn()
+        med, best = time_kernel(fn, 30, flush)
+        print(f'fused[{v:5s}] {args.loss} U={U} I={I} d={d} B={B} N={N}: flushed med {med*1e3:8.1f} us best {best*1e3:8.1f} us'
+              f' -> {ab/med/1e6:8.0f} GB/s algorithmic (rows read once)')
+        g.zero_()
+
+
 def evalk(args):
     """Evaluator scoring kernel alone: one user batch against the whole item table."""
     import math
@@ -112,9 +143,11 @@ def evalk(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['train', 'eval'])
+    ap.add_argument('what', choices=['train', 'trainraw', 'eval'])
+    ap.add_argument('--neg', type=int, default=50)
+    ap.add_argument('--loss', default='bpr')
     ap.add_argument('--workload', default='cfg2')
-    ap.add_argument('--variants', default='regs,tma')
+    ap.add_argument('--variants', default='regs,tma,q')
     ap.add_argument('--users', type=int, default=6040)
     ap.add_argument('--items', type=int, default=3706)
     ap.add_argument('--dim', type=int, default=402)
@@ -122,4 +155,4 @@ if __name__ == '__main__':
     ap.add_argument('--excl', type=int, default=80)
     ap.add_argument('--iters', type=int, default=10)
     a = ap.parse_args()
-    train(a) if a.what == 'train' else evalk(a)
+    {'train': train, 'trainraw': trainraw, 'eval': evalk}[a.what](a)

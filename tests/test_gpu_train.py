@@ -125,11 +125,29 @@ SHAPES = [
     (300, 200, 7, 33, 3, 'bpr', (True, False, True)),              # tiny ragged: d < 32, odd sizes
     (300, 200, 1024, 17, 5, 'sampled_softmax', (False, False, False)),  # maximum supported d
 ]
+# the quarter-warp kernel (rows <= 128 floats; the default for batches >= 2048) forced at small batches, every loss,
+# K4 = 1..4 float4 per lane, ragged batch (B % 8 != 0) and N + 1 not a multiple of the 4-row unroll
+SHAPES_Q = [
+    (20000, 10677, 128, 512, 100, 'sampled_softmax', (False, True, False), 'q'),
+    (5000, 3000, 128, 256, 50, 'bpr', (False, True, False), 'q'),
+    (5000, 3000, 128, 2048, 50, 'bpr', (False, True, False), None),     # default dispatch reaches it at B >= 2048
+    (1000, 500, 96, 67, 9, 'bce', (True, True, True), 'q'),
+    (1000, 500, 100, 67, 10, 'sampled_softmax', (True, True, True), 'q'),
+    (300, 200, 40, 33, 3, 'bpr', (True, True, True), 'q'),
+    (300, 200, 7, 33, 3, 'bpr', (True, False, True), 'q'),
+    (300, 200, 7, 5, 1, 'bce', (False, False, False), 'q'),
+    (5000, 3000, 128, 256, 50, 'bpr', (False, True, False), 'tma'),    # the warp-per-row kernels stay covered at d <= 128
+    (20000, 10677, 128, 512, 100, 'sampled_softmax', (False, True, False), 'regs'),
+]
 
 
-@pytest.mark.parametrize('U,I,d,B,N,kind,biases', SHAPES)
-def test_fused_step_vs_oracle(U, I, d, B, N, kind, biases):
+@pytest.mark.parametrize('U,I,d,B,N,kind,biases,variant', [s + (None,) for s in SHAPES] + SHAPES_Q)
+def test_fused_step_vs_oracle(U, I, d, B, N, kind, biases, variant, monkeypatch):
     """One full step (forward, loss, backward, AdamW) against the oracle on the same seeded batch."""
+    if variant:
+        monkeypatch.setenv('HSK_TRAIN_FUSED', variant)
+    else:
+        monkeypatch.delenv('HSK_TRAIN_FUSED', raising=False)
     from oracle import mf_oracle as O
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
     from hassaku_b200.train.optim import DenseAdam
@@ -177,8 +195,8 @@ def test_fused_step_vs_oracle(U, I, d, B, N, kind, biases):
         assert abs(loss - float(r['loss'])) <= RTOL * abs(float(r['loss']))
         for n, pr in ref.named_parameters():
             got = dict(model.named_parameters())[n].detach().cpu().numpy()
-            if kind == 'bpr' and n in ('user_bias.weight', 'global_bias'):
-                # BPR is invariant to per-user / global offsets: the true gradient is exactly 0 and what either
+            if kind in ('bpr', 'sampled_softmax') and n in ('user_bias.weight', 'global_bias'):
+                # BPR and the softmax are invariant to per-user / global offsets: the true gradient is exactly 0 and what either
                 # implementation feeds Adam is summation-order rounding residue (|g| ~ 1e-9 ~ eps), which Adam
                 # turns into a step of arbitrary sign.  Only Adam's |dp| <= lr bound is checkable.
                 assert np.abs(got - p_before[n]).max() <= lr * (1 + 1e-3) + wd * lr * np.abs(p_before[n]).max(), (s, n)
