@@ -328,6 +328,24 @@ def run_extras(dev, flush):
 
 
 def run_ours_sharded(args, wl):
+    """Cleanup wrapper: captured CUDA graphs hold NCCL work and dist.destroy_process_group() blocks until they are
+    dropped, so ShardedMF.close() must run even when the body raises (a stalled rank would hold the GPU box)."""
+    import faulthandler
+    import torch.distributed as dist
+    # watchdog: a rank stalled in a collective dumps its Python stack to stderr and exits instead of holding the box
+    faulthandler.dump_traceback_later(float(os.environ.get('HSK_BENCH_WATCHDOG', '900')), exit=True)
+    holder = []
+    try:
+        _run_ours_sharded(args, wl, holder)
+        faulthandler.cancel_dump_traceback_later()
+    finally:
+        for smf in holder:
+            smf.close()
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def _run_ours_sharded(args, wl, holder):
     """N > 1: the item-/user-sharded step (hassaku_b200/sharded.py) with a per-GPU batch of `train_batch_size` samples
     (weak scaling: global batch = N x 8192), NCCL all-to-all for the row / gradient exchanges."""
     import torch
@@ -349,6 +367,7 @@ def run_ours_sharded(args, wl):
     torch.manual_seed(64)
     full = SGDMatrixFactorization(U, I, d, use_item_bias=True)
     smf = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+    holder.append(smf)
     smf.load_full_state_dict(full.state_dict())
     del full
     shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
@@ -378,14 +397,15 @@ def run_ours_sharded(args, wl):
             smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
         b.record()
         barrier()
-        # sustained tail (>= 1.5 s, untimed) so that the clock / throttle samples see the load
-        n_sus = max(K, int(1500.0 / max(a.elapsed_time(b) / K, 1e-3)))
+        # sustained tail (>= 1.5 s, untimed) so that the clock / throttle samples see the load; every step holds
+        # collectives, so the step count must be the SAME on every rank: derive it from the max-over-ranks time
+        t_all = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        n_sus = max(K, int(1500.0 / max(float(t_all.item()) / K, 1e-3)))
         for s in range(n_sus):
             smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
         barrier()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(t_all.item())
     last_loss = smf.pop_loss() / (K + n_sus)
     # e2e: host batches
     u_pin = [torch.from_numpy(x).pin_memory() for x in us]
@@ -434,9 +454,7 @@ def run_ours_sharded(args, wl):
                          'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U},
                 'final_loss': last_loss}
         print(json.dumps(line), flush=True)
-    smf.close()
     dist.barrier()
-    dist.destroy_process_group()
 
 
 def run_ours(args, wl):

@@ -46,6 +46,7 @@ def _declare(lib):
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_n': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_gather_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
+        'hsk_shard_local_index': (i32, [vp, i64, i32, i64, vp, vp]),
         'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_adamw_dense': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, i32, i32, i32, vp]),
         'hsk_sample_negatives': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, C.c_uint64, C.c_uint64, i32, vp, vp, vp, vp]),
@@ -179,6 +180,16 @@ def gather_rows(src, idx, dst, status=None):
     _req(idx, torch.int64, 'idx')
     _check(lib().hsk_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), idx.numel(), src.shape[0], dst.data_ptr(),
                                  _ptr(status), _stream()), 'hsk_gather_rows')
+
+
+def shard_local_index(idx, world: int, rank_stride: int, out=None):
+    """out = (idx % world) * rank_stride + idx // world (owner-sharded row numbering, hassaku_b200/sharded.py)."""
+    _req(idx, torch.int64, 'idx')
+    if out is None:
+        out = torch.empty_like(idx)
+    _check(lib().hsk_shard_local_index(idx.data_ptr(), idx.numel(), world, rank_stride, out.data_ptr(), _stream()),
+           'hsk_shard_local_index')
+    return out
 
 
 def scatter_add_rows(dst, idx, src, status=None):

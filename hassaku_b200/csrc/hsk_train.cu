@@ -596,3 +596,23 @@ extern "C" int hsk_scatter_add_rows(float* dst, int ld, const int64_t* idx, int6
     scatter_add_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(dst, ld, idx, n, n_dst, src, status);
     return check_launch("hsk_scatter_add_rows");
 }
+
+namespace hsk {
+__global__ void __launch_bounds__(256) shard_local_index_kernel(const int64_t* __restrict__ idx, int64_t n, int world,
+                                                                int64_t rank_stride, int64_t* __restrict__ out) {
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const int64_t i = idx[e];
+        out[e] = i < 0 ? i : (i % world) * rank_stride + i / world;
+    }
+}
+}  // namespace hsk
+
+extern "C" int hsk_shard_local_index(const int64_t* idx, int64_t n, int world, int64_t rank_stride, int64_t* out,
+                                     hsk_stream_t stream) {
+    HSK_REQUIRE(n >= 0 && world >= 1 && rank_stride >= 0, "hsk_shard_local_index: bad sizes");
+    if (n == 0) return HSK_OK;
+    HSK_REQUIRE(idx && out, "hsk_shard_local_index: null pointer");
+    const int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+    shard_local_index_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(idx, n, world, rank_stride, out);
+    return check_launch("hsk_shard_local_index");
+}

@@ -58,6 +58,9 @@ class CudaOps:
     def scatter_add_rows(self, table2d: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor):
         _C.scatter_add_rows(table2d, idx, rows.contiguous(), self.status)
 
+    def local_index(self, idx: torch.Tensor, world: int, rank_stride: int) -> torch.Tensor:
+        return _C.shard_local_index(idx.contiguous(), world, rank_stride)
+
     def train_fused(self, lay: ArenaLayout, arena, g_arena, Vc, Ibc, gVc, gIbc, u_local, compact_idx, B_global, kind, shift,
                     loss_accum):
         Uw, _, Ub, _, Gb = lay.views(arena)
@@ -204,12 +207,20 @@ class ShardedMF:
 
     # ---- dense exchange: when the batch touches (nearly) every item anyway ----
     def _dense_buffers(self):
+        """Send / replica buffers of the dense exchange.  One rank's block is [capP, ld] floats: rows [0, cap) are its item
+        rows (cap = ceil(n_items / G), unused rows zero), rows [cap, capP) hold its cap item biases flat - so ONE
+        all-gather moves rows and biases, and ONE reduce-scatter brings back both gradients.  The fused kernel indexes
+        the replica as a [G * capP, ld] table (row of item i = (i % G) * capP + i // G) and needs the biases under the
+        same index, hence the compact `Ib` / `gIb` vectors of G * capP floats filled / drained by one strided copy."""
         if getattr(self, '_dense', None) is None:
             G, lay = self.spec.world, self.layout
             cap = math.ceil(self.spec.n_items / G)
+            capP = cap + math.ceil(cap / lay.ld)
             z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=self.device)
-            self._dense = {'cap': cap, 'V': z(G * cap, lay.ld), 'gV': z(G * cap, lay.ld), 'Ib': z(G * cap), 'gIb': z(G * cap),
-                           'Vpad': z(cap, lay.ld), 'gVpad': z(cap, lay.ld), 'Ibpad': z(cap), 'gIbpad': z(cap)}
+            grads = z(G * capP * lay.ld + G * capP)          # [gV replica | gIb compact]: one memset per step
+            self._dense = {'cap': cap, 'capP': capP, 'send': z(capP, lay.ld), 'V': z(G * capP, lay.ld), 'Ib': z(G * capP),
+                           'grads': grads, 'gV': grads[:G * capP * lay.ld].view(G * capP, lay.ld),
+                           'gIb': grads[G * capP * lay.ld:], 'recv': z(capP, lay.ld)}
         return self._dense
 
     def _reduce_scatter(self, out: torch.Tensor, inp: torch.Tensor):
@@ -220,70 +231,52 @@ class ShardedMF:
             n = out.numel()
             out.copy_(inp.view(-1)[self.spec.rank * n:(self.spec.rank + 1) * n].view_as(out))
 
-    def train_step_dense(self, u_global: torch.Tensor, i_global: torch.Tensor, B_global: int, loss_kind: str,
-                         neg_shift: float, lr: float, wd: float, decoupled: bool = True):
-        """Same step with a DENSE exchange: all-gather of the item shards into a rank-major replica (row of item i =
-        (i % G) * cap + i // G), the ordinary fused kernel on it, reduce-scatter of the dense item gradient to the owners.
-        No dedupe, no host sync, fixed shapes (CUDA-graph friendly).  The right choice when B (N + 1) >> n_items
-        (cfg2: 418 k slots on 3 706 items, every row is requested by every rank each step anyway)."""
-        G, r, lay = self.spec.world, self.spec.rank, self.layout
+    def _dense_exchange_and_fused(self, u_global, i_global, B_global, loss_kind, neg_shift):
+        """All-gather of the item shards into the rank-major replica, the ordinary fused kernel on it, reduce-scatter of
+        the dense item gradient to the owners.  No dedupe, no host sync, fixed shapes (CUDA-graph friendly): 2 collectives,
+        1 memset, 2 index kernels, 4 small copies around the fused kernel."""
+        G, lay = self.spec.world, self.layout
         ld, nl = lay.ld, lay.n_items
         D = self._dense_buffers()
-        cap = D['cap']
+        cap, capP = D['cap'], D['capP']
         _, _, _, Ib, _ = lay.views(self.arena)
-        D['Vpad'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
-        dist.all_gather_into_tensor(D['V'], D['Vpad'], group=self.group)
-        if Ib is not None:
-            D['Ibpad'][:nl] = Ib.view(-1)
-            dist.all_gather_into_tensor(D['Ib'], D['Ibpad'], group=self.group)
-        rows = (i_global % G) * cap + torch.div(i_global, G, rounding_mode='floor')
-        u_local = torch.div(u_global, G, rounding_mode='floor')
-        D['gV'].zero_()
-        D['gIb'].zero_()
-        self.ops.train_fused(lay, self.arena, self.g, D['V'], D['Ib'] if Ib is not None else None, D['gV'],
-                             D['gIb'] if Ib is not None else None, u_local, rows.contiguous(), B_global,
+        has_ib = Ib is not None
+        D['send'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
+        if has_ib:
+            D['send'].view(-1)[cap * ld:cap * ld + nl] = Ib.view(-1)
+        dist.all_gather_into_tensor(D['V'], D['send'], group=self.group)
+        if has_ib:
+            D['Ib'].view(G, capP)[:, :cap] = D['V'].view(G, capP * ld)[:, cap * ld:cap * ld + cap]
+        rows = self.ops.local_index(i_global, G, capP)
+        u_local = self.ops.local_index(u_global, G, 0)
+        D['grads'].zero_()
+        self.ops.train_fused(lay, self.arena, self.g, D['V'], D['Ib'] if has_ib else None, D['gV'],
+                             D['gIb'] if has_ib else None, u_local, rows, B_global,
                              _C.LOSS_KINDS[loss_kind], neg_shift, self.loss_accum)
-        self._reduce_scatter(D['gVpad'], D['gV'])
-        self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['gVpad'][:nl])
-        if Ib is not None:
-            self._reduce_scatter(D['gIbpad'], D['gIb'])
-            lay.views(self.g)[3].view(-1).add_(D['gIbpad'][:nl])
+        if has_ib:
+            D['gV'].view(G, capP * ld)[:, cap * ld:cap * ld + cap] = D['gIb'].view(G, capP)[:, :cap]
+        self._reduce_scatter(D['recv'], D['gV'])
+        self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['recv'][:nl])
+        if has_ib:
+            lay.views(self.g)[3].view(-1).add_(D['recv'].view(-1)[cap * ld:cap * ld + nl])
         gGb = lay.views(self.g)[4]
         if gGb is not None:
             dist.all_reduce(gGb, group=self.group)
+
+    def train_step_dense(self, u_global: torch.Tensor, i_global: torch.Tensor, B_global: int, loss_kind: str,
+                         neg_shift: float, lr: float, wd: float, decoupled: bool = True):
+        """Same step with a DENSE exchange (see _dense_exchange_and_fused).  The right choice when B (N + 1) >> n_items
+        (cfg2: 418 k slots on 3 706 items, every row is requested by every rank each step anyway)."""
+        self._dense_exchange_and_fused(u_global, i_global, B_global, loss_kind, neg_shift)
         self.t += 1
         self.ops.adamw(self.arena, self.m, self.v, self.g, lr, wd, self.t, decoupled)
 
-    # ---- the dense step as ONE CUDA graph (fixed shapes): removes ~20 launches / collectives worth of host latency ----
+    # ---- the dense step as ONE CUDA graph (fixed shapes): removes the launches / collectives worth of host latency ----
     CONST_TABLE_STEPS = 4096
 
     def _dense_body(self, u_global, i_global, B_global, loss_kind, neg_shift, consts_dev, decoupled):
         """train_step_dense with the AdamW scalars read from device memory (capturable)."""
-        G, lay = self.spec.world, self.layout
-        ld, nl = lay.ld, lay.n_items
-        D = self._dense_buffers()
-        cap = D['cap']
-        _, _, _, Ib, _ = lay.views(self.arena)
-        D['Vpad'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
-        dist.all_gather_into_tensor(D['V'], D['Vpad'], group=self.group)
-        if Ib is not None:
-            D['Ibpad'][:nl] = Ib.view(-1)
-            dist.all_gather_into_tensor(D['Ib'], D['Ibpad'], group=self.group)
-        rows = (i_global % G) * cap + torch.div(i_global, G, rounding_mode='floor')
-        u_local = torch.div(u_global, G, rounding_mode='floor')
-        D['gV'].zero_()
-        D['gIb'].zero_()
-        self.ops.train_fused(lay, self.arena, self.g, D['V'], D['Ib'] if Ib is not None else None, D['gV'],
-                             D['gIb'] if Ib is not None else None, u_local, rows.contiguous(), B_global,
-                             _C.LOSS_KINDS[loss_kind], neg_shift, self.loss_accum)
-        self._reduce_scatter(D['gVpad'], D['gV'])
-        self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['gVpad'][:nl])
-        if Ib is not None:
-            self._reduce_scatter(D['gIbpad'], D['gIb'])
-            lay.views(self.g)[3].view(-1).add_(D['gIbpad'][:nl])
-        gGb = lay.views(self.g)[4]
-        if gGb is not None:
-            dist.all_reduce(gGb, group=self.group)
+        self._dense_exchange_and_fused(u_global, i_global, B_global, loss_kind, neg_shift)
         _C.adamw_dense_graph(self.arena, self.m, self.v, self.g, consts_dev, decoupled=decoupled, adam_l2=not decoupled)
 
     def _fill_const_table(self, gs, lr, wd):
@@ -307,12 +300,10 @@ class ShardedMF:
                   'consts': torch.empty(8, dtype=torch.float32, device=dev),
                   'step_idx': torch.zeros(1, dtype=torch.int64, device=dev)}
             self._fill_const_table(gs, lr, wd)
-            # NCCL channels for these collectives must exist before capture: warm them up on scratch buffers
+            # NCCL channels for these collectives must exist before capture: warm them up on the gradient buffers
             D = self._dense_buffers()
-            dist.all_gather_into_tensor(D['gV'], D['gVpad'], group=self.group)
-            self._reduce_scatter(D['gVpad'], D['gV'])
-            dist.all_gather_into_tensor(D['gIb'], D['gIbpad'], group=self.group)
-            self._reduce_scatter(D['gIbpad'], D['gIb'])
+            dist.all_gather_into_tensor(D['gV'], D['recv'], group=self.group)
+            self._reduce_scatter(D['recv'], D['gV'])
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):

@@ -106,6 +106,13 @@ HSK_API int hsk_gather_rows(const float* src, int ld, const int64_t* idx, int64_
 HSK_API int hsk_scatter_add_rows(float* dst, int ld, const int64_t* idx, int64_t n, int64_t n_dst, const float* src,
                                  int32_t* status, hsk_stream_t stream);
 
+/* Owner-sharded index arithmetic of the multi-GPU step (row i lives on rank i % world at local row i / world):
+ * out[e] = (idx[e] % world) * rank_stride + idx[e] / world.  rank_stride = rows per rank of a rank-major replica
+ * (dense exchange), or 0 for the plain local row.  Negative indices pass through unchanged so that the consumer's
+ * bounds check still reports them.  out may alias idx. */
+HSK_API int hsk_shard_local_index(const int64_t* idx, int64_t n, int world, int64_t rank_stride, int64_t* out,
+                                  hsk_stream_t stream);
+
 /* ---- a8: torch.optim.AdamW(params, lr, weight_decay).step over a flat fp32 range (trainer.py:52-53,147) ---
  * Dense decoupled-decay Adam over ALL n elements, every step (zero-gradient rows included), in one streaming
  * pass: reads p, m, v, g; writes p, m, v and (zero_grad != 0) g = 0, replacing optimizer.zero_grad().

@@ -19,6 +19,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, out_dir):
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)   # a stalled collective must not hold the GPU box: dump the stack and exit
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -88,6 +90,9 @@ def test_sharded_step_and_eval_match_single_gpu(world, tmp_path):
 
 def _worker_graph(rank, world, port, out_dir):
     """The CUDA-graph replay of the dense step equals the eager dense step (fixed local batch shape)."""
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)
+    models = []
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -103,6 +108,7 @@ def _worker_graph(rank, world, port, out_dir):
                 p.copy_(torch.randn_like(p) * (1 / math.sqrt(d) if p.shape[-1] == d else 0.1))
         a = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
         b = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
+        models += [a, b]
         a.load_full_state_dict(full.state_dict()); b.load_full_state_dict(full.state_dict())
         rng = np.random.RandomState(rank)
         for s in range(5):
@@ -112,14 +118,17 @@ def _worker_graph(rank, world, port, out_dir):
             b.step(u, i, B * world, 'bpr', 0.0, 1e-3, 1e-4, exchange='dense_graph')
         torch.cuda.synchronize()
         assert a.t == b.t == 5
-        assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v)
+        # same kernels and arithmetic; the fp32 atomics of the fused kernel land in a different order run to run
+        for x, y in ((a.m, b.m), (a.v, b.v)):
+            assert float((x - y).abs().max() / x.abs().max()) < 1e-5
         err = float((a.arena - b.arena).abs().max() / a.arena.abs().max())
         assert err < 1e-6, err     # atomics order differs run to run; the arithmetic is identical
         assert abs(a.pop_loss() - b.pop_loss()) < 1e-9
-        b.close()
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
     finally:
+        for mdl in models:      # captured graphs hold NCCL work: destroy_process_group() blocks until they are dropped
+            mdl.close()
         dist.destroy_process_group()
 
 

@@ -21,6 +21,9 @@ class TorchRefOps:
     def gather_rows(self, table2d, idx):
         return table2d[idx].contiguous()
 
+    def local_index(self, idx, world, rank_stride):
+        return (idx % world) * rank_stride + torch.div(idx, world, rounding_mode='floor')
+
     def scatter_add_rows(self, table2d, idx, rows):
         table2d.index_add_(0, idx, rows)
 
