@@ -65,10 +65,21 @@ class ClockSampler:
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, enabled=True):
+        """gpu_index: one index or a comma-separated list (N > 1: rank 0 samples every GPU of the job; one nvidia-smi
+        per rank would put N processes on the driver's global lock inside the timed region)."""
+        self.rows, self.proc, self.gpu, self.enabled = [], None, gpu_index, enabled
+
+    def wait_ready(self, timeout=8.0):
+        """Block until the first sample arrived: nvidia-smi's start-up (NVML init over every GPU of the box, hundreds of
+        ms, serialised on a driver lock) must be over BEFORE the timed region starts."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
@@ -387,11 +398,14 @@ def _run_ours_sharded(args, wl, holder):
         dist.barrier()
         torch.cuda.synchronize()
 
-    for s in range(W):
+    # the W warm-up steps asked for, and at least 30: the first replays of a freshly captured graph with NCCL nodes are slow
+    for s in range(max(W, 30)):
         smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local_rank) as clk:
+    # rank 0 samples the clocks of every GPU of the job; its start-up is over before the barrier that opens the region
+    with ClockSampler(','.join(str(g) for g in range(world)), enabled=(rank == 0)) as clk:
+        clk.wait_ready()
+        barrier()
         a.record()
         for s in range(K):
             smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
@@ -523,6 +537,8 @@ def run_ours(args, wl):
     barrier()
     clk = ClockSampler(local_rank)
     clk.__enter__()   # samples clocks / throttle reasons across every timed region below (stopped after region 2b)
+    clk.wait_ready()
+    barrier()
     for s in range(K):
         flush.zero_()
         ev0[s].record()
