@@ -401,26 +401,37 @@ def _run_ours_sharded(args, wl, holder):
     # the W warm-up steps asked for, and at least 30: the first replays of a freshly captured graph with NCCL nodes are slow
     for s in range(max(W, 30)):
         smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+    smf.pop_loss()      # reset the loss accumulator (collective: every rank calls it)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # rank 0 samples the clocks of every GPU of the job; its start-up is over before the barrier that opens the region
     with ClockSampler(','.join(str(g) for g in range(world)), enabled=(rank == 0)) as clk:
         clk.wait_ready()
         barrier()
+        # (i) pilot region: K steps, only to size the sustained run (reported as `pilot_ms_per_step`)
+        p0.record()
+        for s in range(K):
+            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+        p1.record()
+        barrier()
+        # every step holds collectives, so step counts must be the SAME on every rank: derive them from max-over-ranks times
+        t_pilot = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_pilot, op=dist.ReduceOp.MAX)
+        # (ii) sustained run (>= 1.5 s, untimed): clocks settle under load and the sampler sees it
+        n_sus = max(K, int(1500.0 / max(float(t_pilot.item()) / K, 1e-3)))
+        for s in range(n_sus):
+            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+        barrier()
+        # (iii) THE timed region: exactly K steps between barrier + synchronize, max over ranks
         a.record()
         for s in range(K):
             smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
         b.record()
         barrier()
-        # sustained tail (>= 1.5 s, untimed) so that the clock / throttle samples see the load; every step holds
-        # collectives, so the step count must be the SAME on every rank: derive it from the max-over-ranks time
-        t_all = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        n_sus = max(K, int(1500.0 / max(float(t_all.item()) / K, 1e-3)))
-        for s in range(n_sus):
-            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
-        barrier()
+    t_all = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms = float(t_all.item())
-    last_loss = smf.pop_loss() / (K + n_sus)
+    last_loss = smf.pop_loss() / (2 * K + n_sus)
     # e2e: host batches
     u_pin = [torch.from_numpy(x).pin_memory() for x in us]
     i_pin = [torch.from_numpy(x).pin_memory() for x in its]
@@ -464,6 +475,7 @@ def _run_ours_sharded(args, wl, holder):
                              'step': {'algorithmic_bytes_per_gpu': 2 * ab['A'] + 28 * ab['P'] // world,
                                       'note': 'per-kernel roofline is reported by the N = 1 run'}},
                 'clocks': clk.summary(),
+                'pilot_ms_per_step': float(t_pilot.item()) / K,
                 'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
                          'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U},
                 'final_loss': last_loss}
