@@ -41,6 +41,8 @@ def install(device_loaders: bool = False):
     r_eval = importlib.import_module('eval.eval')
     # model factory: AlgorithmsEnum.mf.value.build_from_conf (experiment_helper.py:39)
     rebind(r_alg.SGDMatrixFactorization, 'build_from_conf', staticmethod(h_alg.SGDMatrixFactorization.build_from_conf))
+    # AlgorithmsEnum.sgdbias: the bias-only baseline runs on the same kernels (embedding_dim 1, zero embedding tables)
+    rebind(r_alg.SGDBaseline, 'build_from_conf', staticmethod(h_alg.SGDBaseline.build_from_conf))
     # loss factories: RecommenderSystemLossesEnum[...].value.build_from_conf (experiment_helper.py:42)
     for name in ('RecBinaryCrossEntropy', 'RecBayesianPersonalizedRankingLoss', 'RecSampledSoftmaxLoss'):
         rebind(getattr(r_loss, name), 'build_from_conf', staticmethod(getattr(h_loss, name).build_from_conf))
@@ -49,6 +51,8 @@ def install(device_loaders: bool = False):
     for mod in (r_trainer, r_eval):
         rebind(mod, 'FullEvaluator', h_eval.FullEvaluator)
         rebind(mod, 'evaluate_recommender_algorithm', h_eval.evaluate_recommender_algorithm)
+    # sweep_test.py imports the calibration decorator from eval.eval by name
+    rebind(r_eval, 'FullEvaluatorCalibrationDecorator', h_eval.FullEvaluatorCalibrationDecorator)
     try:
         r_helper = importlib.import_module('experiment_helper')
         rebind(r_helper, 'Trainer', h_trainer.Trainer)

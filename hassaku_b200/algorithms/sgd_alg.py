@@ -84,8 +84,9 @@ class _MfScoreFn(torch.autograd.Function):
         g_arena = torch.zeros(lay.n_total, dtype=torch.float32, device=dscores.device)
         _C.mf_scatter_grads(model._tables(), lay.tables(g_arena), u_idxs, i_idxs,
                             dscores.contiguous().float(), model._status())
-        gU, gV, gUb, gIb, gGb = lay.views(g_arena)
-        return None, None, None, gU, gV, gUb, gIb, gGb
+        grads = lay.views(g_arena)   # (gU, gV, gUb, gIb, gGb); None where the model has no such table
+        need = ctx.needs_input_grad[3:]
+        return (None, None, None) + tuple(g if n else None for g, n in zip(grads, need))
 
 
 class SGDMatrixFactorization(SGDBasedRecommenderAlgorithm):
@@ -236,3 +237,83 @@ class SGDMatrixFactorization(SGDBasedRecommenderAlgorithm):
         # sgd_alg.py:181-184
         return SGDMatrixFactorization(dataset.n_users, dataset.n_items, conf['embedding_dim'], conf['use_user_bias'],
                                       conf['use_item_bias'], conf['use_global_bias'])
+
+
+class SGDBaseline(SGDMatrixFactorization):
+    """Bias-only baseline `user_bias[u] + item_bias[i] + global_bias` (algorithms/sgd_alg.py:72-107) on the SAME kernels:
+    it is the matrix factorization with embedding_dim 1 whose two embedding tables are identically zero.  Zero
+    embeddings stay exactly zero under every supported optimizer (their gradient ds * 0 is 0, so m = v = 0 and the
+    Adam / Adagrad update 0 / (0 + eps) is 0; weight decay of 0 is 0), so training, the fused step, the sharded step and
+    the full-rank evaluator all work unchanged.  Parameters, `state_dict()` names / shapes and the initialisation order
+    are the reference's (`user_bias.weight [U, 1]`, `item_bias.weight [I, 1]`, `global_bias [1]`); the zero tables are
+    plain tensors inside the arena, not parameters."""
+
+    def __init__(self, n_users: int, n_items: int):
+        SGDBasedRecommenderAlgorithm.__init__(self)
+        self.n_users = n_users
+        self.n_items = n_items
+        self.embedding_dim = 1
+        self.use_user_bias = self.use_item_bias = self.use_global_bias = True
+        # reference construction order (sgd_alg.py:83-87): same torch seed -> bit-identical initial weights
+        self.user_bias = nn.Embedding(self.n_users, 1)
+        self.item_bias = nn.Embedding(self.n_items, 1)
+        self.global_bias = nn.Parameter(torch.zeros(1), requires_grad=True)
+        self.apply(general_weight_init)
+
+        self.layout = ArenaLayout(n_users, n_items, 1, True, True, True)
+        arena = torch.zeros(self.layout.n_total, dtype=torch.float32)
+        _, _, Ub, Ib, Gb = self.layout.views(arena)
+        with torch.no_grad():
+            Ub.copy_(self.user_bias.weight)
+            Ib.copy_(self.item_bias.weight)
+            Gb.copy_(self.global_bias)
+        self._status_flag = None
+        self._set_arena(arena)
+        self.name = 'SGDBaseline'
+        logging.info(f'Built {self.name} module\n')
+
+    def _set_arena(self, arena: torch.Tensor):
+        self._arena = arena
+        Uw, Vw, Ub, Ib, Gb = self.layout.views(arena)
+        # the zero embedding tables: attributes with a `.weight`, like nn.Embedding, for the code that reads
+        # `alg.user_embeddings.weight` (TopKScorer); not registered as modules / parameters
+        object.__setattr__(self, 'user_embeddings', _FrozenTable(Uw))
+        object.__setattr__(self, 'item_embeddings', _FrozenTable(Vw))
+        self.user_bias.weight = nn.Parameter(Ub)
+        self.item_bias.weight = nn.Parameter(Ib)
+        self.global_bias = nn.Parameter(Gb)
+        self._tables_cache = None
+        self._status_flag = None
+
+    def get_user_representations(self, u_idxs: torch.Tensor) -> torch.Tensor:
+        return self.user_bias(u_idxs)                       # sgd_alg.py:93-94
+
+    def get_item_representations(self, i_idxs: torch.Tensor) -> torch.Tensor:
+        return self.item_bias(i_idxs).squeeze()             # sgd_alg.py:96-97
+
+    def combine_user_item_representations(self, u_repr, i_repr) -> torch.Tensor:
+        return u_repr + i_repr + self.global_bias           # sgd_alg.py:99-102
+
+    def forward(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor) -> torch.Tensor:
+        if not self._arena.is_cuda:
+            raise _C.HskError('SGDBaseline.forward needs the model on a CUDA device (hassaku_b200 has no CPU path): '
+                              'call model.to("cuda")')
+        squeeze = i_idxs.dim() == 1
+        if squeeze:
+            i_idxs = i_idxs.unsqueeze(1)
+        u_idxs = u_idxs.to(self._arena.device, torch.int64).contiguous()
+        i_idxs = i_idxs.to(self._arena.device, torch.int64).contiguous()
+        out = _MfScoreFn.apply(self, u_idxs, i_idxs, None, None, self.user_bias.weight, self.item_bias.weight,
+                               self.global_bias)
+        return out.squeeze(1) if squeeze else out
+
+    @staticmethod
+    def build_from_conf(conf: dict, dataset):
+        return SGDBaseline(dataset.n_users, dataset.n_items)   # sgd_alg.py:104-106
+
+
+class _FrozenTable:
+    """`.weight` holder for the all-zero embedding tables of SGDBaseline (a view of the arena, never trained)."""
+
+    def __init__(self, weight: torch.Tensor):
+        self.weight = weight

@@ -18,7 +18,8 @@ from tqdm import tqdm
 from hassaku_b200 import _C
 from hassaku_b200.algorithms.base_classes import RecommenderAlgorithm
 from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
-from hassaku_b200.eval.metrics import dense_topk, discount_table
+from hassaku_b200.eval.metrics import (dense_topk, discount_table, hellinger_distance, jensen_shannon_distance,
+                                       kl_divergence)
 
 METRIC_ORDER = ('precision@{}', 'recall@{}', 'ndcg@{}')  # eval.py:78-80; column order of hsk_rank_metrics
 
@@ -144,6 +145,124 @@ class FullEvaluator:
                         key = name.format(k) if g == -1 else f'group_{g}_' + name.format(k)
                         metrics_dict[key] = per_user[sel, t, c]
         self._reset_internal_dict()
+        return metrics_dict
+
+
+class FullEvaluatorCalibrationDecorator(FullEvaluator):
+    """Reference `FullEvaluatorCalibrationDecorator` (eval/eval.py:121-208): adds, for k in CALIBRATION_K_VALUES,
+    `{prefix}_hellinger_distance@k`, `{prefix}_jensen_shannon_distance@k`, `{prefix}_kl_divergence@k` between each
+    user's training distribution over tags (`user_tag_mtx[u]`) and the distribution of the top-k recommended items
+    (mean of `item_tag_mtx` rows, smoothed with `beta_smoothening` of the training distribution, Steck eq. 5).
+    Decorators nest (sweep_test.py:68-69: 'tag' then 'pop').  It consumes the ranked ids the wrapped evaluator already
+    has: the fused path (`eval_batch_topk`) computes no second top-k; sums live on the device until `get_results()`."""
+    CALIBRATION_K_VALUES = [5, 10, 50, 100]
+    _NAMES = ('hellinger_distance@{}', 'jensen_shannon_distance@{}', 'kl_divergence@{}')
+    _MAX_GATHER_BYTES = 256 << 20   # item_tag_mtx[top ids] is [B, k, n_tags] fp32: chunk the users above this
+
+    def __init__(self, full_evaluator: FullEvaluator, item_tag_mtx: torch.Tensor, user_tag_mtx: torch.Tensor,
+                 metric_name_prefix: str = 'tag', beta_smoothening: float = .01):
+        assert 0 <= beta_smoothening <= 1, 'Beta value out of bounds'
+        self.full_evaluator = full_evaluator
+        self.item_tag_mtx = item_tag_mtx
+        self.user_tag_mtx = user_tag_mtx
+        self.metric_name_prefix = metric_name_prefix
+        self.beta_smoothening = beta_smoothening
+        self._cal_reset()
+
+    @property
+    def aggr_by_group(self):
+        return self.full_evaluator.aggr_by_group
+
+    @property
+    def K_VALUES(self):
+        return self.full_evaluator.K_VALUES
+
+    def _cal_reset(self):
+        self._cal_sums = None
+        self._cal_counts = None
+        self._cal_per_user = []
+        self._cal_group = None
+
+    def _reset_internal_dict(self):
+        self.full_evaluator._reset_internal_dict()
+        self._cal_reset()
+
+    def get_n_groups(self):
+        return self.full_evaluator.get_n_groups()
+
+    def get_user_to_user_group(self):
+        return self.full_evaluator.get_user_to_user_group()
+
+    def _cal_ks(self):
+        return sorted(self.CALIBRATION_K_VALUES, reverse=True)
+
+    def _calibration(self, u_idxs: torch.Tensor, top_ids: torch.Tensor):
+        dev = top_ids.device
+        ks, G = self._cal_ks(), self.get_n_groups()
+        assert top_ids.shape[-1] >= ks[0], 'Top-k indexes are shorter than the largest calibration k'
+        self.user_tag_mtx = self.user_tag_mtx.to(dev)
+        self.item_tag_mtx = self.item_tag_mtx.to(dev)
+        if self._cal_sums is None:
+            self._cal_sums = torch.zeros((1 + G, len(ks), 3), dtype=torch.float64, device=dev)
+            self._cal_counts = torch.zeros(1 + G, dtype=torch.int64, device=dev)
+            if G > 0:
+                g = self.get_user_to_user_group()
+                g = g if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g))
+                self._cal_group = g.to(device=dev, dtype=torch.int64)
+        u = u_idxs.to(dev, torch.int64)
+        B, T = len(u), self.item_tag_mtx.shape[-1]
+        chunk = max(1, min(B, self._MAX_GATHER_BYTES // max(1, ks[0] * T * 4)))
+        res = torch.empty((B, len(ks), 3), dtype=torch.float32, device=dev)
+        for s in range(0, B, chunk):
+            p = self.user_tag_mtx[u[s:s + chunk]]                               # training distribution [b, T]
+            rows = self.item_tag_mtx[top_ids[s:s + chunk, :ks[0]].long()]        # [b, k_max, T]
+            for t, k in enumerate(ks):
+                q = rows[:, :k].sum(1) / k                                       # recommendation distribution
+                q = self.beta_smoothening * p + (1 - self.beta_smoothening) * q  # eval.py:180-182
+                res[s:s + chunk, t, 0] = hellinger_distance(p, q)
+                res[s:s + chunk, t, 1] = jensen_shannon_distance(p, q)
+                res[s:s + chunk, t, 2] = kl_divergence(p, q)                     # target distribution first (eval.py:192)
+        grp = self._cal_group[u] if G > 0 else None
+        if self.aggr_by_group:
+            self._cal_sums[0] += res.double().sum(0)
+            self._cal_counts[0] += B
+            if G > 0:
+                self._cal_sums[1:].index_add_(0, grp, res.double())
+                self._cal_counts[1:] += torch.bincount(grp, minlength=G)[:G]
+        else:
+            self._cal_per_user.append((res, grp))
+
+    def eval_batch(self, u_idxs: torch.Tensor, logits: torch.Tensor, y_true: torch.Tensor):
+        self.full_evaluator.eval_batch(u_idxs, logits, y_true)
+        if logits.is_cuda:
+            _, ids = dense_topk(logits, self._cal_ks()[0])
+        else:   # host tensors only reach this when the wrapped evaluator accepts them (tests with a stub evaluator)
+            ids = logits.topk(self._cal_ks()[0]).indices
+        self._calibration(u_idxs, ids)
+
+    def eval_batch_topk(self, u_idxs: torch.Tensor, top_ids: torch.Tensor, labels: DeviceCSR):
+        self.full_evaluator.eval_batch_topk(u_idxs, top_ids, labels)
+        self._calibration(u_idxs, top_ids)
+
+    def get_results(self):
+        metrics_dict = self.full_evaluator.get_results()
+        ks, G = self._cal_ks(), self.get_n_groups()
+        if self._cal_sums is not None:
+            if self.aggr_by_group:
+                sums, counts = self._cal_sums.cpu().numpy(), self._cal_counts.cpu().numpy()
+            else:
+                per_user = torch.cat([r for r, _ in self._cal_per_user]).cpu().numpy()
+                grp = torch.cat([g for _, g in self._cal_per_user]).cpu().numpy() if G > 0 else None
+            for g in range(-1, G):
+                for t, k in enumerate(ks):
+                    for c, name in enumerate(self._NAMES):
+                        key = self.metric_name_prefix + '_' + name.format(k)
+                        key = key if g == -1 else f'group_{g}_' + key
+                        if self.aggr_by_group:
+                            metrics_dict[key] = float(sums[g + 1, t, c]) / int(counts[g + 1])
+                        else:
+                            metrics_dict[key] = per_user[slice(None) if g == -1 else (grp == g), t, c]
+        self._cal_reset()
         return metrics_dict
 
 

@@ -70,3 +70,22 @@ def ndcg_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, agg
                     idx_topk: torch.Tensor = None):
     """NDCG@k with binary relevance (metrics.py:70-105), clamped to 1, 0 for users without positives."""
     return _one_metric(2, logits, y_true, k, aggr_sum, idx_topk)
+
+
+# ---- calibration distances between per-user distributions over tags / popularity buckets (eval/metrics.py:108-152) ----
+# Plain torch on whatever device the inputs live on: consumers of the top-k ids, [B, n_tags] work per batch.
+def hellinger_distance(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """sqrt(1/2 * sum_t (sqrt p_t - sqrt q_t)^2), shape [*]; symmetric (metrics.py:108-119)."""
+    return torch.sqrt(.5 * ((torch.sqrt(p) - torch.sqrt(q)) ** 2).sum(-1))
+
+
+def kl_divergence(true_p: torch.Tensor, model_q: torch.Tensor) -> torch.Tensor:
+    """sum_t p_t (log p_t - log q_t), shape [*]; NaN / inf where either is 0 on an event, like the reference
+    (metrics.py:122-131)."""
+    return (true_p * (true_p.log() - model_q.log())).sum(-1)
+
+
+def jensen_shannon_distance(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """sqrt(1/2 KL(p || m) + 1/2 KL(q || m)), m = (p + q) / 2 (metrics.py:134-152)."""
+    m = .5 * (p + q)
+    return torch.sqrt(.5 * (kl_divergence(p, m) + kl_divergence(q, m)))

@@ -36,18 +36,22 @@ def tiny_data():
     return make_interactions(**TINY)
 
 
-def gen_train(name, loss_kind, d, use_user_bias, use_item_bias, use_global_bias, optimizer, B, N, lr, wd, n_steps=3):
-    from algorithms.sgd_alg import SGDMatrixFactorization
+def gen_train(name, loss_kind, d, use_user_bias, use_item_bias, use_global_bias, optimizer, B, N, lr, wd, n_steps=3,
+              model_kind='mf'):
+    from algorithms.sgd_alg import SGDBaseline, SGDMatrixFactorization
     from train.rec_losses import RecommenderSystemLossesEnum
     data = tiny_data()
     U, I = data.n_users, data.n_items
     torch.manual_seed(64)
     rng = np.random.RandomState(64)
-    model = SGDMatrixFactorization(U, I, d, use_user_bias, use_item_bias, use_global_bias)
+    if model_kind == 'baseline':
+        model = SGDBaseline(U, I)
+    else:
+        model = SGDMatrixFactorization(U, I, d, use_user_bias, use_item_bias, use_global_bias)
     # larger-than-init weights so that scores/gradients are O(1) and the comparison is meaningful
     with torch.no_grad():
         for p in model.parameters():
-            p.copy_(torch.randn_like(p) * (1.0 / np.sqrt(d) if p.shape[-1] == d else 0.1))
+            p.copy_(torch.randn_like(p) * (0.3 if model_kind == 'baseline' else 1.0 / np.sqrt(d) if p.shape[-1] == d else 0.1))
     conf = {'train_neg_strategy': 'uniform', 'neg_train': N}
 
     class _DS:
@@ -56,7 +60,7 @@ def gen_train(name, loss_kind, d, use_user_bias, use_item_bias, use_global_bias,
     loss_obj = RecommenderSystemLossesEnum[loss_kind].value.build_from_conf(conf, _DS())
     opt_cls = {'adamw': torch.optim.AdamW, 'adam': torch.optim.Adam, 'adagrad': torch.optim.Adagrad}[optimizer]
     opt = opt_cls(model.parameters(), lr=lr, weight_decay=wd)
-    out = {'meta_loss': loss_kind, 'meta_optimizer': optimizer, 'meta_dims': np.array([U, I, d, B, N]),
+    out = {'meta_loss': loss_kind, 'meta_optimizer': optimizer, 'meta_dims': np.array([U, I, d or 0, B, N]),
            'meta_hparams': np.array([lr, wd]),
            'meta_flags': np.array([use_user_bias, use_item_bias, use_global_bias])}
     for n, p in model.state_dict().items():
@@ -186,10 +190,80 @@ def gen_metrics_kat():
     print('metrics_kat ok')
 
 
+def gen_calibration():
+    """Reference FullEvaluatorCalibrationDecorator (eval/eval.py:121-208), nested 'tag' + 'pop' like sweep_test.py:68-69,
+    over two dense batches; aggregated (with 2 user groups) and per-user (aggr_by_group=False) results."""
+    from eval.eval import FullEvaluator, FullEvaluatorCalibrationDecorator
+    rng = np.random.RandomState(7)
+    U, I, T, P = 40, 150, 7, 3
+    logits = torch.from_numpy(rng.randn(U, I).astype(np.float32))
+    y_true = torch.from_numpy((rng.rand(U, I) < 0.05).astype(np.float32))
+    tags = (rng.rand(I, T) < 0.3).astype(np.float32)
+    tags[:5] = 0.                                        # items without tags (data_utils.py:413)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        item_tag = np.nan_to_num(tags / tags.sum(-1, keepdims=True)).astype(np.float32)
+    train = (rng.rand(U, I) < 0.1).astype(np.float32)
+    train[:, 0] = 1.                                     # every user has a train item
+    ut = train @ item_tag / train.sum(-1, keepdims=True)
+    user_tag = (0.01 / T + 0.99 * ut).astype(np.float32)   # eq. 7 smoothing (data_utils.py:425)
+    bucket = np.minimum((np.argsort(np.argsort(-train.sum(0))) * P) // I, P - 1)
+    item_pop = np.eye(P, dtype=np.float32)[bucket]
+    user_pop = (0.01 / P + 0.99 * (train @ item_pop / train.sum(-1, keepdims=True))).astype(np.float32)
+    group = rng.randint(0, 2, U)
+    out = {'logits': logits.numpy(), 'y_true': y_true.numpy(), 'item_tag': item_tag, 'user_tag': user_tag,
+           'item_pop': item_pop, 'user_pop': user_pop, 'user_group': group, 'beta': np.array(0.01)}
+    for aggr in (True, False):
+        ev = FullEvaluator(aggr_by_group=aggr, n_groups=2, user_to_user_group=torch.from_numpy(group))
+        ev = FullEvaluatorCalibrationDecorator(ev, torch.from_numpy(item_tag), torch.from_numpy(user_tag), 'tag', 0.01)
+        ev = FullEvaluatorCalibrationDecorator(ev, torch.from_numpy(item_pop), torch.from_numpy(user_pop), 'pop', 0.01)
+        for lo, hi in ((0, 24), (24, 40)):
+            ev.eval_batch(torch.arange(lo, hi), logits[lo:hi], y_true[lo:hi])
+        res = ev.get_results()
+        tagk = 'aggr' if aggr else 'peruser'
+        out[f'{tagk}/names'] = np.array(sorted(res))
+        if aggr:
+            out[f'{tagk}/values'] = np.array([float(res[k]) for k in sorted(res)])
+        else:
+            for k in sorted(res):
+                out[f'{tagk}/{k}'] = np.asarray(res[k])
+    np.savez_compressed(os.path.join(GOLD, 'calibration_kat.npz'), **out)
+    print('calibration_kat ok', len(out['aggr/names']), 'keys')
+
+
+def gen_baseline_init():
+    """Reference SGDBaseline (algorithms/sgd_alg.py:72-107): initial weights under a fixed torch seed (module
+    construction + general_weight_init order), parameter names / shapes, and scores of a small batch."""
+    from algorithms.sgd_alg import SGDBaseline
+    torch.manual_seed(64)
+    m = SGDBaseline(37, 23)
+    out = {f'init/{n}': p.detach().numpy().copy() for n, p in m.state_dict().items()}
+    rng = np.random.RandomState(3)
+    u = rng.randint(0, 37, 16).astype(np.int64)
+    i = rng.randint(0, 23, (16, 6)).astype(np.int64)
+    with torch.no_grad():
+        out['u_idxs'], out['i_idxs'] = u, i
+        out['scores'] = m(torch.from_numpy(u), torch.from_numpy(i)).numpy()
+    np.savez_compressed(os.path.join(GOLD, 'baseline_init.npz'), **out)
+    print('baseline_init ok', sorted(k for k in out if k.startswith('init/')))
+
+
 def main():
     ref_shim.load()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])      # e.g. `python -m oracle.make_golden calibration baseline`: regenerate just those
+    if only:
+        if 'calibration' in only:
+            gen_calibration()
+        if 'baseline' in only:
+            gen_baseline_init()
+            gen_train('train_baseline_bce', 'bce', d=None, use_user_bias=True, use_item_bias=True, use_global_bias=True,
+                      optimizer='adamw', B=64, N=4, lr=1e-3, wd=1e-4, model_kind='baseline')
+        return
+    gen_calibration()
+    gen_baseline_init()
+    gen_train('train_baseline_bce', 'bce', d=None, use_user_bias=True, use_item_bias=True, use_global_bias=True,
+              optimizer='adamw', B=64, N=4, lr=1e-3, wd=1e-4, model_kind='baseline')
     gen_metrics_kat()
     gen_train('train_bpr', 'bpr', d=18, use_user_bias=False, use_item_bias=True, use_global_bias=False,
               optimizer='adamw', B=96, N=7, lr=3e-4, wd=4e-5)

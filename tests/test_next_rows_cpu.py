@@ -1,0 +1,131 @@
+"""CPU: the SURVEY §8(f) rows that are host logic over the kernels' outputs — calibration metrics / decorator (row 3) and
+the SGDBaseline model shell (row 4) — against fixtures generated from the unmodified reference
+(oracle/make_golden.py: calibration_kat.npz, baseline_init.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from hsk_testutil import load_golden
+
+
+class _StubEvaluator:
+    """Stands in for hassaku_b200.eval.eval.FullEvaluator (whose metric kernels need a GPU): the decorator only needs
+    the group bookkeeping and something to delegate to."""
+    K_VALUES = [5, 10, 50, 100]
+
+    def __init__(self, aggr_by_group, n_groups, user_to_user_group):
+        self.aggr_by_group, self.n_groups, self.user_to_user_group = aggr_by_group, n_groups, user_to_user_group
+        self.calls = 0
+
+    def _reset_internal_dict(self):
+        self.calls = 0
+
+    def get_n_groups(self):
+        return self.n_groups
+
+    def get_user_to_user_group(self):
+        return self.user_to_user_group
+
+    def eval_batch(self, u, logits, y):
+        self.calls += 1
+
+    def eval_batch_topk(self, u, ids, labels):
+        self.calls += 1
+
+    def get_results(self):
+        out = {'inner': float(self.calls)}
+        self._reset_internal_dict()
+        return out
+
+
+def _decorated(g, aggr):
+    from hassaku_b200.eval.eval import FullEvaluatorCalibrationDecorator as Deco
+    ev = _StubEvaluator(aggr, 2, torch.from_numpy(g['user_group']))
+    ev = Deco(ev, torch.from_numpy(g['item_tag']), torch.from_numpy(g['user_tag']), 'tag', float(g['beta']))
+    return Deco(ev, torch.from_numpy(g['item_pop']), torch.from_numpy(g['user_pop']), 'pop', float(g['beta']))
+
+
+@pytest.mark.parametrize('path', ['dense', 'topk'])
+def test_calibration_decorator_aggregated_vs_reference(path):
+    g = load_golden('calibration_kat')
+    ev = _decorated(g, True)
+    logits, y = torch.from_numpy(g['logits']), torch.from_numpy(g['y_true'])
+    for lo, hi in ((0, 24), (24, 40)):
+        u = torch.arange(lo, hi)
+        if path == 'dense':
+            ev.eval_batch(u, logits[lo:hi], y[lo:hi])
+        else:   # what the fused evaluator hands over: ranked top-100 ids
+            ev.eval_batch_topk(u, logits[lo:hi].topk(100).indices.int(), None)
+    res = ev.get_results()
+    assert res.pop('inner') == 2.0                       # both decorators delegated to the wrapped evaluator once per batch
+    want = {k: v for k, v in zip(g['aggr/names'], g['aggr/values']) if 'tag_' in k or 'pop_' in k}
+    assert sorted(res) == sorted(want) and len(want) == 2 * 3 * 4 * 3   # 2 prefixes x 3 distances x 4 k x (ALL + 2 groups)
+    for k, v in want.items():
+        assert np.isclose(res[k], v, rtol=1e-5, atol=1e-7, equal_nan=True), (k, res[k], v)
+    assert ev.get_results() == {'inner': 0.0}            # reset after get_results (eval.py:116)
+
+
+def test_calibration_decorator_per_user_vectors_vs_reference():
+    g = load_golden('calibration_kat')
+    ev = _decorated(g, False)
+    logits, y = torch.from_numpy(g['logits']), torch.from_numpy(g['y_true'])
+    for lo, hi in ((0, 24), (24, 40)):
+        ev.eval_batch(torch.arange(lo, hi), logits[lo:hi], y[lo:hi])
+    res = ev.get_results()
+    n = 0
+    for k in g['peruser/names']:
+        if 'tag_' in k or 'pop_' in k:
+            want = g[f'peruser/{k}']
+            assert res[k].shape == want.shape, k
+            assert np.allclose(res[k], want, rtol=1e-5, atol=1e-7, equal_nan=True), k
+            n += 1
+    assert n == 72
+
+
+def test_calibration_distances_closed_forms():
+    from hassaku_b200.eval.metrics import hellinger_distance, jensen_shannon_distance, kl_divergence
+    p = torch.tensor([[0.5, 0.5, 0.0], [0.2, 0.3, 0.5]])
+    assert torch.allclose(hellinger_distance(p, p), torch.zeros(2))
+    one = torch.tensor([[1.0, 0.0]]); other = torch.tensor([[0.0, 1.0]])
+    assert torch.allclose(hellinger_distance(one, other), torch.ones(1))          # disjoint supports: distance 1
+    q = torch.tensor([[0.25, 0.25, 0.5], [0.2, 0.3, 0.5]])
+    assert abs(float(kl_divergence(q[1:], q[1:]))) < 1e-7
+    a, b = torch.tensor([[0.5, 0.5]]), torch.tensor([[0.25, 0.75]])
+    want = 0.5 * np.log(0.5 / 0.25) + 0.5 * np.log(0.5 / 0.75)
+    assert abs(float(kl_divergence(a, b)) - want) < 1e-6
+    assert torch.allclose(jensen_shannon_distance(a, b), jensen_shannon_distance(b, a))   # symmetric
+    assert torch.isnan(kl_divergence(p[:1], q[:1])).all()                                  # 0 * log 0 -> nan, like the reference
+
+
+def test_calibration_decorator_rejects_bad_beta_and_short_topk():
+    from hassaku_b200.eval.eval import FullEvaluatorCalibrationDecorator as Deco
+    g = load_golden('calibration_kat')
+    with pytest.raises(AssertionError):
+        Deco(_StubEvaluator(True, 0, None), torch.from_numpy(g['item_tag']), torch.from_numpy(g['user_tag']), 'tag', 1.5)
+    ev = Deco(_StubEvaluator(True, 0, None), torch.from_numpy(g['item_tag']), torch.from_numpy(g['user_tag']))
+    with pytest.raises(AssertionError):
+        ev.eval_batch_topk(torch.arange(4), torch.zeros((4, 50), dtype=torch.int32), None)
+
+
+def test_sgd_baseline_shell_matches_reference_init_names_and_shapes():
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import SGDBaseline, SGDMatrixFactorization
+    g = load_golden('baseline_init')
+    torch.manual_seed(64)
+    m = SGDBaseline(37, 23)
+    sd = m.state_dict()
+    assert sorted(sd) == ['global_bias', 'item_bias.weight', 'user_bias.weight']     # base_classes.py:156-165 round trip
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), g['init/' + k]), k                          # same seed -> bit-identical init
+    assert [n for n, _ in m.named_parameters()] == ['global_bias', 'user_bias.weight', 'item_bias.weight']
+    assert isinstance(m, SGDMatrixFactorization) and m.name == 'SGDBaseline' and m.embedding_dim == 1
+    assert float(m.user_embeddings.weight.abs().max()) == 0.0 and float(m.item_embeddings.weight.abs().max()) == 0.0
+    # materialising accessors follow the reference (sgd_alg.py:93-102)
+    u = torch.from_numpy(g['u_idxs']); i = torch.from_numpy(g['i_idxs'])
+    out = m.combine_user_item_representations(m.get_user_representations(u), m.get_item_representations(i))
+    assert np.allclose(out.detach().numpy(), g['scores'], rtol=1e-6, atol=1e-7)
+    with pytest.raises(_C.HskError):
+        m(u, i)                                                                      # no CPU path
+    m2 = SGDBaseline.build_from_conf({}, type('D', (), {'n_users': 37, 'n_items': 23})())
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.arena, m.arena)
