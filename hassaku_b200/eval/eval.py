@@ -323,10 +323,44 @@ class TopKScorer:
         return scores, ids
 
 
+_FACTOR_ATTRS = (('users_factors', 'items_factors'), ('X', 'C'))   # SVDAlgorithm / AlternatingLeastSquare; RBMF
+
+
+def factor_model_of(alg, device='cuda') -> Optional[SGDMatrixFactorization]:
+    """Fitted factor models whose `predict` is the same `[B, d] x [I, d]` dot product as the MF scorer — the reference's
+    SVDAlgorithm, AlternatingLeastSquare (`users_factors`, `items_factors`; algorithms/mf_algs.py:41-49, 117-125) and
+    RBMF (`X`, `C`; mf_algs.py:187-194) — as a frozen SGDMatrixFactorization shell on `device`, so that they are
+    evaluated by the fused top-k kernels instead of the dense `[Be, I, d]` product.  Factors are cast to fp32 (the
+    reference keeps what scipy / numpy produced, usually float64).  None when `alg` is not such a model.  The shell is
+    cached on the algorithm object and rebuilt when the factor arrays are replaced (a new `fit`)."""
+    for ua, ia in _FACTOR_ATTRS:
+        uf, itf = getattr(alg, ua, None), getattr(alg, ia, None)
+        if uf is None or itf is None or isinstance(alg, SGDMatrixFactorization):
+            continue
+        if getattr(uf, 'ndim', 0) != 2 or getattr(itf, 'ndim', 0) != 2 or uf.shape[1] != itf.shape[1]:
+            continue
+        if not 1 <= uf.shape[1] <= 1024:
+            continue
+        cached = alg.__dict__.get('_hsk_factor_model')
+        if cached is not None and cached[0] is uf and cached[1] is itf and str(cached[2].arena.device).startswith(str(device)):
+            return cached[2]
+        shell = SGDMatrixFactorization(uf.shape[0], itf.shape[0], uf.shape[1])
+        with torch.no_grad():
+            shell.user_embeddings.weight.copy_(torch.as_tensor(np.asarray(uf), dtype=torch.float32))
+            shell.item_embeddings.weight.copy_(torch.as_tensor(np.asarray(itf), dtype=torch.float32))
+        shell.to(device)
+        shell.name = f'FactorModel({getattr(alg, "name", type(alg).__name__)})'
+        alg.__dict__['_hsk_factor_model'] = (uf, itf, shell)
+        return shell
+    return None
+
+
 def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evaluator: FullEvaluator, device='cpu',
                                    verbose=False):
     """Evaluation procedure that calls FullEvaluator on the dataset (eval/eval.py:211-258)."""
     dataset = eval_loader.dataset
+    if not isinstance(alg, SGDMatrixFactorization):
+        alg = factor_model_of(alg) or alg      # SVD / ALS / RBMF: same contraction, same kernels
     if isinstance(alg, SGDMatrixFactorization):
         if not alg.arena.is_cuda:  # the reference's run_test evaluates with device='cpu' (experiment_helper.py:116)
             alg.to('cuda')

@@ -13,6 +13,14 @@ Fixtures
                            dataset through the reference FullEvalDataset: metric dict, masked scores, top-100 ids.
   metrics_kat.npz          the 15 known answers of framework_tests/eval/test_metrics.py evaluated by the
                            reference's own metric functions.
+  calibration_kat.npz      reference FullEvaluatorCalibrationDecorator ('tag' + 'pop', nested) over two dense batches:
+                           aggregated dict (2 user groups) and per-user vectors.
+  calibration_matrices.npz reference build_user_and_item_{tag,pop}_matrix on the tiny dataset (CSV layout + random tags).
+  baseline_init.npz        reference SGDBaseline: seeded initial weights, names / shapes, scores of one batch.
+  train_baseline_bce.npz   reference SGDBaseline + bce + AdamW, 3 teacher-forced steps (same layout as train_*.npz).
+
+`python -m oracle.make_golden [calibration] [calibration_matrices] [baseline]` regenerates only the named groups;
+without arguments everything (the run is deterministic: regenerated files are identical to the committed ones).
 """
 import os
 import sys
@@ -230,6 +238,32 @@ def gen_calibration():
     print('calibration_kat ok', len(out['aggr/names']), 'keys')
 
 
+def gen_calibration_matrices():
+    """Reference build_user_and_item_tag_matrix / build_user_and_item_pop_matrix (data/data_utils.py:378-499) on the
+    'tiny' synthetic dataset written in the reference's CSV layout plus a random item-tag table."""
+    import pandas as pd
+    import scipy.sparse as sp
+    if not hasattr(sp.csr_matrix, 'A'):     # scipy >= 1.14 dropped `.A`, which data_utils.py:494-499 uses
+        sp.csr_matrix.A = property(lambda self: self.toarray())
+    from data.data_utils import build_user_and_item_pop_matrix, build_user_and_item_tag_matrix
+    from hassaku_b200.data.synthetic import write_csv_dataset
+    data = tiny_data()
+    T = 9
+    rng = np.random.RandomState(1)
+    pairs = np.argwhere(rng.rand(data.n_items, T) < 0.25)
+    pairs = pairs[pairs[:, 0] >= 4]           # items 0..3 carry no tag
+    with tempfile.TemporaryDirectory() as d:
+        base = write_csv_dataset(data, os.path.join(d, 'processed_dataset'))
+        pd.DataFrame({'tag_idx': np.arange(T)}).to_csv(os.path.join(base, 'tag_idxs.csv'), index=False)
+        pd.DataFrame({'item_idx': pairs[:, 0], 'tag_idx': pairs[:, 1]}).to_csv(os.path.join(base, 'item_tag_idxs.csv'),
+                                                                              index=False)
+        ut, it = build_user_and_item_tag_matrix(d)
+        up, ip = build_user_and_item_pop_matrix(d)
+    np.savez_compressed(os.path.join(GOLD, 'calibration_matrices.npz'), item_tag_pairs=pairs, n_tags=np.array(T),
+                        user_tag=ut.numpy(), item_tag=it.numpy(), user_pop=up.numpy(), item_pop=ip.numpy())
+    print('calibration_matrices ok', tuple(ut.shape), tuple(ip.shape), ip.sum(0).tolist())
+
+
 def gen_baseline_init():
     """Reference SGDBaseline (algorithms/sgd_alg.py:72-107): initial weights under a fixed torch seed (module
     construction + general_weight_init order), parameter names / shapes, and scores of a small batch."""
@@ -255,12 +289,15 @@ def main():
     if only:
         if 'calibration' in only:
             gen_calibration()
+        if 'calibration_matrices' in only:
+            gen_calibration_matrices()
         if 'baseline' in only:
             gen_baseline_init()
             gen_train('train_baseline_bce', 'bce', d=None, use_user_bias=True, use_item_bias=True, use_global_bias=True,
                       optimizer='adamw', B=64, N=4, lr=1e-3, wd=1e-4, model_kind='baseline')
         return
     gen_calibration()
+    gen_calibration_matrices()
     gen_baseline_init()
     gen_train('train_baseline_bce', 'bce', d=None, use_user_bias=True, use_item_bias=True, use_global_bias=True,
               optimizer='adamw', B=64, N=4, lr=1e-3, wd=1e-4, model_kind='baseline')

@@ -150,3 +150,33 @@ def test_shard_local_index_matches_formula():
     _C.shard_local_index(out, 4, 9, out=out)           # in place
     want = (idx % 4) * 9 + torch.div(idx, 4, rounding_mode='floor'); want[0, 0] = -5
     assert torch.equal(out, want)
+
+
+def test_factor_model_evaluation_equals_dense_predict_path():
+    """A fitted SVD-like model goes through the fused top-k kernels and gives the metrics of the reference's dense
+    predict path (eval.py:224-236) on the same factors."""
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.data.synthetic import make_interactions
+    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+    data = make_interactions(300, 200, 6000, seed=0, n_user_groups=2)
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+    rng = np.random.RandomState(1)
+
+    class SVDLike:
+        name = 'SVDAlgorithm'
+        users_factors = rng.randn(300, 12)
+        items_factors = rng.randn(200, 12)
+
+    class L:
+        dataset, batch_size = ds, 128
+
+    alg = SVDLike()
+    got = evaluate_recommender_algorithm(alg, L, FullEvaluator(True, 2, ds.user_to_user_group), 'cuda')
+    scores = torch.from_numpy((alg.users_factors.astype(np.float32) @ alg.items_factors.astype(np.float32).T)).cuda()
+    scores[torch.from_numpy(data.train.toarray().astype(bool)).cuda()] = -torch.inf
+    ev = FullEvaluator(True, 2, ds.user_to_user_group)
+    ev.eval_batch(torch.arange(300, device='cuda'), scores, torch.from_numpy(data.val.toarray()).float().cuda())
+    want = ev.get_results()
+    assert sorted(got) == sorted(want)
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-6, (k, got[k], v)

@@ -129,3 +129,71 @@ def test_sgd_baseline_shell_matches_reference_init_names_and_shapes():
     m2 = SGDBaseline.build_from_conf({}, type('D', (), {'n_users': 37, 'n_items': 23})())
     m2.load_state_dict(sd)
     assert torch.equal(m2.arena, m.arena)
+
+
+def test_factor_model_detection_builds_a_frozen_mf_shell():
+    """SVD / ALS (`users_factors`, `items_factors`) and RBMF (`X`, `C`) are scored by the MF kernels."""
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.eval.eval import factor_model_of
+    rng = np.random.RandomState(0)
+
+    class SVDLike:
+        name = 'SVDAlgorithm'
+        users_factors = rng.randn(11, 6)            # float64, as scipy's svds returns
+        items_factors = rng.randn(7, 6)
+
+    class RBMFLike:
+        X = rng.randn(5, 3).astype(np.float32)
+        C = rng.randn(9, 3).astype(np.float32)
+
+    a = SVDLike()
+    m = factor_model_of(a, device='cpu')
+    assert isinstance(m, SGDMatrixFactorization) and (m.n_users, m.n_items, m.embedding_dim) == (11, 7, 6)
+    assert not (m.use_user_bias or m.use_item_bias or m.use_global_bias) and 'SVDAlgorithm' in m.name
+    assert np.allclose(m.user_embeddings.weight.detach().numpy(), a.users_factors.astype(np.float32))
+    assert np.allclose(m.item_embeddings.weight.detach().numpy(), a.items_factors.astype(np.float32))
+    assert factor_model_of(a, device='cpu') is m                       # cached while the factor arrays are the same objects
+    a.users_factors = a.users_factors.copy()                           # a new fit -> rebuilt
+    assert factor_model_of(a, device='cpu') is not m
+    r = factor_model_of(RBMFLike(), device='cpu')
+    assert (r.n_users, r.n_items, r.embedding_dim) == (5, 9, 3)
+    assert factor_model_of(object()) is None
+
+    class Unfitted:
+        users_factors = None
+        items_factors = None
+
+    assert factor_model_of(Unfitted()) is None
+
+    class Mismatch:
+        users_factors = np.zeros((4, 3))
+        items_factors = np.zeros((4, 2))
+
+    assert factor_model_of(Mismatch()) is None
+
+
+def test_calibration_matrices_vs_reference(tmp_path):
+    """build_user_and_item_{tag,pop}_matrix on the tiny dataset: in-memory and CSV entry points against the reference's
+    outputs (oracle/make_golden.py gen_calibration_matrices)."""
+    import pandas as pd
+    from hassaku_b200.data import calibration as C
+    from hassaku_b200.data.synthetic import make_interactions, write_csv_dataset
+    g = load_golden('calibration_matrices')
+    data = make_interactions(300, 200, 6000, seed=0, n_user_groups=2)
+    pairs, T = g['item_tag_pairs'], int(g['n_tags'])
+    ut, it = C.tag_matrices_from_csr(data.train.tocsr(), pairs[:, 0], pairs[:, 1], T)
+    up, ip = C.pop_matrices_from_csr(data.train.tocsr())
+    assert np.array_equal(it.numpy(), g['item_tag']) and np.array_equal(ip.numpy(), g['item_pop'])
+    assert np.allclose(ut.numpy(), g['user_tag'], rtol=1e-6, atol=1e-8, equal_nan=True)
+    assert np.allclose(up.numpy(), g['user_pop'], rtol=1e-6, atol=1e-8, equal_nan=True)
+    assert float(it[:4].abs().max()) == 0.0                                   # untagged items: zero rows
+    assert ut.dtype == torch.float32 and ip.shape == (200, 3) and float(ip.sum()) == 200.0
+    base = write_csv_dataset(data, str(tmp_path / 'processed_dataset'))
+    pd.DataFrame({'tag_idx': np.arange(T)}).to_csv(base + '/tag_idxs.csv', index=False)
+    pd.DataFrame({'item_idx': pairs[:, 0], 'tag_idx': pairs[:, 1]}).to_csv(base + '/item_tag_idxs.csv', index=False)
+    ut2, it2 = C.build_user_and_item_tag_matrix(str(tmp_path))
+    up2, ip2 = C.build_user_and_item_pop_matrix(str(tmp_path))
+    assert torch.equal(it2, it) and torch.equal(ip2, ip)
+    assert torch.allclose(ut2, ut, equal_nan=True) and torch.allclose(up2, up, equal_nan=True)
+    with pytest.raises(AssertionError):
+        C.pop_matrices_from_csr(data.train.tocsr(), alpha_smoothening=2.0)
