@@ -355,8 +355,9 @@ class ShardedMF:
         """Every rank evaluates ITS users (u % G == rank) against ALL items; returns the global metric dict on every
         rank.  `labels_csr` / `exclude_csr`: full scipy CSR matrices (global ids)."""
         from hassaku_b200.eval.eval import DeviceCSR
-        if precision != 'fp32':
-            raise NotImplementedError('sharded evaluation currently scores in fp32-exact mode')
+        if precision not in _C.PRECISIONS:
+            raise ValueError(f'eval precision {precision!r} not in {sorted(_C.PRECISIONS)}')
+        prec = _C.PRECISIONS[precision]          # 0: fp32-exact SIMT kernel; tf32 / bf16: tcgen05 kernel on the local shard
         G, r, lay, dev = self.spec.world, self.spec.rank, self.layout, self.device
         k = max(evaluator.K_VALUES)
         labels = labels_csr if isinstance(labels_csr, DeviceCSR) else self._csr_cache(labels_csr)
@@ -367,7 +368,11 @@ class ShardedMF:
         U2d = self.arena[lay.off_U:lay.off_U + lay.n_users * ld].view(lay.n_users, ld)
         Uw, Vw, Ub, Ib, Gb = lay.views(self.arena)
         Be = G * bs
-        scratch = torch.empty(_C.eval_topk_scratch_bytes(Be, lay.n_items, k), dtype=torch.uint8, device=dev)
+        if prec == 0:
+            scratch = torch.empty(_C.eval_topk_scratch_bytes(Be, lay.n_items, k), dtype=torch.uint8, device=dev)
+        else:
+            scratch = torch.empty(_C.eval_topk_tc_scratch_bytes(Be, lay.n_items, k), dtype=torch.uint8, device=dev)
+            Vq = _C.pack_rows(Vw.detach(), lay.d, prec)         # the local item shard, packed once per sweep
         top_s = torch.empty((Be, k), dtype=torch.float32, device=dev)
         top_i = torch.empty((Be, k), dtype=torch.int32, device=dev)
         u_rows = torch.arange(Be, dtype=torch.int64, device=dev)
@@ -389,9 +394,15 @@ class ShardedMF:
             dist.all_gather_into_tensor(all_ub, ubias, group=self.group)
             valid = all_gids >= 0
             safe_gids = torch.where(valid, all_gids, torch.zeros_like(all_gids))
-            t = _C.make_tables(all_rows[:, :lay.d], Vw, all_ub if Ub is not None else None, Ib, Gb, lay.d)
-            _C.eval_topk(t, safe_gids, k, top_s, top_i, scratch, exclude.indptr, exclude.indices, id_offset=r, id_stride=G,
-                         status=self.status, u_rows=u_rows, n_users_global=self.spec.n_users)
+            if prec == 0:
+                t = _C.make_tables(all_rows[:, :lay.d], Vw, all_ub if Ub is not None else None, Ib, Gb, lay.d)
+                _C.eval_topk(t, safe_gids, k, top_s, top_i, scratch, exclude.indptr, exclude.indices, id_offset=r,
+                             id_stride=G, status=self.status, u_rows=u_rows, n_users_global=self.spec.n_users)
+            else:
+                Uq = _C.pack_rows(all_rows[:, :lay.d], lay.d, prec)
+                _C.eval_topk_tc(Uq, Vq, prec, safe_gids, self.spec.n_users, k, top_s, top_i, scratch,
+                                Ub=all_ub if Ub is not None else None, Ib=Ib, Gb=Gb, excl_indptr=exclude.indptr,
+                                excl_indices=exclude.indices, id_offset=r, id_stride=G, status=self.status, u_rows=u_rows)
             # exchange: rank q receives the G partial lists of its bs users
             recv_s = torch.empty((G, bs, k), dtype=torch.float32, device=dev)
             recv_i = torch.empty((G, bs, k), dtype=torch.int32, device=dev)
