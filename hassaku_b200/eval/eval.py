@@ -18,8 +18,8 @@ from tqdm import tqdm
 from hassaku_b200 import _C
 from hassaku_b200.algorithms.base_classes import RecommenderAlgorithm
 from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
-from hassaku_b200.eval.metrics import (dense_topk, discount_table, hellinger_distance, jensen_shannon_distance,
-                                       kl_divergence)
+from hassaku_b200.eval.metrics import (dense_topk, discount_table, hellinger_distance, hit_from_precision,
+                                       jensen_shannon_distance, kl_divergence)
 
 METRIC_ORDER = ('precision@{}', 'recall@{}', 'ndcg@{}')  # eval.py:78-80; column order of hsk_rank_metrics
 
@@ -51,10 +51,14 @@ class FullEvaluator:
     group (-1) and each user group; `get_results()` returns the means and resets.  Accumulators live on the device."""
     K_VALUES = [5, 10, 50, 100]  # eval.py:20
 
-    def __init__(self, aggr_by_group: bool = True, n_groups: int = 0, user_to_user_group: dict = None):
+    def __init__(self, aggr_by_group: bool = True, n_groups: int = 0, user_to_user_group: dict = None, *,
+                 hit: bool = False):
+        """`hit=True` (not in the reference; keyword-only, default off so the returned dict keeps the reference's keys)
+        adds `hit@k` — the share of users with at least one relevant item in the top k — next to the three metrics."""
         self.aggr_by_group = aggr_by_group
         self.n_groups = n_groups
         self.user_to_user_group = user_to_user_group
+        self.hit = hit
         self._reset_internal_dict()
 
     def _reset_internal_dict(self):
@@ -62,6 +66,7 @@ class FullEvaluator:
         self._counts = None
         self._per_user = []   # (per_user [B, n_ks, 3], group [B]) when aggr_by_group is False
         self._group_dev = None
+        self._hit_sums = None
 
     def get_n_groups(self):
         return self.n_groups
@@ -78,20 +83,26 @@ class FullEvaluator:
             n_ks = len(self.K_VALUES)
             self._sums = torch.zeros((1 + self.n_groups, n_ks, 3), dtype=torch.float64, device=device)
             self._counts = torch.zeros(1 + self.n_groups, dtype=torch.int64, device=device)
+            if getattr(self, 'hit', False) and self.aggr_by_group:
+                self._hit_sums = torch.zeros((1 + self.n_groups, n_ks), dtype=torch.float64, device=device)
             if self.n_groups > 0:
                 g = self.user_to_user_group
                 g = g if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g))
                 self._group_dev = g.to(device=device, dtype=torch.int32).contiguous()
 
     def _per_user_buf(self, B, device):
-        if self.aggr_by_group:
+        if self.aggr_by_group and not getattr(self, 'hit', False):
             return None
         return torch.empty((B, len(self.K_VALUES), 3), dtype=torch.float32, device=device)
 
     def _keep(self, u_idxs, per_user):
-        if per_user is not None:
-            grp = self._group_dev[u_idxs] if self.n_groups > 0 else None
+        if per_user is None:
+            return
+        grp = self._group_dev[u_idxs] if self.n_groups > 0 else None
+        if not self.aggr_by_group:
             self._per_user.append((per_user, grp))
+        elif getattr(self, 'hit', False):
+            self._hit_sums = accumulate_hits(self._hit_sums, per_user, grp, self.n_groups)
 
     # ---- reference API: dense logits / labels (eval.py:54-99) ----
     def eval_batch(self, u_idxs: torch.Tensor, logits: torch.Tensor, y_true: torch.Tensor):
@@ -135,6 +146,9 @@ class FullEvaluator:
                     for c, name in enumerate(METRIC_ORDER):
                         key = name.format(k) if g == -1 else f'group_{g}_' + name.format(k)
                         metrics_dict[key] = float(sums[g + 1, t, c]) / int(counts[g + 1])
+                    if self._hit_sums is not None:
+                        key = f'hit@{k}' if g == -1 else f'group_{g}_hit@{k}'
+                        metrics_dict[key] = float(self._hit_sums[g + 1, t]) / int(counts[g + 1])
         else:
             per_user = torch.cat([p for p, _ in self._per_user]).cpu().numpy()
             grp = torch.cat([g for _, g in self._per_user]).cpu().numpy() if self.n_groups > 0 else None
@@ -144,8 +158,24 @@ class FullEvaluator:
                     for c, name in enumerate(METRIC_ORDER):
                         key = name.format(k) if g == -1 else f'group_{g}_' + name.format(k)
                         metrics_dict[key] = per_user[sel, t, c]
+                    if getattr(self, 'hit', False):
+                        key = f'hit@{k}' if g == -1 else f'group_{g}_hit@{k}'
+                        metrics_dict[key] = (per_user[sel, t, 0] > 0).astype(per_user.dtype)
         self._reset_internal_dict()
         return metrics_dict
+
+
+def accumulate_hits(hit_sums: Optional[torch.Tensor], per_user: torch.Tensor, grp: Optional[torch.Tensor],
+                    n_groups: int) -> torch.Tensor:
+    """hit_sums [1 + n_groups, n_ks] (fp64, created on first use) += per-user hit indicators of one batch; row 0 is the
+    'ALL' group, row 1 + g user group g."""
+    hits = hit_from_precision(per_user).double()
+    if hit_sums is None:
+        hit_sums = torch.zeros((1 + n_groups, hits.shape[1]), dtype=torch.float64, device=per_user.device)
+    hit_sums[0] += hits.sum(0)
+    if n_groups > 0:
+        hit_sums[1:].index_add_(0, grp.long(), hits)
+    return hit_sums
 
 
 class FullEvaluatorCalibrationDecorator(FullEvaluator):

@@ -72,6 +72,19 @@ def ndcg_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, agg
     return _one_metric(2, logits, y_true, k, aggr_sum, idx_topk)
 
 
+def hit_at_k_batch(logits: torch.Tensor, y_true: torch.Tensor, k: int = 10, aggr_sum: bool = True,
+                   idx_topk: torch.Tensor = None):
+    """Hit@k: 1 if at least one relevant item is among the top k, else 0 (BASELINE north_star lists it; the reference has
+    no such function — same signature as its three metrics).  Derived from the precision column: hits > 0."""
+    res = (_one_metric(0, logits, y_true, k, False, idx_topk) > 0).float()
+    return res.sum() if aggr_sum else res
+
+
+def hit_from_precision(per_user: torch.Tensor) -> torch.Tensor:
+    """per_user [B, n_ks, 3] (precision, recall, ndcg) -> hit [B, n_ks] in {0, 1}: precision@k > 0."""
+    return (per_user[..., 0] > 0).to(per_user.dtype)
+
+
 # ---- calibration distances between per-user distributions over tags / popularity buckets (eval/metrics.py:108-152) ----
 # Plain torch on whatever device the inputs live on: consumers of the top-k ids, [B, n_tags] work per batch.
 def hellinger_distance(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:

@@ -417,6 +417,8 @@ class ShardedMF:
         evaluator._prepare(dev)
         dist.all_reduce(evaluator._sums, group=self.group)
         dist.all_reduce(evaluator._counts, group=self.group)
+        if getattr(evaluator, '_hit_sums', None) is not None:
+            dist.all_reduce(evaluator._hit_sums, group=self.group)
         return evaluator.get_results()
 
 

@@ -180,3 +180,30 @@ def test_factor_model_evaluation_equals_dense_predict_path():
     assert sorted(got) == sorted(want)
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-6, (k, got[k], v)
+
+
+def test_hit_at_k_through_both_evaluator_paths():
+    from hassaku_b200.eval.eval import FullEvaluator
+    from hassaku_b200.eval.metrics import hit_at_k_batch
+    g = load_golden('calibration_kat')
+    logits, y = torch.from_numpy(g['logits']).cuda(), torch.from_numpy(g['y_true']).cuda()
+    grp = torch.from_numpy(g['user_group'])
+    want = {}
+    top = logits.topk(100).indices
+    for k in (5, 10, 50, 100):
+        hit = (torch.gather(y, 1, top[:, :k]).sum(1) > 0).float().cpu()
+        want[f'hit@{k}'] = float(hit.mean())
+        for gi in range(2):
+            want[f'group_{gi}_hit@{k}'] = float(hit[grp == gi].mean())
+        assert abs(float(hit_at_k_batch(logits, y, k)) - float(hit.sum())) < 1e-6
+    ev = FullEvaluator(True, 2, grp, hit=True)
+    for lo, hi in ((0, 24), (24, 40)):
+        ev.eval_batch(torch.arange(lo, hi, device='cuda'), logits[lo:hi], y[lo:hi])
+    res = ev.get_results()
+    assert len(res) == 48                      # (3 + 1) metrics x 4 k x (ALL + 2 groups)
+    for k_, v in want.items():
+        assert abs(res[k_] - v) < 1e-9, (k_, res[k_], v)
+    ref = dict(zip(g['aggr/names'], g['aggr/values']))
+    for k_, v in res.items():
+        if 'hit@' not in k_:
+            assert abs(v - ref[k_]) < 1e-6, k_   # the reference's own metrics are unchanged by hit=True

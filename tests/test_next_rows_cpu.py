@@ -197,3 +197,19 @@ def test_calibration_matrices_vs_reference(tmp_path):
     assert torch.allclose(ut2, ut, equal_nan=True) and torch.allclose(up2, up, equal_nan=True)
     with pytest.raises(AssertionError):
         C.pop_matrices_from_csr(data.train.tocsr(), alpha_smoothening=2.0)
+
+
+def test_hit_accumulation_and_keys():
+    """Hit@k (north_star; not in the reference): derived from the precision column, per group, opt-in."""
+    from hassaku_b200.eval.eval import FullEvaluator, accumulate_hits
+    from hassaku_b200.eval.metrics import hit_from_precision
+    pu = torch.tensor([[[0.2, 0, 0], [0, 0, 0]], [[0, 0, 0], [0, 0, 0]], [[0.1, 0, 0], [0.5, 0, 0]]])
+    assert hit_from_precision(pu).tolist() == [[1, 0], [0, 0], [1, 1]]
+    h = accumulate_hits(None, pu, torch.tensor([0, 1, 1]), 2)
+    assert h.tolist() == [[2, 1], [1, 0], [1, 1]]
+    h = accumulate_hits(h, pu, torch.tensor([1, 1, 0]), 2)
+    assert h.tolist() == [[4, 2], [2, 1], [2, 1]]
+    assert accumulate_hits(None, pu, None, 0).tolist() == [[2, 1]]
+    assert FullEvaluator(True, 0, None).hit is False            # default keeps the reference's 12 (1 + n_groups) keys
+    ev = FullEvaluator(True, 2, torch.tensor([0, 1, 1]), hit=True)
+    assert ev._per_user_buf(3, 'cpu') is not None and FullEvaluator(True, 0, None)._per_user_buf(3, 'cpu') is None
