@@ -356,13 +356,59 @@ class TopKScorer:
 _FACTOR_ATTRS = (('users_factors', 'items_factors'), ('X', 'C'))   # SVDAlgorithm / AlternatingLeastSquare; RBMF
 
 
+def _cat_last(*xs):
+    return torch.cat(xs, dim=-1)
+
+
+# SGD models of the reference whose `combine_user_item_representations` is a dot product of per-user and per-item
+# vectors (algorithms/sgd_alg.py:262-267 ACF, :353-356 UProtoMF, :450-453 IProtoMF, :535-543 UIProtoMF): the two
+# representation matrices, computed once per evaluation by the model's own methods, are the factors of a frozen MF.
+# UIProtoMF's sum of two dot products is one dot product of the concatenations.
+_DOT_PRODUCT_REPRESENTATIONS = {
+    'ACF': lambda m, u, i: (m.get_user_representations(u), m.get_item_representations(i)[0]),
+    'UProtoMF': lambda m, u, i: (m.get_user_representations(u), m.get_item_representations(i)),
+    'IProtoMF': lambda m, u, i: (m.get_user_representations(u), m.get_item_representations(i)),
+    'UIProtoMF': lambda m, u, i: (_cat_last(*m.get_user_representations(u)),
+                                  _cat_last(*reversed(m.get_item_representations(i)))),
+}
+
+
+def _representation_factors(alg):
+    """(user matrix [U, p], item matrix [I, p]) of a dot-product SGD model, or None."""
+    fn = _DOT_PRODUCT_REPRESENTATIONS.get(type(alg).__name__)
+    if fn is None or not isinstance(alg, torch.nn.Module) or isinstance(alg, SGDMatrixFactorization):
+        return None
+    try:
+        dev = next(alg.parameters()).device
+    except StopIteration:
+        return None
+    was_training = alg.training
+    alg.eval()
+    with torch.no_grad():
+        uf, itf = fn(alg, torch.arange(alg.n_users, device=dev), torch.arange(alg.n_items, device=dev))
+    alg.train(was_training)
+    return uf.detach().float(), itf.detach().float()
+
+
 def factor_model_of(alg, device='cuda') -> Optional[SGDMatrixFactorization]:
     """Fitted factor models whose `predict` is the same `[B, d] x [I, d]` dot product as the MF scorer — the reference's
     SVDAlgorithm, AlternatingLeastSquare (`users_factors`, `items_factors`; algorithms/mf_algs.py:41-49, 117-125) and
     RBMF (`X`, `C`; mf_algs.py:187-194) — as a frozen SGDMatrixFactorization shell on `device`, so that they are
-    evaluated by the fused top-k kernels instead of the dense `[Be, I, d]` product.  Factors are cast to fp32 (the
+    evaluated by the fused top-k kernels instead of the dense `[Be, I, d]` product.  The reference's ACF / UProtoMF /
+    IProtoMF / UIProtoMF torch models are handled the same way through their representation matrices (see
+    `_DOT_PRODUCT_REPRESENTATIONS`; note that their regularisation side effects only happen in `forward`, which is not
+    called).  Factors are cast to fp32 (the
     reference keeps what scipy / numpy produced, usually float64).  None when `alg` is not such a model.  The shell is
     cached on the algorithm object and rebuilt when the factor arrays are replaced (a new `fit`)."""
+    rep = _representation_factors(alg)
+    if rep is not None and 1 <= rep[0].shape[1] <= 1024:      # trainable torch model: weights change, never cached
+        shell = SGDMatrixFactorization(rep[0].shape[0], rep[1].shape[0], rep[0].shape[1])
+        with torch.no_grad():
+            shell.user_embeddings.weight.copy_(rep[0])
+            shell.item_embeddings.weight.copy_(rep[1])
+        shell.to(device)
+        shell.name = f'FactorModel({getattr(alg, "name", type(alg).__name__)})'
+        return shell
     for ua, ia in _FACTOR_ATTRS:
         uf, itf = getattr(alg, ua, None), getattr(alg, ia, None)
         if uf is None or itf is None or isinstance(alg, SGDMatrixFactorization):

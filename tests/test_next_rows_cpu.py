@@ -213,3 +213,32 @@ def test_hit_accumulation_and_keys():
     assert FullEvaluator(True, 0, None).hit is False            # default keeps the reference's 12 (1 + n_groups) keys
     ev = FullEvaluator(True, 2, torch.tensor([0, 1, 1]), hit=True)
     assert ev._per_user_buf(3, 'cpu') is not None and FullEvaluator(True, 0, None)._per_user_buf(3, 'cpu') is None
+
+
+@pytest.mark.parametrize('name', ['ACF', 'UProtoMF', 'IProtoMF', 'UIProtoMF'])
+def test_dot_product_sgd_models_reduce_to_mf_factors(name):
+    """The reference's prototype / anchor models score by a dot product of representations (sgd_alg.py:262-267, 353-356,
+    450-453, 535-543): the frozen MF shell built from the representation matrices reproduces `predict` exactly."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference checkout not mounted')
+    ref_shim.load()
+    import algorithms.sgd_alg as R
+    from hassaku_b200.eval.eval import factor_model_of
+    torch.manual_seed(0)
+    U, I = 23, 31
+    model = {'ACF': lambda: R.ACF(U, I, embedding_dim=12, n_anchors=5),
+             'UProtoMF': lambda: R.UProtoMF(U, I, embedding_dim=12, n_prototypes=7),
+             'IProtoMF': lambda: R.IProtoMF(U, I, embedding_dim=12, n_prototypes=7),
+             'UIProtoMF': lambda: R.UIProtoMF(U, I, embedding_dim=12, u_n_prototypes=7, i_n_prototypes=5)}[name]()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn_like(p))
+    shell = factor_model_of(model, device='cpu')
+    assert shell is not None and (shell.n_users, shell.n_items) == (U, I)
+    assert model.training                                             # mode restored (the reference's predict() leaves eval())
+    u = torch.arange(U)
+    i = torch.arange(I).repeat(U, 1)
+    want = model.predict(u, i)                                        # base_classes.py:150-154, the evaluator's call
+    got = shell.user_embeddings.weight.detach() @ shell.item_embeddings.weight.detach().T
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), float((got - want).abs().max())
