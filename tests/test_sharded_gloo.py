@@ -139,6 +139,15 @@ def test_sharded_dense_exchange_world2_matches_oracle(tmp_path):
     assert (tmp_path / 'ok').exists()
 
 
+@pytest.mark.parametrize('exchange,flags', [('dense', (True, True, True)), ('dense', (False, False, False)),
+                                            ('sparse', (False, True, False))])
+def test_sharded_step_world3_ragged_shards_matches_oracle(exchange, flags, tmp_path):
+    """41 items / 53 users over 3 ranks: unequal shard sizes (14 / 14 / 13 items), bias block of the dense exchange
+    rounded up to whole rows (cap 14, ld 8 -> 2 extra rows), and the dense exchange without any bias table."""
+    mp.spawn(_worker, args=(3, _free_port(), 'bce', flags, str(tmp_path), exchange), nprocs=3, join=True)
+    assert (tmp_path / 'ok').exists()
+
+
 def test_partition_and_shard_spec():
     from hassaku_b200.sharded import ShardSpec, partition_batch_by_user_owner
     s = ShardSpec(4, 1, 10, 7)
