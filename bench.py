@@ -196,6 +196,26 @@ def workload_config(wname, wl, U, I):
             'l2': 'flushed between timed steps (tables + optimizer state fit L2); value_l2_warm = back to back'}
 
 
+def cpu_eval_baseline(wl, data, n_users=512, eval_batch_size=256):
+    """The reference's full-rank evaluation (eval/eval.py:237-253: [Be, I, d] broadcast product, dense mask, torch.topk,
+    12 metrics per batch; eval batch 256 as in its README) on a bounded sample of users, host cores only."""
+    import torch
+    from oracle import mf_oracle as O
+    name, d, B, N, loss, lr, wd = wl
+    torch.manual_seed(64)
+    model = O.OracleMF(data.n_users, data.n_items, d, use_item_bias=True)
+    users = np.arange(min(n_users, data.n_users))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        res = O.evaluate(model, data.val.tocsr(), data.train.tocsr(), eval_batch_size=eval_batch_size, users=users)
+    dt = time.perf_counter() - t0
+    cores = torch.get_num_threads()
+    return {'value': len(users) / dt, 'unit': 'users/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{len(users)} of {data.n_users} users against all {data.n_items} items, eval batch {eval_batch_size}, '
+                      f'oracle port of eval/eval.py:237-253 (torch CPU, {cores} threads), {dt:.1f} s',
+            'ndcg@10_of_sample': float(res['ndcg@10'])}
+
+
 def cpu_baseline(wl, data, us, its, budget_s=20.0):
     import torch
     from oracle import mf_oracle as O
@@ -683,6 +703,10 @@ def run_ours(args, wl):
             line['cpu_baseline'] = cpu_baseline(wl, data, us, its)
         except Exception as ex:  # never lose the GPU numbers to a baseline problem
             line['cpu_baseline'] = {'error': repr(ex)}
+        try:
+            line['eval']['cpu_baseline'] = cpu_eval_baseline(wl, data)
+        except Exception as ex:
+            line['eval']['cpu_baseline'] = {'error': repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
