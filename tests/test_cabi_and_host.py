@@ -236,3 +236,22 @@ def test_install_rebinds_reference_symbols_and_uninstall_restores():
     m2 = AlgorithmsEnum.mf.value.build_from_conf(
         {'embedding_dim': 8, 'use_user_bias': False, 'use_item_bias': True, 'use_global_bias': False}, DS())
     assert type(m2) is r_alg.SGDMatrixFactorization
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/hassaku_b200.h compiles as C99 (-pedantic) and as C++11, and a C program
+    links against the library and calls its CUDA-free entry points (examples/c_abi_link_check.c)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    from hsk_testutil import ROOT
+    inc, libdir = os.path.join(ROOT, 'include'), os.path.join(ROOT, 'hassaku_b200', 'lib')
+    src = os.path.join(ROOT, 'examples', 'c_abi_link_check.c')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, '-fsyntax-only', src], check=True)
+    subprocess.run(['g++', '-std=c++11', '-Wall', '-Wextra', '-Werror', '-I', inc, '-fsyntax-only', '-x', 'c++', src], check=True)
+    exe = str(tmp_path / 'c_abi_check')
+    subprocess.run(['gcc', '-std=c99', '-I', inc, src, '-L', libdir, '-lhassaku_b200', f'-Wl,-rpath,{libdir}', '-o', exe],
+                   check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert 'hsk_version' in out and 'tables are null' in out
