@@ -496,6 +496,7 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
     // register-gather kernel of this file (kept for A/B measurements and as the sampled-softmax path)
     const char* variant = getenv("HSK_TRAIN_FUSED");
     const bool use_tma = !(variant && strcmp(variant, "regs") == 0);
+    const bool use_tma2 = variant && strcmp(variant, "tma2") == 0;
     const char* nored = getenv("HSK_DEBUG_NORED");
     a.debug_flags = (nored && nored[0] == '1') ? 1 : 0;
     const bool use_q = !variant || strcmp(variant, "q") == 0;   // default; "regs" / "tma" force the warp-per-row kernels
@@ -516,6 +517,7 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
             cudaError_t e = cudaMemsetAsync(dscores_out, 0, sizeof(float) * (size_t)B * N1, s);
             if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_mf_train_fused: memset: %s", cudaGetErrorString(e));
         }
+        if (use_tma2) return launch_train_fused_tma2(a, loss_kind, s);
         if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BPR><<<grid, threads, 0, s>>>(a)));
     } else if (loss_kind == HSK_LOSS_BCE) {
@@ -523,6 +525,7 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
         a.j_per_cta = pick_j_per_cta(B, N1, true);
         if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 + a.j_per_cta - 1) / a.j_per_cta);
+        if (use_tma2) return launch_train_fused_tma2(a, loss_kind, s);
         if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BCE><<<grid, threads, 0, s>>>(a)));
     } else {

@@ -36,6 +36,8 @@ struct TrainArgs {
 
 // hsk_train_tma.cu: the bulk-copy (TMA) pipelined fused step for bpr / bce; returns HSK_OK or an error code
 int launch_train_fused_tma(const TrainArgs& a, int loss_kind, cudaStream_t s);
+// hsk_train_tma2.cu: the same kernel with a leaner inner loop; opt-in (HSK_TRAIN_FUSED=tma2) until measured on a B200
+int launch_train_fused_tma2(const TrainArgs& a, int loss_kind, cudaStream_t s);
 // hsk_train_q.cu: quarter-warp-per-sample fused step for rows of at most 128 floats; returns 1 (no launch) when the
 // shape is outside its range and the caller should use the warp-per-row kernels
 int launch_train_fused_q(const TrainArgs& a, int loss_kind, cudaStream_t s);

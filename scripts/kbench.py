@@ -147,7 +147,7 @@ if __name__ == '__main__':
     ap.add_argument('--neg', type=int, default=50)
     ap.add_argument('--loss', default='bpr')
     ap.add_argument('--workload', default='cfg2')
-    ap.add_argument('--variants', default='regs,tma,q')
+    ap.add_argument('--variants', default='regs,tma,tma2,q')
     ap.add_argument('--users', type=int, default=6040)
     ap.add_argument('--items', type=int, default=3706)
     ap.add_argument('--dim', type=int, default=402)

@@ -207,3 +207,50 @@ def test_hit_at_k_through_both_evaluator_paths():
     for k_, v in res.items():
         if 'hit@' not in k_:
             assert abs(v - ref[k_]) < 1e-6, k_   # the reference's own metrics are unchanged by hit=True
+
+
+@pytest.mark.parametrize('U,I,d,B,N,kind,biases', [
+    (6040, 3706, 402, 512, 50, 'bpr', (False, True, False)),     # cfg2 shape: NV 4 with the scalar tail round
+    (6040, 3706, 402, 128, 50, 'bpr', (False, True, False)),     # small batch: item slots split over gridDim.y
+    (1000, 500, 256, 64, 9, 'bce', (True, True, True)),
+    (300, 200, 7, 33, 3, 'bpr', (True, False, True)),
+    (300, 200, 1024, 17, 5, 'bce', (False, False, False)),
+    (5000, 3000, 128, 256, 50, 'bpr', (False, True, False)),
+])
+def test_lean_loop_ring_kernel_equals_the_shipping_ring_kernel(U, I, d, B, N, kind, biases, monkeypatch):
+    """HSK_TRAIN_FUSED=tma2 (hsk_train_tma2.cu, opt-in) against HSK_TRAIN_FUSED=tma on the same inputs: scores, dL/ds,
+    loss and every gradient table."""
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    lay = ArenaLayout(U, I, d, *biases)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    arena = torch.zeros(lay.n_total, device='cuda')
+    for v, scale in zip(lay.views(arena), (d ** -0.5, d ** -0.5, 0.1, 0.1, 0.1)):
+        if v is not None:
+            v.copy_(torch.randn(v.shape, device='cuda', generator=gen) * scale)
+    u = torch.randint(0, U, (B,), device='cuda', generator=gen)
+    i = torch.randint(0, I, (B, N + 1), device='cuda', generator=gen)
+    i[:, 1] = i[:, 2]
+    u[:4] = u[0]
+    out = {}
+    for variant in ('tma', 'tma2'):
+        monkeypatch.setenv('HSK_TRAIN_FUSED', variant)
+        g = torch.zeros_like(arena); loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+        sc = torch.empty((B, N + 1), device='cuda'); ds = torch.empty((B, N + 1), device='cuda')
+        st = torch.zeros(1, dtype=torch.int32, device='cuda')
+        _C.mf_train_fused(lay.tables(arena), lay.tables(g), u, i, _C.LOSS_KINDS[kind], 0.0, loss, scores_out=sc,
+                          dscores_out=ds, status=st)
+        assert int(st.item()) == 0
+        out[variant] = (sc, ds, loss.item(), g)
+    a, b = out['tma'], out['tma2']
+    assert torch.equal(a[0], b[0])                                               # same dot order -> same scores
+    assert rel_err(b[1].cpu().numpy(), a[1].cpu().numpy()) < 1e-6                # rcp.approx vs rcp.rn: 1 ulp
+    assert abs(a[2] - b[2]) <= 1e-6 * abs(a[2])
+    assert rel_err(b[3].cpu().numpy(), a[3].cpu().numpy()) < 1e-5
+    # an out-of-range item index is reported, not dereferenced
+    i_bad = i.clone(); i_bad[3, 2] = I + 5
+    monkeypatch.setenv('HSK_TRAIN_FUSED', 'tma2')
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    _C.mf_train_fused(lay.tables(arena), lay.tables(torch.zeros_like(arena)), u, i_bad, _C.LOSS_KINDS[kind], 0.0,
+                      torch.zeros(1, dtype=torch.float64, device='cuda'), status=st)
+    assert int(st.item()) & _C.STATUS_BAD_INDEX
