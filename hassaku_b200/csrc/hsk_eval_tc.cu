@@ -20,6 +20,23 @@
 
 #include "hsk_topk.cuh"
 
+// This file is compiled twice: as itself (the shipping kernel + every host entry point) and through
+// hsk_eval_tc_lean.cu with HSK_TC_LEAN = 1 (only the kernel, under another name, plus its launcher).  LEAN is an
+// opt-in experiment (HSK_EVAL_TC=lean) that has not been measured yet: the in-kernel phase counters are compiled out
+// and the two 32-column chunks of a tile are processed by two inlined copies of the chunk body instead of one copy
+// plus a 32-register move of the second chunk into the first one's registers.  With HSK_TC_LEAN = 0 the preprocessed
+// source — and therefore the SASS of the shipping kernel — is unchanged.
+#ifndef HSK_TC_LEAN
+#define HSK_TC_LEAN 0
+#endif
+#if HSK_TC_LEAN
+#define HSK_TC_KERNEL eval_topk_tc_lean_kernel
+#define HSK_TC_PROF (static_cast<unsigned long long*>(nullptr))
+#else
+#define HSK_TC_KERNEL eval_topk_tc_kernel
+#define HSK_TC_PROF (a.prof)
+#endif
+
 namespace hsk {
 
 constexpr int TC_BM = 128;        // users per CTA tile (UMMA_M)
@@ -268,7 +285,7 @@ __device__ __noinline__ void tc_final_sort(uint64_t* lp, int nA, int nB, int k, 
 
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[TC_ACC_STAGES], bar_tempty[TC_ACC_STAGES];
     __shared__ uint32_t s_tmem_base;
@@ -407,8 +424,13 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
         unsigned long long n_app = 0, n_scan_lane = 0, n_scan_warp = 0;
+#if HSK_TC_LEAN
+        long long tk = 0;
+#define HSK_TICK(i) do { } while (0)
+#else
         long long tk = clock64();
 #define HSK_TICK(i) do { if (a.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } } while (0)
+#endif
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t % TC_ACC_STAGES;
             const int ibs = t & 1;
@@ -437,6 +459,34 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[as]);
             HSK_TICK(1);
+#if HSK_TC_LEAN
+            {   // two inlined copies of the chunk body: chunk 0 reads raw0, chunk 1 reads raw1 in place
+                auto chunk = [&](const uint32_t (&raw)[32], int cc) {
+                    const int c = half * 64 + cc * 32;
+                    if (c >= ncols) return;
+                    float v[32];
+                    const float4* ib4 = reinterpret_cast<const float4*>(ibt + c);
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b4 = ib4[q];
+                        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b4.x;
+                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z;
+                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q + 0], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
+                    }
+                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
+                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
+                    if (row_ok && mx >= tau && !(a.debug_flags & 1))
+                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
+                                      cnt, region);
+                };
+                chunk(raw0, 0);
+                chunk(raw1, 1);
+            }
+#else
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {   // one code instance for both chunks (keeps the hot loop inside the I-cache)
                 const int c = half * 64 + cc * 32;
@@ -460,13 +510,14 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const int c0 = cnt;
                         tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
                                       cnt, region);
-                        if (a.prof) { n_app += cnt - c0; n_scan_lane += 1; }
+                        if (HSK_TC_PROF) { n_app += cnt - c0; n_scan_lane += 1; }
                     }
-                    if (a.prof && __any_sync(kFull, row_ok && mx >= tau)) n_scan_warp += 1;
+                    if (HSK_TC_PROF && __any_sync(kFull, row_ok && mx >= tau)) n_scan_warp += 1;
                 }
 #pragma unroll
                 for (int e = 0; e < 32; ++e) raw0[e] = raw1[e];
             }
+#endif
             ib_pair[(ibs ^ 1) * TC_BN + pt] = ibn0;
             ib_pair[(ibs ^ 1) * TC_BN + pt + 64] = ibn1;
             // Does any row of this pair need its list cut before the next tile?  Common case: no -> one flag store, one
@@ -504,7 +555,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // keeps total / 2 <= 160 of its 256 slots); the last cut always tests and keeps <= 192 for the final sort
                     const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > 288;
                     const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
-                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey, a.prof);
+                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey, HSK_TC_PROF);
                     __syncwarp();
                     const int nA = (total + 1) >> 1;
                     if (lane == 0) {
@@ -535,11 +586,11 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 HSK_TICK(5);
             }
         }
-        if (a.prof && lane == 0) {
-            for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, pc[i]);
-            atomicAdd(a.prof + 12, n_scan_warp);
+        if (HSK_TC_PROF && lane == 0) {
+            for (int i = 0; i < 6; ++i) atomicAdd(HSK_TC_PROF + i, pc[i]);
+            atomicAdd(HSK_TC_PROF + 12, n_scan_warp);
         }
-        if (a.prof) { atomicAdd(a.prof + 10, n_app); atomicAdd(a.prof + 11, n_scan_lane); }
+        if (HSK_TC_PROF) { atomicAdd(HSK_TC_PROF + 10, n_app); atomicAdd(HSK_TC_PROF + 11, n_scan_lane); }
         // rows with a bad user index: empty lists / -1 ids
         for (int j = 0; j < 16; ++j) {
             const int rr = quarter * 32 + half * 16 + j;
@@ -560,6 +611,21 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TC_ACC_STAGES * TC_BN));
     }
 }
+
+#if HSK_TC_LEAN
+// launcher of the LEAN instantiations (called by hsk_eval_topk_tc in the other translation unit)
+int launch_eval_tc_lean(bool tf32, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const EvalTcArgs& a) {
+    auto kern = tf32 ? HSK_TC_KERNEL<true> : HSK_TC_KERNEL<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(lean): smem attribute: %s", cudaGetErrorString(e));
+    kern<<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+    return HSK_OK;
+}
+}  // namespace hsk
+#else
+int launch_eval_tc_lean(bool tf32, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const EvalTcArgs& a);   // hsk_eval_tc_lean.cu
 
 // ---- operand packing: fp32 table rows (optionally gathered) -> [rows, kpad] bf16 | tf32, zero padded ----
 template <bool TF32>
@@ -709,7 +775,12 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     cudaStream_t s = as_stream(stream);
     dim3 grid((Be + TC_BM - 1) / TC_BM, a.n_splits);
     cudaError_t e;
-    if (tf32) {
+    const char* tcv = getenv("HSK_EVAL_TC");   // "lean": the opt-in variant (no phase counters, no chunk-register moves)
+    if (tcv && strcmp(tcv, "lean") == 0 && a.prof == nullptr) {
+        rc = launch_eval_tc_lean(tf32, grid, smem, s, tmA, tmB, a);
+        if (rc) return rc;
+        e = cudaSuccess;
+    } else if (tf32) {
         e = cudaFuncSetAttribute(eval_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
     } else {
@@ -722,3 +793,4 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, TC_CAP, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
     return rc;
 }
+#endif  // !HSK_TC_LEAN

@@ -254,3 +254,33 @@ def test_lean_loop_ring_kernel_equals_the_shipping_ring_kernel(U, I, d, B, N, ki
     _C.mf_train_fused(lay.tables(arena), lay.tables(torch.zeros_like(arena)), u, i_bad, _C.LOSS_KINDS[kind], 0.0,
                       torch.zeros(1, dtype=torch.float64, device='cuda'), status=st)
     assert int(st.item()) & _C.STATUS_BAD_INDEX
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+def test_lean_tensor_core_evaluator_equals_the_shipping_kernel(prec, monkeypatch):
+    """HSK_EVAL_TC=lean (hsk_eval_tc_lean.cu: counters compiled out, chunk bodies duplicated) returns exactly what the
+    shipping kernel returns: same operands, same MMA order, same selection."""
+    from scipy import sparse as sp
+    from hassaku_b200 import _C
+    from hassaku_b200.eval.eval import DeviceCSR
+    U, I, d, B, k = 700, 50_011, 96, 700, 100          # ragged last tile (50 011 % 128 != 0), several CTAs, one split
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    Uw = torch.randn((U, d), device='cuda', generator=gen) / d ** 0.5
+    Vw = torch.randn((I, d), device='cuda', generator=gen) / d ** 0.5
+    Ib = torch.randn((I, 1), device='cuda', generator=gen) * 0.1
+    rng = np.random.RandomState(0)
+    rows = np.repeat(np.arange(U), 40)
+    ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+    ex.sum_duplicates(); ex.sort_indices()
+    exd = DeviceCSR(ex, 'cuda')
+    users = torch.arange(B, device='cuda')
+    P = _C.PRECISIONS[prec]
+    Uq, Vq = _C.pack_rows(Uw, d, P, row_idx=users), _C.pack_rows(Vw, d, P)
+    out = {}
+    for variant in ('', 'lean'):
+        monkeypatch.setenv('HSK_EVAL_TC', variant)
+        s = torch.empty((B, k), device='cuda'); ids = torch.empty((B, k), dtype=torch.int32, device='cuda')
+        scr = torch.empty(_C.eval_topk_tc_scratch_bytes(B, I, k), dtype=torch.uint8, device='cuda')
+        _C.eval_topk_tc(Uq, Vq, P, users, U, k, s, ids, scr, Ib=Ib, excl_indptr=exd.indptr, excl_indices=exd.indices)
+        out[variant] = (s, ids)
+    assert torch.equal(out[''][1], out['lean'][1]) and torch.equal(out[''][0], out['lean'][0])
