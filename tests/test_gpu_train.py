@@ -130,7 +130,8 @@ SHAPES = [
 SHAPES_Q = [
     (20000, 10677, 128, 512, 100, 'sampled_softmax', (False, True, False), 'q'),
     (5000, 3000, 128, 256, 50, 'bpr', (False, True, False), 'q'),
-    (5000, 3000, 128, 2048, 50, 'bpr', (False, True, False), None),     # default dispatch reaches it at B >= 2048
+    (5000, 3000, 128, 2048, 50, 'bpr', (False, True, False), None),     # default dispatch at B >= 2048 (bpr, d 128: the ring; sampled softmax
+                                                                        # at B 8192 takes the quarter-warp kernel in test_gpu_fullsize_properties.py)
     (1000, 500, 96, 67, 9, 'bce', (True, True, True), 'q'),
     (1000, 500, 100, 67, 10, 'sampled_softmax', (True, True, True), 'q'),
     (300, 200, 40, 33, 3, 'bpr', (True, True, True), 'q'),
