@@ -242,3 +242,75 @@ def test_dot_product_sgd_models_reduce_to_mf_factors(name):
     want = model.predict(u, i)                                        # base_classes.py:150-154, the evaluator's call
     got = shell.user_embeddings.weight.detach() @ shell.item_embeddings.weight.detach().T
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize('model_kind', ['mf_item_bias', 'mf_all_biases', 'baseline'])
+def test_autograd_plumbing_of_the_score_function_with_stubbed_kernels(model_kind, monkeypatch):
+    """Host logic only: `_MfScoreFn` routes the dense gradient tables of hsk_mf_scatter_grads to exactly the parameters
+    that exist (None for absent tables, SGDBaseline has no embedding parameters).  The two kernels are replaced by torch
+    stand-ins here — the kernels themselves are tested on the GPU."""
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms import sgd_alg as A
+    U, I, d, B, N1 = 13, 11, 5, 7, 4
+    torch.manual_seed(0)
+    if model_kind == 'baseline':
+        model = A.SGDBaseline(U, I)
+    else:
+        model = A.SGDMatrixFactorization(U, I, d, model_kind == 'mf_all_biases', True, model_kind == 'mf_all_biases')
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn_like(p))
+    lay = model.layout
+
+    def dense_scores(arena, u, i):
+        Uw, Vw, Ub, Ib, Gb = lay.views(arena)
+        s = (Uw[u][:, None, :] * Vw[i]).sum(-1)
+        if Ub is not None:
+            s = s + Ub[u]
+        if Ib is not None:
+            s = s + Ib[i].squeeze(-1)
+        if Gb is not None:
+            s = s + Gb
+        return s
+
+    def fake_scores(tables, u, i, out, status=None):
+        out.copy_(dense_scores(model.arena.detach(), u, i))
+
+    def fake_scatter(tables, gtables, u, i, ds, status=None):
+        with torch.enable_grad():                  # Function.backward runs with grad mode off
+            a = model.arena.detach().clone().requires_grad_()
+            (dense_scores(a, u, i) * ds).sum().backward()
+        fake_scatter.g_arena.copy_(a.grad)
+
+    orig_tables = lay.tables
+
+    def tables_spy(arena):
+        if arena is not model.arena and arena.numel() == lay.n_total and float(arena.abs().sum()) == 0.0:
+            fake_scatter.g_arena = arena           # the fresh gradient arena backward() allocates
+        return orig_tables(arena)
+
+    monkeypatch.setattr(_C, 'make_tables', lambda *args, **kw: None)   # the real one (rightly) refuses host tensors
+    monkeypatch.setattr(_C, 'mf_scores', fake_scores)
+    monkeypatch.setattr(_C, 'mf_scatter_grads', fake_scatter)
+    monkeypatch.setattr(lay, 'tables', tables_spy)
+    u = torch.randint(0, U, (B,))
+    i = torch.randint(0, I, (B, N1))
+    Ub = model.user_bias.weight if model.use_user_bias else None
+    Ib = model.item_bias.weight if model.use_item_bias else None
+    Gb = model.global_bias if model.use_global_bias else None
+    if model_kind == 'baseline':
+        out = A._MfScoreFn.apply(model, u, i, None, None, Ub, Ib, Gb)
+    else:
+        out = A._MfScoreFn.apply(model, u, i, model.user_embeddings.weight, model.item_embeddings.weight, Ub, Ib, Gb)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    # reference: plain autograd through the dense formula on a copy of the arena
+    a = model.arena.detach().clone().requires_grad_()
+    (dense_scores(a, u, i) * w).sum().backward()
+    want = dict(zip(['user_embeddings.weight', 'item_embeddings.weight', 'user_bias.weight', 'item_bias.weight', 'global_bias'],
+                    lay.views(a.grad)))
+    names = [n for n, _ in model.named_parameters()]
+    assert ('user_embeddings.weight' in names) == (model_kind != 'baseline')
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        assert torch.allclose(p.grad, want[n].reshape(p.grad.shape), rtol=1e-6, atol=1e-7), n
