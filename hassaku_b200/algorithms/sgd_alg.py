@@ -29,21 +29,32 @@ class ArenaLayout:
     ALIGN = 32
 
     def __init__(self, n_users: int, n_items: int, d: int, use_user_bias: bool, use_item_bias: bool,
-                 use_global_bias: bool):
+                 use_global_bias: bool, item_block_rows: int = 0, item_bias_row: int = 0):
+        """`item_block_rows` > 0 (sharded step, in-place exchange): the item segment is a block of that many rows whose
+        rows [0, n_items) are the item embeddings and whose rows from `item_bias_row` on hold the item biases flat —
+        the block is then sent / received by the collectives as it lies in the arena (hassaku_b200/sharded.py)."""
         self.n_users, self.n_items, self.d = n_users, n_items, d
         self.ld = _align_up(d, 4)
         off = 0
         self.off_U = off
         off = _align_up(off + n_users * self.ld, self.ALIGN)
         self.off_V = off
-        off = _align_up(off + n_items * self.ld, self.ALIGN)
+        self.item_block_rows, self.item_bias_row = item_block_rows, item_bias_row
+        if item_block_rows:
+            assert n_items <= item_bias_row and item_bias_row * self.ld + item_bias_row <= item_block_rows * self.ld
+            off = _align_up(off + item_block_rows * self.ld, self.ALIGN)
+        else:
+            off = _align_up(off + n_items * self.ld, self.ALIGN)
         self.off_Ub = self.off_Ib = self.off_Gb = -1
         if use_user_bias:
             self.off_Ub = off
             off = _align_up(off + n_users, self.ALIGN)
         if use_item_bias:
-            self.off_Ib = off
-            off = _align_up(off + n_items, self.ALIGN)
+            if item_block_rows:
+                self.off_Ib = self.off_V + item_bias_row * self.ld
+            else:
+                self.off_Ib = off
+                off = _align_up(off + n_items, self.ALIGN)
         if use_global_bias:
             self.off_Gb = off
             off = _align_up(off + 1, self.ALIGN)

@@ -24,6 +24,7 @@ kernels) in production; the world-size-2 gloo tests on CPU plug in a torch refer
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -115,13 +116,27 @@ class ShardedMF:
     """The local shard of an SGDMatrixFactorization plus its optimizer state."""
 
     def __init__(self, n_users: int, n_items: int, d: int, use_user_bias=False, use_item_bias=False, use_global_bias=False,
-                 world: Optional[int] = None, rank: Optional[int] = None, device='cuda', ops=None, group=None):
+                 world: Optional[int] = None, rank: Optional[int] = None, device='cuda', ops=None, group=None,
+                 inplace_exchange: Optional[bool] = None):
+        """`inplace_exchange` (default: env HSK_SHARDED_INPLACE == '1', else off; opt-in until measured on GPUs): lay the
+        item rows and item biases out in the arena as the [capP, ld] block the dense exchange sends, so that the
+        all-gather reads the arena and the reduce-scatter writes the gradient arena directly (4 small copies fewer
+        per step)."""
         world = dist.get_world_size(group) if world is None else world
         rank = dist.get_rank(group) if rank is None else rank
         self.spec = ShardSpec(world, rank, n_users, n_items)
         self.d, self.group, self.device = d, group, torch.device(device)
         self.flags = (use_user_bias, use_item_bias, use_global_bias)
-        self.layout = ArenaLayout(self.spec.n_local_users, self.spec.n_local_items, d, *self.flags)
+        if inplace_exchange is None:
+            inplace_exchange = os.environ.get('HSK_SHARDED_INPLACE') == '1'
+        self.inplace_exchange = bool(inplace_exchange)
+        if self.inplace_exchange:
+            ld = (d + 3) // 4 * 4
+            cap = math.ceil(n_items / world)
+            self.layout = ArenaLayout(self.spec.n_local_users, self.spec.n_local_items, d, *self.flags,
+                                      item_block_rows=cap + math.ceil(cap / ld), item_bias_row=cap)
+        else:
+            self.layout = ArenaLayout(self.spec.n_local_users, self.spec.n_local_items, d, *self.flags)
         self.arena = torch.zeros(self.layout.n_total, dtype=torch.float32, device=self.device)
         self.m = torch.zeros_like(self.arena)
         self.v = torch.zeros_like(self.arena)
@@ -218,9 +233,15 @@ class ShardedMF:
             capP = cap + math.ceil(cap / lay.ld)
             z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=self.device)
             grads = z(G * capP * lay.ld + G * capP)          # [gV replica | gIb compact]: one memset per step
-            self._dense = {'cap': cap, 'capP': capP, 'send': z(capP, lay.ld), 'V': z(G * capP, lay.ld), 'Ib': z(G * capP),
+            self._dense = {'cap': cap, 'capP': capP, 'V': z(G * capP, lay.ld), 'Ib': z(G * capP),
                            'grads': grads, 'gV': grads[:G * capP * lay.ld].view(G * capP, lay.ld),
-                           'gIb': grads[G * capP * lay.ld:], 'recv': z(capP, lay.ld)}
+                           'gIb': grads[G * capP * lay.ld:]}
+            if self.inplace_exchange:      # the arena / gradient arena hold the block themselves
+                blk = slice(lay.off_V, lay.off_V + capP * lay.ld)
+                self._dense['send'] = self.arena[blk].view(capP, lay.ld)
+                self._dense['recv'] = self.g[blk].view(capP, lay.ld)
+            else:
+                self._dense['send'], self._dense['recv'] = z(capP, lay.ld), z(capP, lay.ld)
         return self._dense
 
     def _reduce_scatter(self, out: torch.Tensor, inp: torch.Tensor):
@@ -241,9 +262,10 @@ class ShardedMF:
         cap, capP = D['cap'], D['capP']
         _, _, _, Ib, _ = lay.views(self.arena)
         has_ib = Ib is not None
-        D['send'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
-        if has_ib:
-            D['send'].view(-1)[cap * ld:cap * ld + nl] = Ib.view(-1)
+        if not self.inplace_exchange:
+            D['send'][:nl] = self.arena[lay.off_V:lay.off_V + nl * ld].view(nl, ld)
+            if has_ib:
+                D['send'].view(-1)[cap * ld:cap * ld + nl] = Ib.view(-1)
         dist.all_gather_into_tensor(D['V'], D['send'], group=self.group)
         if has_ib:
             D['Ib'].view(G, capP)[:, :cap] = D['V'].view(G, capP * ld)[:, cap * ld:cap * ld + cap]
@@ -255,10 +277,13 @@ class ShardedMF:
                              _C.LOSS_KINDS[loss_kind], neg_shift, self.loss_accum)
         if has_ib:
             D['gV'].view(G, capP * ld)[:, cap * ld:cap * ld + cap] = D['gIb'].view(G, capP)[:, :cap]
+        # in-place: the block of the gradient arena is otherwise untouched by a dense step (item gradients went to the
+        # replica), so the reduce-scatter writes it directly
         self._reduce_scatter(D['recv'], D['gV'])
-        self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['recv'][:nl])
-        if has_ib:
-            lay.views(self.g)[3].view(-1).add_(D['recv'].view(-1)[cap * ld:cap * ld + nl])
+        if not self.inplace_exchange:
+            self.g[lay.off_V:lay.off_V + nl * ld].view(nl, ld).add_(D['recv'][:nl])
+            if has_ib:
+                lay.views(self.g)[3].view(-1).add_(D['recv'].view(-1)[cap * ld:cap * ld + nl])
         gGb = lay.views(self.g)[4]
         if gGb is not None:
             dist.all_reduce(gGb, group=self.group)

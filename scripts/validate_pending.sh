@@ -4,6 +4,9 @@
 #   gpurun --timeout 600 -- 'bash scripts/validate_pending.sh'
 # 2-GPU part (sharded tensor-core evaluation), separately:
 #   gpurun --gpus 2 --timeout 300 -- 'HSK_RUN_UNVALIDATED=1 timeout 200 python -m pytest tests/test_gpu_sharded.py -q -m gpu'
+# in-place exchange A/B (N = 2):
+#   gpurun --gpus 2 --timeout 300 -- 'for v in 0 1; do HSK_SHARDED_INPLACE=$v HSK_BENCH_WATCHDOG=90 timeout 130 python -m torch.distributed.run \
+#       --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 bench.py --gpus 2 --steps 200 --warmup 20 --no-extras --no-cpu-baseline; done'
 set -u
 mkdir -p gpurun_out
 export HSK_RUN_UNVALIDATED=1

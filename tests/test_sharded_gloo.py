@@ -82,7 +82,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse'):
+def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse', inplace=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -96,7 +96,8 @@ def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse'):
             for p in ref.parameters():
                 p.copy_(torch.randn_like(p) * 0.3)
         lr, wd = 1e-2, 1e-3
-        smf = ShardedMF(U, I, d, *flags, world=world, rank=rank, device='cpu', ops=TorchRefOps())
+        smf = ShardedMF(U, I, d, *flags, world=world, rank=rank, device='cpu', ops=TorchRefOps(), inplace_exchange=inplace)
+        assert smf.inplace_exchange == inplace
         smf.load_full_state_dict(ref.state_dict())
         tr = O.OracleTrainer(ref, kind, lr, wd, 'adamw', neg_train=N)
         rng = np.random.RandomState(3)
@@ -146,6 +147,28 @@ def test_sharded_step_world3_ragged_shards_matches_oracle(exchange, flags, tmp_p
     rounded up to whole rows (cap 14, ld 8 -> 2 extra rows), and the dense exchange without any bias table."""
     mp.spawn(_worker, args=(3, _free_port(), 'bce', flags, str(tmp_path), exchange), nprocs=3, join=True)
     assert (tmp_path / 'ok').exists()
+
+
+@pytest.mark.parametrize('world,exchange,flags', [(2, 'dense', (True, True, True)), (3, 'dense', (False, False, False)),
+                                                  (3, 'dense', (False, True, False)), (2, 'sparse', (False, True, False))])
+def test_sharded_step_inplace_exchange_layout_matches_oracle(world, exchange, flags, tmp_path):
+    """inplace_exchange=True: the item rows + biases live in the arena as the [capP, ld] block the collectives move
+    (no staging copies); dense and sparse steps, state_dict round trip and AdamW over the padded block all still match
+    the single-process oracle."""
+    mp.spawn(_worker, args=(world, _free_port(), 'bce', flags, str(tmp_path), exchange, True), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()
+
+
+def test_inplace_layout_offsets():
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    lay = ArenaLayout(7, 5, 6, True, True, True, item_block_rows=8, item_bias_row=7)    # ld 8: 7 bias floats fit row 7
+    a = torch.arange(lay.n_total, dtype=torch.float32)
+    Uw, Vw, Ub, Ib, Gb = lay.views(a)
+    assert Vw.shape == (5, 6) and Ib.shape == (5, 1)
+    assert int(Ib[0, 0]) == lay.off_V + 7 * 8 and int(Vw[0, 0]) == lay.off_V
+    assert lay.off_Ub >= lay.off_V + 8 * 8 and lay.off_Gb > lay.off_Ub          # nothing overlaps the item block
+    plain = ArenaLayout(7, 5, 6, True, True, True)
+    assert plain.off_Ib > plain.off_Ub and plain.n_total != lay.n_total
 
 
 def test_partition_and_shard_spec():
