@@ -8,16 +8,19 @@ from typing import Dict, Tuple, Union
 
 import torch
 from torch import nn
-from torch.utils import data
+
+MODEL_FILE = 'model.pth'      # checkpoint name inside `conf['model_path']` (base_classes.py:156-165)
+Representation = Union[torch.Tensor, Tuple[torch.Tensor, ...]]
 
 
 class RecommenderAlgorithm(ABC):
-    """algorithms/base_classes.py:12-52."""
+    """What every algorithm of the reference offers (algorithms/base_classes.py:12-52): scoring of (user, items) index
+    batches, a checkpoint round trip through a directory, and a `build_from_conf(conf, dataset)` factory."""
 
     def __init__(self):
         super().__init__()
         self.name = 'RecommenderAlgorithm'
-        logging.info(f'Built {self.name} module')
+        logging.info('Built %s module', self.name)
 
     @abstractmethod
     def predict(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor) -> torch.Tensor:
@@ -25,63 +28,62 @@ class RecommenderAlgorithm(ABC):
 
     @abstractmethod
     def save_model_to_path(self, path: str):
-        pass
+        """Write the model into directory `path`."""
 
     @abstractmethod
     def load_model_from_path(self, path: str):
-        pass
+        """Read back what `save_model_to_path` wrote."""
 
     @staticmethod
     @abstractmethod
-    def build_from_conf(conf: dict, dataset: data.Dataset):
-        pass
+    def build_from_conf(conf: dict, dataset):
+        """Factory from the experiment configuration and the dataset (n_users, n_items, ...)."""
 
 
 class SGDBasedRecommenderAlgorithm(RecommenderAlgorithm, ABC, nn.Module):
-    """algorithms/base_classes.py:88-165."""
+    """Algorithms trained by a `Trainer` with SGD (algorithms/base_classes.py:88-165): an `nn.Module` whose score is
+    `combine(user representation, item representation)`."""
 
     def __init__(self):
         super().__init__()
         self.name = 'SGDBasedRecommenderAlgorithm'
-        logging.info(f'Built {self.name} module')
+        logging.info('Built %s module', self.name)
 
+    # ---- the three pieces a model defines ----
+    @abstractmethod
+    def get_user_representations(self, u_idxs: torch.Tensor) -> Representation:
+        """u_idxs [batch] -> the model's user representation(s)."""
+
+    @abstractmethod
+    def get_item_representations(self, i_idxs: torch.Tensor) -> Representation:
+        """i_idxs [batch, n_neg + 1] -> the model's item representation(s)."""
+
+    @abstractmethod
+    def combine_user_item_representations(self, u_repr: Representation, i_repr: Representation) -> torch.Tensor:
+        """-> logits [batch, n_neg + 1]."""
+
+    # ---- defaults shared by all SGD models ----
     def forward(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor) -> torch.Tensor:
-        # base_classes.py:99-108
-        u_repr = self.get_user_representations(u_idxs)
-        i_repr = self.get_item_representations(i_idxs)
-        return self.combine_user_item_representations(u_repr, i_repr)
-
-    @abstractmethod
-    def get_user_representations(self, u_idxs: torch.Tensor) -> Union[torch.Tensor, Tuple[torch.Tensor]]:
-        pass
-
-    @abstractmethod
-    def get_item_representations(self, i_idxs: torch.Tensor) -> Union[torch.Tensor, Tuple[torch.Tensor, ...]]:
-        pass
-
-    @abstractmethod
-    def combine_user_item_representations(self, u_repr, i_repr) -> torch.Tensor:
-        pass
+        """Training-time scores (base_classes.py:99-108); SGDMatrixFactorization overrides it with the fused kernel."""
+        return self.combine_user_item_representations(self.get_user_representations(u_idxs),
+                                                      self.get_item_representations(i_idxs))
 
     def get_and_reset_other_loss(self) -> Dict:
-        # base_classes.py:139-148
+        """Model-specific extra losses accumulated during `forward` (base_classes.py:139-148).  The Trainer adds
+        `reg_loss` to the recommendation loss after every batch; plain MF has none."""
         return {'reg_loss': torch.zeros(1)}
 
-    @torch.no_grad()
     def predict(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor) -> torch.Tensor:
-        # base_classes.py:150-154
+        """Inference-time scores: eval mode, no autograd (base_classes.py:150-154)."""
         self.eval()
-        return self(u_idxs, i_idxs)
+        with torch.no_grad():
+            return self(u_idxs, i_idxs)
 
     def save_model_to_path(self, path: str):
-        # base_classes.py:156-159
-        path = os.path.join(path, 'model.pth')
-        torch.save(self.state_dict(), path)
+        torch.save(self.state_dict(), os.path.join(path, MODEL_FILE))
         print('Model Saved')
 
     def load_model_from_path(self, path: str):
-        # base_classes.py:161-165 (+ map_location so a GPU-trained model.pth loads anywhere)
-        path = os.path.join(path, 'model.pth')
-        state_dict = torch.load(path, map_location='cpu')
-        self.load_state_dict(state_dict)
+        # map_location: a model.pth written on a GPU loads on any host
+        self.load_state_dict(torch.load(os.path.join(path, MODEL_FILE), map_location='cpu'))
         print('Model Loaded')

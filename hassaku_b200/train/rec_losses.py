@@ -14,25 +14,31 @@ from hassaku_b200 import _C
 
 
 class RecommenderSystemLoss(ABC):
+    """Interface of the reference's loss objects (rec_losses.py:12-25): `compute_loss(logits, labels)` and the
+    `build_from_conf(conf, dataset)` factory; `.name` is the class name.  `loss_kind` / `neg_shift()` are what the fused
+    Trainer path hands to hsk_mf_train_fused instead of calling `compute_loss`."""
+    loss_kind = None
+
     def __init__(self):
-        super().__init__()
-        self.name = 'RecommenderSystemLoss'
-        logging.info(f'Built {self.name} module')
+        self.name = type(self).__name__
+        logging.info('Built %s module', self.name)
+
+    def neg_shift(self) -> float:
+        return 0.0
 
     @abstractmethod
     def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor):
-        pass
+        """logits fp32 [B, 1 + N] (column 0 = positive), labels [B, 1 + N] -> 0-dim loss tensor with autograd."""
 
     @staticmethod
     @abstractmethod
     def build_from_conf(conf: dict, dataset):
-        pass
+        """Factory used by `RecommenderSystemLossesEnum[...].value.build_from_conf` (experiment_helper.py:42)."""
 
-    # --- used by the fused Trainer path (hsk_mf_train_fused) ---
-    loss_kind = None
 
-    def neg_shift(self) -> float:
-        return 0.0
+def _promoted(logits: torch.Tensor, labels) -> torch.dtype:
+    # the reference's BCEWithLogits on float64 labels returns float64 (SURVEY A.2)
+    return torch.promote_types(logits.dtype, labels.dtype) if labels is not None else logits.dtype
 
 
 class _RecLossFn(torch.autograd.Function):
@@ -68,36 +74,24 @@ class RecBinaryCrossEntropy(RecommenderSystemLoss):
     """rec_losses.py:28-53: BCEWithLogits over all B*(1+N) logits."""
     loss_kind = 'bce'
 
-    def __init__(self):
-        super().__init__()
-        self.name = 'RecBinaryCrossEntropy'
-        logging.info(f'Built {self.name} module')
+    def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        return _apply(logits, labels, _C.LOSS_KINDS[self.loss_kind], 0.0, _promoted(logits, labels))
 
     @staticmethod
     def build_from_conf(conf: dict, dataset):
         return RecBinaryCrossEntropy()
-
-    def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        out_dtype = torch.promote_types(logits.dtype, labels.dtype) if labels is not None else logits.dtype
-        return _apply(logits, labels, _C.LOSS_KINDS['bce'], 0.0, out_dtype)
 
 
 class RecBayesianPersonalizedRankingLoss(RecommenderSystemLoss):
     """rec_losses.py:56-88: mean over B*N of -log sigmoid(pos - neg)."""
     loss_kind = 'bpr'
 
-    def __init__(self):
-        super().__init__()
-        self.name = 'RecBayesianPersonalizedRankingLoss'
-        logging.info(f'Built {self.name} module')
+    def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        return _apply(logits, labels, _C.LOSS_KINDS[self.loss_kind], 0.0, _promoted(logits, labels))
 
     @staticmethod
     def build_from_conf(conf: dict, dataset):
         return RecBayesianPersonalizedRankingLoss()
-
-    def compute_loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        out_dtype = torch.promote_types(logits.dtype, labels.dtype) if labels is not None else logits.dtype
-        return _apply(logits, labels, _C.LOSS_KINDS['bpr'], 0.0, out_dtype)
 
 
 class RecSampledSoftmaxLoss(RecommenderSystemLoss):
@@ -107,11 +101,7 @@ class RecSampledSoftmaxLoss(RecommenderSystemLoss):
 
     def __init__(self, n_items: int = None, train_neg_strategy: str = None, neg_train: int = None):
         super().__init__()
-        self.n_items = n_items
-        self.train_neg_strategy = train_neg_strategy
-        self.neg_train = neg_train
-        self.name = 'RecSampledSoftmaxLoss'
-        logging.info(f'Built {self.name} module')
+        self.n_items, self.train_neg_strategy, self.neg_train = n_items, train_neg_strategy, neg_train
 
     @staticmethod
     def build_from_conf(conf: dict, dataset):
