@@ -297,7 +297,7 @@ class ShardedMF:
         self.ops.adamw(self.arena, self.m, self.v, self.g, lr, wd, self.t, decoupled)
 
     # ---- the dense step as ONE CUDA graph (fixed shapes): removes the launches / collectives worth of host latency ----
-    CONST_TABLE_STEPS = 4096
+    CONST_TABLE_STEPS = 32768   # 1 MB table, 0.1 s to fill: a refill (host sync) practically never lands inside a timed region
 
     def _dense_body(self, u_global, i_global, B_global, loss_kind, neg_shift, consts_dev, decoupled):
         """train_step_dense with the AdamW scalars read from device memory (capturable)."""
