@@ -190,6 +190,173 @@ extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n
     return check_launch("hsk_adamw_dense");
 }
 
+// ---- the SAME dense update with a per-row "touched" stamp: rows nobody scattered a gradient into this step have an
+// all-zero gradient row (the optimizer leaves g zero, the scatter kernels are the only writers), so their g is neither
+// read nor re-zeroed: 24 B / element (read + write p, m, v) instead of 32 B.  With g = 0 the arithmetic is the arithmetic
+// of adamw_dense_kernel on a zero gradient, hence bit-identical results.  At cfg4 (2 M x 1 M x 128, B 8192) a step
+// touches 0.35 M of 3 M rows.  A row counts as touched when stamps[row] == stamp; the stamp of step t is
+// 1 + t % 255, so the byte array never needs clearing (a stale match after 255 steps only costs that row's g traffic).
+namespace hsk {
+
+struct AdamSeg {
+    int64_t begin4, end4;            // float4 range [begin4, end4) of the arena
+    const uint8_t* stamps;           // one byte per row of the segment, or null: always read / zero g
+    uint32_t nvec;                   // float4 per row
+};
+struct AdamSegs {
+    AdamSeg s[4];
+    int n;
+};
+
+__host__ __device__ __forceinline__ int stamp_of_step(int64_t step) { return 1 + (int)(step % 255); }
+
+template <int ARITH, bool L2, bool DECAY>
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                         float* __restrict__ g, int64_t n, AdamConsts c_host,
+                                                         const AdamConsts* __restrict__ c_dev, AdamSegs segs, int stamp_host,
+                                                         const int64_t* __restrict__ step_dev) {
+    const AdamConsts c = c_dev ? *c_dev : c_host;
+    const int stamp = step_dev ? stamp_of_step(*step_dev) : stamp_host;
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        bool touched = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < segs.n && segs.s[k].stamps && i >= segs.s[k].begin4 && i < segs.s[k].end4) {
+                const uint32_t row = (uint32_t)(i - segs.s[k].begin4) / segs.s[k].nvec;
+                touched = __ldg(segs.s[k].stamps + row) == (uint8_t)stamp;
+            }
+        }
+        float4 P = p4[i], M = m4[i], V = v4[i];
+        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (touched) G = __ldcs(g4 + i);
+        adam_elem<ARITH, L2, DECAY>(P.x, M.x, V.x, G.x, c);
+        adam_elem<ARITH, L2, DECAY>(P.y, M.y, V.y, G.y, c);
+        adam_elem<ARITH, L2, DECAY>(P.z, M.z, V.z, G.z, c);
+        adam_elem<ARITH, L2, DECAY>(P.w, M.w, V.w, G.w, c);
+        p4[i] = P;
+        m4[i] = M;
+        v4[i] = V;
+        if (touched) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float P = p[t], M = m[t], V = v[t], G = g[t];
+        adam_elem<ARITH, L2, DECAY>(P, M, V, G, c);
+        p[t] = P; m[t] = M; v[t] = V; g[t] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) mark_rows_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t n_rows,
+                                                        uint8_t* __restrict__ stamps, int stamp_host,
+                                                        const int64_t* __restrict__ step_dev) {
+    const uint8_t stamp = (uint8_t)(step_dev ? stamp_of_step(*step_dev) : stamp_host);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int64_t r = idx[e];
+        if (!bad_index(r, n_rows)) stamps[r] = stamp;
+    }
+}
+
+__global__ void __launch_bounds__(256) mark_batch_kernel(const int64_t* __restrict__ u_idx, const int64_t* __restrict__ i_idx,
+                                                         int64_t B, int64_t BN1, int64_t n_users, int64_t n_items,
+                                                         uint8_t* __restrict__ su, uint8_t* __restrict__ si, int stamp_host,
+                                                         const int64_t* __restrict__ step_dev) {
+    const uint8_t stamp = (uint8_t)(step_dev ? stamp_of_step(*step_dev) : stamp_host);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < BN1; e += stride) {
+        if (si) {
+            const int64_t it = i_idx[e];
+            if (!bad_index(it, n_items)) si[it] = stamp;
+        }
+        if (su && e < B) {
+            const int64_t u = u_idx[e];
+            if (!bad_index(u, n_users)) su[u] = stamp;
+        }
+    }
+}
+
+}  // namespace hsk
+
+extern "C" int hsk_row_stamp(int64_t step) { return hsk::stamp_of_step(step); }
+
+extern "C" int hsk_mark_batch(const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t n_users, int64_t n_items,
+                              uint8_t* stamps_users, uint8_t* stamps_items, int64_t step, const int64_t* step_dev,
+                              hsk_stream_t stream) {
+    HSK_REQUIRE(u_idx && i_idx, "hsk_mark_batch: null pointer");
+    if (B <= 0 || (!stamps_users && !stamps_items)) return HSK_OK;
+    const int64_t n = (int64_t)B * N1;
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)hsk::sm_count() * 8;
+    hsk::mark_batch_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, hsk::as_stream(stream)>>>(
+        u_idx, i_idx, B, n, n_users, n_items, stamps_users, stamps_items, hsk::stamp_of_step(step), step_dev);
+    return hsk::check_launch("hsk_mark_batch");
+}
+
+extern "C" int hsk_mark_rows(const int64_t* idx, int64_t n, int64_t n_rows, uint8_t* stamps, int64_t step,
+                             const int64_t* step_dev, hsk_stream_t stream) {
+    HSK_REQUIRE(n >= 0 && n_rows >= 0, "hsk_mark_rows: bad sizes");
+    if (n == 0) return HSK_OK;
+    HSK_REQUIRE(idx && stamps, "hsk_mark_rows: null pointer");
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)hsk::sm_count() * 8;
+    hsk::mark_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, hsk::as_stream(stream)>>>(idx, n, n_rows, stamps,
+                                                                                            hsk::stamp_of_step(step), step_dev);
+    return hsk::check_launch("hsk_mark_rows");
+}
+
+extern "C" int hsk_adamw_dense_rows(float* p, float* m, float* v, float* g, int64_t n, const hsk_row_segment* segments,
+                                    int n_segments, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                    int64_t step, const float* consts_dev, const int64_t* step_dev, int arith, int adam_l2,
+                                    hsk_stream_t stream) {
+    using namespace hsk;
+    HSK_REQUIRE(p && m && v && g, "hsk_adamw_dense_rows: null pointer");
+    HSK_REQUIRE(n >= 0 && (consts_dev || step >= 1), "hsk_adamw_dense_rows: n >= 0 and step >= 1 required");
+    HSK_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), "hsk_adamw_dense_rows: pointers must be 16-byte aligned");
+    HSK_REQUIRE(arith == 0 || arith == 1, "hsk_adamw_dense_rows: arith must be 0 (cuda foreach) or 1 (cpu single-tensor)");
+    HSK_REQUIRE(n_segments >= 0 && n_segments <= 4 && (n_segments == 0 || segments), "hsk_adamw_dense_rows: at most 4 row segments");
+    HSK_REQUIRE((consts_dev == nullptr) == (step_dev == nullptr), "hsk_adamw_dense_rows: consts_dev and step_dev go together (graph mode)");
+    HSK_REQUIRE(!consts_dev || aligned16(consts_dev), "hsk_adamw_dense_rows: consts_dev must be 16-byte aligned");
+    if (n == 0) return HSK_OK;
+    AdamSegs segs;
+    memset(&segs, 0, sizeof(segs));
+    segs.n = n_segments;
+    for (int k = 0; k < n_segments; ++k) {
+        const hsk_row_segment& sg = segments[k];
+        HSK_REQUIRE(sg.offset >= 0 && sg.n_rows >= 0 && sg.ld >= 4 && sg.ld % 4 == 0 && sg.offset % 4 == 0 &&
+                        sg.offset + sg.n_rows * sg.ld <= n && sg.stamps,
+                    "hsk_adamw_dense_rows: segment %d must be a 16-byte aligned range of rows (ld %% 4 == 0) inside [0, n)", k);
+        HSK_REQUIRE((sg.n_rows * (int64_t)sg.ld) / 4 < ((int64_t)1 << 32), "hsk_adamw_dense_rows: segment %d too long", k);
+        segs.s[k].begin4 = sg.offset / 4;
+        segs.s[k].end4 = (sg.offset + sg.n_rows * sg.ld) / 4;
+        segs.s[k].stamps = sg.stamps;
+        segs.s[k].nvec = (uint32_t)(sg.ld / 4);
+    }
+    AdamConsts c;
+    memset(&c, 0, sizeof(c));
+    if (!consts_dev) fill_consts(c, lr, beta1, beta2, eps, weight_decay, step);
+    const bool l2 = adam_l2 != 0 && weight_decay != 0.0;
+    const bool decay = adam_l2 == 0 && weight_decay != 0.0;
+    const int threads = 256;
+    int64_t want = ((n >> 2) + threads - 1) / threads;
+    if (want < 1) want = 1;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const int blocks = (int)(want < cap ? want : cap);
+    cudaStream_t s = as_stream(stream);
+    const AdamConsts* cp = reinterpret_cast<const AdamConsts*>(consts_dev);
+    const int stamp = stamp_of_step(step);
+#define HSK_LAUNCH_ADAMR(A, L, D) adamw_rows_kernel<A, L, D><<<blocks, threads, 0, s>>>(p, m, v, g, n, c, cp, segs, stamp, step_dev)
+#define HSK_ADAMR_LD(A)                                 \
+    if (l2) { HSK_LAUNCH_ADAMR(A, true, false); }       \
+    else if (decay) { HSK_LAUNCH_ADAMR(A, false, true); } \
+    else { HSK_LAUNCH_ADAMR(A, false, false); }
+    if (arith == 0) { HSK_ADAMR_LD(0) } else { HSK_ADAMR_LD(1) }
+    return check_launch("hsk_adamw_dense_rows");
+}
+
 // ---- row-sparse "lazy" AdamW (north_star item 2, reported separately from the dense, torch-faithful mode) ------------
 // Only rows that received a gradient in this step are updated (p, m, v) — the semantics of torch.optim.SparseAdam plus
 // decoupled weight decay on the touched rows; untouched rows keep p, m, v unchanged (no decay, no momentum tail), which

@@ -3,8 +3,8 @@
 //
 // Per CTA (320 threads, 1 per SM):
 //   warp 0      TMA producer: the 128-user A tile is loaded ONCE (resident for every item tile); item (B) tiles of
-//               128 rows x 128 bytes of K stream through a 4-stage ring (cp.async.bulk.tensor.2d, SWIZZLE_128B)
-//   warp 1      allocates 256 TMEM columns (2 accumulator stages x 128 fp32 columns) and issues tcgen05.mma
+//               128 rows x 128 bytes of K stream through a ring of up to 10 stages (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//   warp 1      allocates all 512 TMEM columns (4 accumulator stages x 128 fp32 columns) and issues tcgen05.mma
 //               (cta_group::1, M = 128, N = 128, 32 bytes of K per instruction), tcgen05.commit -> mbarriers
 //   warps 2-9   epilogue (two warps per scheduler): a thread owns accumulator lane (= user row) r and one 64-column half of
 //               the tile; tcgen05.ld 32 columns at a time, + item bias (128-bit uniform loads), chunk max against the row's
@@ -19,23 +19,6 @@
 #include <cuda_bf16.h>
 
 #include "hsk_topk.cuh"
-
-// This file is compiled twice: as itself (the shipping kernel + every host entry point) and through
-// hsk_eval_tc_lean.cu with HSK_TC_LEAN = 1 (only the kernel, under another name, plus its launcher).  LEAN is an
-// opt-in experiment (HSK_EVAL_TC=lean) that has not been measured yet: the in-kernel phase counters are compiled out
-// and the two 32-column chunks of a tile are processed by two inlined copies of the chunk body instead of one copy
-// plus a 32-register move of the second chunk into the first one's registers.  With HSK_TC_LEAN = 0 the preprocessed
-// source — and therefore the SASS of the shipping kernel — is unchanged.
-#ifndef HSK_TC_LEAN
-#define HSK_TC_LEAN 0
-#endif
-#if HSK_TC_LEAN
-#define HSK_TC_KERNEL eval_topk_tc_lean_kernel
-#define HSK_TC_PROF (static_cast<unsigned long long*>(nullptr))
-#else
-#define HSK_TC_KERNEL eval_topk_tc_kernel
-#define HSK_TC_PROF (a.prof)
-#endif
 
 namespace hsk {
 
@@ -62,8 +45,6 @@ struct EvalTcArgs {
     int64_t n_users, n_local, id_offset, id_stride;
     int Be, k, num_kb, kelems_per_kb;
     int n_tiles, tiles_per_split, n_splits, n_stages;
-    int debug_flags;   // HSK_TC_DEBUG (measurement only): 1 = no candidate scan
-    unsigned long long* prof;   // optional [8] cycle counters of the epilogue phases (hsk_eval_tc_set_profile_buffer)
     uint64_t* cand;
     float* out_scores;
     int32_t* out_ids;
@@ -170,13 +151,11 @@ constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
 // Returns the number of survivors.
 __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, int chkB, int k, int lane,
                                           const int32_t* __restrict__ excl, int64_t lo, int64_t hi, bool check, int max_keep,
-                                          float* new_tau, uint64_t* new_taukey, unsigned long long* tprof) {
+                                          float* new_tau, uint64_t* new_taukey) {
     // check == false: the exclusion test is postponed to the final cut.  At most n_excl = hi - lo excluded items can sit
     // in the list, so selecting the (k + n_excl)-th largest RAW key is still a conservative threshold; it saves the
     // ~11 k cycles of binary searches that made every cut stall the MMA pipeline.
     if (!check) k += (int)(hi - lo);
-    long long t0 = tprof ? clock64() : 0;
-#define HSK_CUT_TICK(i) do { if (tprof) { const long long t1 = clock64(); if (lane == 0) atomicAdd(tprof + (i), (unsigned long long)(t1 - t0)); t0 = t1; } } while (0)
     uint64_t key[TC_KPL];
     bool unchecked[TC_KPL];
 #pragma unroll
@@ -188,11 +167,6 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
         key[r] = valid ? lp[e] : 0ull;
         unchecked[r] = valid && idx >= (inA ? chkA : chkB);
     }
-    { uint64_t x = 0;
-#pragma unroll
-      for (int r = 0; r < TC_KPL; ++r) x ^= key[r];
-      if (tprof && x == 0x123456789ull) lp[0] = x; }
-    HSK_CUT_TICK(6);
     if (check && hi > lo) {
         int32_t id[TC_KPL];
         bool found[TC_KPL];
@@ -204,7 +178,6 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
         for (int r = 0; r < TC_KPL; ++r)
             if (found[r] && key[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
     }
-    HSK_CUT_TICK(7);
     const int n = cA + cB;
     uint32_t T = 0;
     if (n > k) {
@@ -221,7 +194,6 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
             if (c >= k) T = cand;
         }
     }
-    HSK_CUT_TICK(8);
     // compaction: keep keys whose prefix >= T (all valid keys when n <= k)
     int mine = 0;
 #pragma unroll
@@ -257,8 +229,6 @@ __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, i
             ++pos;
         }
     }
-    HSK_CUT_TICK(9);
-    if (tprof && lane == 0) atomicAdd(tprof + 13, 1ull);
     *new_tau = (n > k) ? from_orderable(T << 16) : -INFINITY;   // lower edge of bucket T (n > k implies T >= 0x007F)
     *new_taukey = (n > k) ? ((uint64_t)(T << 16) << 32) : 0ull;
     return total;
@@ -285,7 +255,7 @@ __device__ __noinline__ void tc_final_sort(uint64_t* lp, int nA, int nB, int k, 
 
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[TC_ACC_STAGES], bar_tempty[TC_ACC_STAGES];
     __shared__ uint32_t s_tmem_base;
@@ -422,15 +392,6 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         named_bar_sync(bar_id, 64);
 
-        unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
-        unsigned long long n_app = 0, n_scan_lane = 0, n_scan_warp = 0;
-#if HSK_TC_LEAN
-        long long tk = 0;
-#define HSK_TICK(i) do { } while (0)
-#else
-        long long tk = clock64();
-#define HSK_TICK(i) do { if (a.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } } while (0)
-#endif
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t % TC_ACC_STAGES;
             const int ibs = t & 1;
@@ -448,7 +409,6 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             mbar_wait(&bar_tfull[as], ((uint32_t)t / TC_ACC_STAGES) & 1u);
             tc_fence_after();
-            HSK_TICK(0);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN + (uint32_t)(half * 64);
             uint32_t raw0[32], raw1[32];
             tc_ld32_issue(taddr, raw0);
@@ -458,8 +418,6 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[as]);
-            HSK_TICK(1);
-#if HSK_TC_LEAN
             {   // two inlined copies of the chunk body: chunk 0 reads raw0, chunk 1 reads raw1 in place
                 auto chunk = [&](const uint32_t (&raw)[32], int cc) {
                     const int c = half * 64 + cc * 32;
@@ -479,45 +437,13 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
                     const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
                     if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
-                    if (row_ok && mx >= tau && !(a.debug_flags & 1))
+                    if (row_ok && mx >= tau)
                         tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
                                       cnt, region);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);
             }
-#else
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {   // one code instance for both chunks (keeps the hot loop inside the I-cache)
-                const int c = half * 64 + cc * 32;
-                if (c < ncols) {
-                    float v[32];
-                    const float4* ib4 = reinterpret_cast<const float4*>(ibt + c);
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b4 = ib4[q];
-                        v[4 * q + 0] = __uint_as_float(raw0[4 * q + 0]) + b4.x;
-                        v[4 * q + 1] = __uint_as_float(raw0[4 * q + 1]) + b4.y;
-                        v[4 * q + 2] = __uint_as_float(raw0[4 * q + 2]) + b4.z;
-                        v[4 * q + 3] = __uint_as_float(raw0[4 * q + 3]) + b4.w;
-                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q + 0], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
-                    }
-                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
-                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
-                    if (row_ok && mx >= tau && !(a.debug_flags & 1)) {
-                        const int c0 = cnt;
-                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
-                                      cnt, region);
-                        if (HSK_TC_PROF) { n_app += cnt - c0; n_scan_lane += 1; }
-                    }
-                    if (HSK_TC_PROF && __any_sync(kFull, row_ok && mx >= tau)) n_scan_warp += 1;
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) raw0[e] = raw1[e];
-            }
-#endif
             ib_pair[(ibs ^ 1) * TC_BN + pt] = ibn0;
             ib_pair[(ibs ^ 1) * TC_BN + pt + 64] = ibn1;
             // Does any row of this pair need its list cut before the next tile?  Common case: no -> one flag store, one
@@ -526,9 +452,7 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const bool last = (t + 1 == n_my_tiles);
             const bool warp_need = __any_sync(kFull, row_ok && cnt > prune_at) || last;
             if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
-            HSK_TICK(2);
             named_bar_sync(bar_id, 64);
-            HSK_TICK(3);
             const bool pair_need = (s_need[quarter][0][t & 1] | s_need[quarter][1][t & 1]) != 0;
             if (pair_need) {
                 s_cnt2[half][r] = cnt;
@@ -555,7 +479,7 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     // keeps total / 2 <= 160 of its 256 slots); the last cut always tests and keeps <= 192 for the final sort
                     const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > 288;
                     const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
-                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey, HSK_TC_PROF);
+                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey);
                     __syncwarp();
                     const int nA = (total + 1) >> 1;
                     if (lane == 0) {
@@ -580,17 +504,10 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         }
                     }
                 }
-                HSK_TICK(4);
                 named_bar_sync(bar_id, 64);
                 cnt = s_cnt2[half][r];
-                HSK_TICK(5);
             }
         }
-        if (HSK_TC_PROF && lane == 0) {
-            for (int i = 0; i < 6; ++i) atomicAdd(HSK_TC_PROF + i, pc[i]);
-            atomicAdd(HSK_TC_PROF + 12, n_scan_warp);
-        }
-        if (HSK_TC_PROF) { atomicAdd(HSK_TC_PROF + 10, n_app); atomicAdd(HSK_TC_PROF + 11, n_scan_lane); }
         // rows with a bad user index: empty lists / -1 ids
         for (int j = 0; j < 16; ++j) {
             const int rr = quarter * 32 + half * 16 + j;
@@ -611,21 +528,6 @@ HSK_TC_KERNEL(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TC_ACC_STAGES * TC_BN));
     }
 }
-
-#if HSK_TC_LEAN
-// launcher of the LEAN instantiations (called by hsk_eval_topk_tc in the other translation unit)
-int launch_eval_tc_lean(bool tf32, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                        const EvalTcArgs& a) {
-    auto kern = tf32 ? HSK_TC_KERNEL<true> : HSK_TC_KERNEL<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(lean): smem attribute: %s", cudaGetErrorString(e));
-    kern<<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
-    return HSK_OK;
-}
-}  // namespace hsk
-#else
-int launch_eval_tc_lean(bool tf32, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                        const EvalTcArgs& a);   // hsk_eval_tc_lean.cu
 
 // ---- operand packing: fp32 table rows (optionally gathered) -> [rows, kpad] bf16 | tf32, zero padded ----
 template <bool TF32>
@@ -700,9 +602,6 @@ static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split,
 
 using namespace hsk;
 
-static unsigned long long* g_tc_prof = nullptr;   // measurement hook, not part of the public header
-extern "C" void hsk_debug_eval_tc_profile(unsigned long long* dev_counters) { g_tc_prof = dev_counters; }
-
 extern "C" int hsk_eval_tc_kpad(int d, int precision) {
     const int per_kb = (precision == HSK_PREC_TF32) ? 32 : 64;
     return ((d + per_kb - 1) / per_kb) * per_kb;
@@ -769,18 +668,11 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
     if (n_stages < 2) n_stages = 2;
     a.n_stages = n_stages;
-    { const char* dbg = getenv("HSK_TC_DEBUG"); a.debug_flags = dbg ? atoi(dbg) : 0; }
-    a.prof = g_tc_prof;
     const size_t smem = (size_t)(num_kb + n_stages) * TC_TILE_BYTES + 1024;
     cudaStream_t s = as_stream(stream);
     dim3 grid((Be + TC_BM - 1) / TC_BM, a.n_splits);
     cudaError_t e;
-    const char* tcv = getenv("HSK_EVAL_TC");   // "lean": the opt-in variant (no phase counters, no chunk-register moves)
-    if (tcv && strcmp(tcv, "lean") == 0 && a.prof == nullptr) {
-        rc = launch_eval_tc_lean(tf32, grid, smem, s, tmA, tmB, a);
-        if (rc) return rc;
-        e = cudaSuccess;
-    } else if (tf32) {
+    if (tf32) {
         e = cudaFuncSetAttribute(eval_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
     } else {
@@ -793,4 +685,3 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, TC_CAP, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
     return rc;
 }
-#endif  // !HSK_TC_LEAN

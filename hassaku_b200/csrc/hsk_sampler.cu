@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_negatives_kernel(
     const int64_t lo = indptr[u], hi = indptr[u + 1];
     for (int j = lane; j < N; j += 32) { cnt[j] = 0u; val[j] = 0xFFFFFFFFu; }  // 0xFFFFFFFF = "flagged, must draw"
     __syncwarp();
+    bool clean = false;
     for (int round = 0; round < kSamplerMaxRounds; ++round) {
         // draw for flagged slots (flag is kept in the top bit of cnt)
         for (int j = lane; j < N; j += 32) {
@@ -112,8 +113,11 @@ __global__ void __launch_bounds__(kSamplerWarps * 32) sample_negatives_kernel(
             any |= f;
         }
         __syncwarp();
-        if (!__any_sync(kFull, any)) break;
+        if (!__any_sync(kFull, any)) { clean = true; break; }
     }
+    // round cap hit (e.g. more distinct negatives asked for than the user has non-train items): the row still holds flagged
+    // slots — report it instead of emitting them silently
+    if (!clean && lane == 0 && status) atomicOr(status, HSK_STATUS_SAMPLER_ROUNDS);
     if (lane == 0) out[0] = pos_idx ? pos_idx[b] : 0;
     for (int j = lane; j < N; j += 32) out[1 + j] = (int64_t)val[j];
 }

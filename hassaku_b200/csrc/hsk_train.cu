@@ -467,17 +467,26 @@ extern "C" int hsk_mf_train_fused(const hsk_mf_tables* t, const hsk_mf_tables* g
                                   const int64_t* i_idx, int B, int N1, int loss_kind, float neg_shift,
                                   double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,
                                   hsk_stream_t stream) {
-    return hsk_mf_train_fused_n(t, g, u_idx, i_idx, B, N1, B, loss_kind, neg_shift, loss_accum, scores_out, dscores_out,
-                                status, stream);
+    return hsk_mf_train_fused_v(t, g, u_idx, i_idx, B, N1, B, loss_kind, neg_shift, loss_accum, scores_out, dscores_out,
+                                status, HSK_TRAIN_AUTO, stream);
 }
 
 extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx,
                                     const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind, float neg_shift,
                                     double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,
                                     hsk_stream_t stream) {
+    return hsk_mf_train_fused_v(t, g, u_idx, i_idx, B, N1, B_global, loss_kind, neg_shift, loss_accum, scores_out,
+                                dscores_out, status, HSK_TRAIN_AUTO, stream);
+}
+
+extern "C" int hsk_mf_train_fused_v(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx,
+                                    const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind, float neg_shift,
+                                    double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,
+                                    int variant, hsk_stream_t stream) {
     TrainArgs a;
     HSK_REQUIRE(B_global >= B, "hsk_mf_train_fused_n: the global batch cannot be smaller than the local one");
     HSK_REQUIRE(g, "hsk_mf_train_fused: gradient tables are null");
+    HSK_REQUIRE(variant >= HSK_TRAIN_AUTO && variant <= HSK_TRAIN_QWARP, "hsk_mf_train_fused_v: unknown kernel variant %d", variant);
     int rc = fill_args(a, t, g, u_idx, i_idx, B, N1, "hsk_mf_train_fused");
     if (rc) return rc;
     HSK_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "hsk_mf_train_fused: unknown loss kind %d", loss_kind);
@@ -492,21 +501,18 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
     cudaStream_t s = as_stream(stream);
     const int nv = (a.nvec + 31) / 32;
     const int threads = kWarpsPerCta * 32;
-    // bpr / bce default to the TMA-pipelined kernel (hsk_train_tma.cu); HSK_TRAIN_FUSED=regs selects the
-    // register-gather kernel of this file (kept for A/B measurements and as the sampled-softmax path)
-    const char* variant = getenv("HSK_TRAIN_FUSED");
-    const bool use_tma = !(variant && strcmp(variant, "regs") == 0);
-    const bool use_tma2 = variant && strcmp(variant, "tma2") == 0;
-    const char* nored = getenv("HSK_DEBUG_NORED");
-    a.debug_flags = (nored && nored[0] == '1') ? 1 : 0;
-    const bool use_q = !variant || strcmp(variant, "q") == 0;   // default; "regs" / "tma" force the warp-per-row kernels
-    if (use_q) {
-        if (variant) a.debug_flags |= 4;   // HSK_TRAIN_FUSED=q: take the quarter-warp kernel whatever the batch size (tests)
+    // Kernel choice (all variants compute the same step; HSK_TRAIN_AUTO picks by shape from the B200 measurements):
+    //   quarter-warp kernel (hsk_train_q.cu) for rows <= 128 floats where it measured faster, else for bpr / bce the
+    //   bulk-copy ring (hsk_train_tma.cu), else (sampled softmax with long rows) the register-gather kernel of this file
+    const bool try_q = variant == HSK_TRAIN_AUTO || variant == HSK_TRAIN_QWARP;
+    const bool use_ring = variant != HSK_TRAIN_REGS;
+    if (try_q) {
+        a.force_q = variant == HSK_TRAIN_QWARP ? 1 : 0;
         a.inv_count = loss_kind == HSK_LOSS_BPR ? 1.0 / ((double)B_global * (double)(N1 - 1))
                     : loss_kind == HSK_LOSS_BCE ? 1.0 / ((double)B_global * (double)N1) : 1.0 / (double)B_global;
         a.j_per_cta = N1;
-        const int rc = launch_train_fused_q(a, loss_kind, s);
-        if (rc != 1) return rc;
+        const int rcq = launch_train_fused_q(a, loss_kind, s);
+        if (rcq != 1) return rcq;
     }
     if (loss_kind == HSK_LOSS_BPR) {
         a.inv_count = 1.0 / ((double)B_global * (double)(N1 - 1));
@@ -517,16 +523,14 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
             cudaError_t e = cudaMemsetAsync(dscores_out, 0, sizeof(float) * (size_t)B * N1, s);
             if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_mf_train_fused: memset: %s", cudaGetErrorString(e));
         }
-        if (use_tma2) return launch_train_fused_tma2(a, loss_kind, s);
-        if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
+        if (use_ring) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BPR><<<grid, threads, 0, s>>>(a)));
     } else if (loss_kind == HSK_LOSS_BCE) {
         a.inv_count = 1.0 / ((double)B_global * (double)N1);
         a.j_per_cta = pick_j_per_cta(B, N1, true);
         if (a.j_per_cta > 128) a.j_per_cta = 128;
         dim3 grid(B, (N1 + a.j_per_cta - 1) / a.j_per_cta);
-        if (use_tma2) return launch_train_fused_tma2(a, loss_kind, s);
-        if (use_tma) return launch_train_fused_tma(a, loss_kind, s);
+        if (use_ring) return launch_train_fused_tma(a, loss_kind, s);
         HSK_DISPATCH_NV(nv, (mf_train_fused_kernel<NV, HSK_LOSS_BCE><<<grid, threads, 0, s>>>(a)));
     } else {
         a.inv_count = 1.0 / (double)B_global;

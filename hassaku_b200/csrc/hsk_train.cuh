@@ -1,4 +1,4 @@
-// Argument block shared by the training-step kernels (hsk_train.cu, hsk_train_tma.cu).
+// Argument block shared by the training-step kernels (hsk_train.cu, hsk_train_tma.cu, hsk_train_q.cu).
 #pragma once
 #include "hsk_common.cuh"
 
@@ -30,14 +30,12 @@ struct TrainArgs {
     float* dscores_out;
     const float* __restrict__ dscores_in;
     int32_t* status;
-    int debug_flags;  // bit 0: skip item-gradient reductions (HSK_DEBUG_NORED=1, measurement only); bit 2: force the quarter-warp kernel
+    int force_q;  // hsk_mf_train_fused_v(variant = quarter-warp): take that kernel whatever the batch size (parity tests)
 };
 
 
 // hsk_train_tma.cu: the bulk-copy (TMA) pipelined fused step for bpr / bce; returns HSK_OK or an error code
 int launch_train_fused_tma(const TrainArgs& a, int loss_kind, cudaStream_t s);
-// hsk_train_tma2.cu: the same kernel with a leaner inner loop; opt-in (HSK_TRAIN_FUSED=tma2) until measured on a B200
-int launch_train_fused_tma2(const TrainArgs& a, int loss_kind, cudaStream_t s);
 // hsk_train_q.cu: quarter-warp-per-sample fused step for rows of at most 128 floats; returns 1 (no launch) when the
 // shape is outside its range and the caller should use the warp-per-row kernels
 int launch_train_fused_q(const TrainArgs& a, int loss_kind, cudaStream_t s);

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
     const bool has_ub = a.Ub != nullptr, has_ib = a.Ib != nullptr, has_gb = a.Gb != nullptr;
     const float ubv = (has_ub && live) ? a.Ub[u] : 0.f, gbv = has_gb ? a.Gb[0] : 0.f;
     const float invf = (float)a.inv_count;
-    const bool do_red = !(a.debug_flags & 1);
+    constexpr bool do_red = true;
 
     QRow<K4> ur, gu;
     gu.zero();
@@ -278,7 +278,7 @@ static int launch_q(const TrainArgs& a, cudaStream_t s) {
 // where the warp-per-row ring measured faster
 int launch_train_fused_q(const TrainArgs& a, int loss_kind, cudaStream_t s) {
     if (a.nvec > 32) return 1;
-    if (!(a.debug_flags & 4)) {
+    if (!a.force_q) {
         if (a.B < 2048) return 1;
         // measured on B200 (B 8192, N 100, tables in L2; scripts/kbench.py trainraw): at d = 128 bpr / bce are bound by L2
         // traffic (reads + REDs) in every layout and the bulk-copy ring is ~10 % ahead (160 vs 176 us); at d = 64 this

@@ -34,6 +34,7 @@ class NegativeSampler(InteractionSampler):
         self.n_items = train_dataset.n_items
         self.pop_distribution = train_dataset.pop_distribution.copy()
         self.name = 'NegativeSampler'
+        logging.info(f'Built {self.name} module: n_neg={n_neg}, strategy={neg_sampling_strategy}')
 
     def popularity_cdf(self) -> np.ndarray:
         """64-bit fixed-point CDF of pop^alpha (what hsk_sample_negatives consumes for the 'popular' strategy)."""
@@ -44,7 +45,6 @@ class NegativeSampler(InteractionSampler):
         out = np.array([min(int(x * 18446744073709551616.0), 18446744073709551615) for x in c], dtype=np.uint64)
         out[-1] = np.uint64(18446744073709551615)
         return out
-        logging.info(f'Built {self.name} module: n_neg={n_neg}, strategy={neg_sampling_strategy}')
 
 
 class TrainDataLoader:
@@ -97,6 +97,19 @@ class TrainDataLoader:
                             self.indices, self.seed, step, i_idxs, s.distinct_in_row, self.status, pop_cdf=self.pop_cdf)
         return i_idxs
 
+    def check_status(self):
+        """One host sync: raise if a sampler launch since the last check met a bad user index or hit its round cap."""
+        st = int(self.status.item())
+        if st:
+            self.status.zero_()
+            what = []
+            if st & _C.STATUS_BAD_INDEX:
+                what.append('a user index outside [0, n_users)')
+            if st & _C.STATUS_SAMPLER_ROUNDS:
+                what.append('a row that still held train positives / duplicates after the round cap (neg_train larger '
+                            'than the number of admissible items of a user?)')
+            raise _C.HskError('hsk_sample_negatives reported ' + ' and '.join(what))
+
     def __iter__(self):
         n = len(self.dataset)
         order = torch.randperm(n, device=self.device, generator=self._gen) if self.shuffle else \
@@ -107,6 +120,7 @@ class TrainDataLoader:
             i_idxs = self.sample_batch(u_idxs, pos, self.step)
             self.step += 1
             yield u_idxs, i_idxs, self.labels_for(len(sel))
+        self.check_status()      # once per epoch, like model.check_status()
 
 
 class EvalLoader:

@@ -307,13 +307,23 @@ def log_info_results(metrics_values: dict):
 class TopKScorer:
     """hsk_eval_topk / hsk_eval_topk_tc for one model: owns the scratch, output buffers and (tensor-core modes) the
     packed operand copies for a fixed user-batch size.  precision: 'fp32' (exact, SIMT FFMA), 'tf32' or 'bf16'
-    (tcgen05).  Call `refresh()` after the model's weights changed (re-packs the item table)."""
+    (tcgen05).  In the tensor-core modes the kernel ranks all items in low precision and returns its best
+    k + RESCORE_MARGIN candidates, which hsk_rescore_topk scores again from the fp32 tables: the returned ids / scores
+    are the fp32 evaluator's unless a true top-k item fell more than RESCORE_MARGIN ranks in the low-precision pass
+    (`rescore=False` returns the raw low-precision ranking).  Call `refresh()` after the model's weights changed
+    (re-packs the item table)."""
+    RESCORE_MARGIN = 28
 
-    def __init__(self, alg: SGDMatrixFactorization, batch_size: int, k: int, precision: str = 'fp32'):
+    def __init__(self, alg: SGDMatrixFactorization, batch_size: int, k: int, precision: str = 'fp32',
+                 rescore: Optional[bool] = None):
         if precision not in _C.PRECISIONS:
             raise ValueError(f'eval precision {precision!r} not in {sorted(_C.PRECISIONS)}')
         self.alg, self.k, self.precision = alg, k, _C.PRECISIONS[precision]
         dev = alg.arena.device
+        if rescore is None:
+            rescore = bool(getattr(alg, 'eval_rescore', True))
+        self.kc = min(128, k + self.RESCORE_MARGIN, alg.n_items) if (self.precision != 0 and rescore) else k
+        self.rescore = self.kc > k
         if self.precision == 0:
             nbytes = _C.eval_topk_scratch_bytes(batch_size, alg.n_items, k)
         else:
@@ -326,6 +336,9 @@ class TopKScorer:
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.scores = torch.empty((batch_size, k), dtype=torch.float32, device=dev)
         self.ids = torch.empty((batch_size, k), dtype=torch.int32, device=dev)
+        if self.rescore:
+            self.cand_scores = torch.empty((batch_size, self.kc), dtype=torch.float32, device=dev)
+            self.cand_ids = torch.empty((batch_size, self.kc), dtype=torch.int32, device=dev)
         self.batch_size = batch_size
 
     def refresh(self):
@@ -345,11 +358,14 @@ class TopKScorer:
             Uq = self.Uq[:B]
             _C.pack_rows(alg.user_embeddings.weight.detach(), alg.embedding_dim, self.precision, row_idx=u_idxs, out=Uq,
                          status=alg._status())
-            _C.eval_topk_tc(Uq, self.Vq, self.precision, u_idxs, alg.n_users, self.k, scores, ids, self.scratch,
+            cs, ci = (self.cand_scores[:B], self.cand_ids[:B]) if self.rescore else (scores, ids)
+            _C.eval_topk_tc(Uq, self.Vq, self.precision, u_idxs, alg.n_users, self.kc, cs, ci, self.scratch,
                             Ub=alg.user_bias.weight.detach() if alg.use_user_bias else None,
                             Ib=alg.item_bias.weight.detach() if alg.use_item_bias else None,
                             Gb=alg.global_bias.detach() if alg.use_global_bias else None,
                             excl_indptr=ex_p, excl_indices=ex_i, status=alg._status())
+            if self.rescore:
+                _C.rescore_topk(alg._tables(), u_idxs, ci, self.k, scores, ids, status=alg._status())
         return scores, ids
 
 
@@ -456,13 +472,19 @@ def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evalu
                 evaluator.eval_batch_topk(u_idxs, ids, labels)
         alg.check_status()
     else:
-        # generic algorithms: the reference's dense path (eval.py:224-236) on CUDA tensors
+        # generic algorithms (eval.py:224-236): `predict` runs where the algorithm lives — numpy / scipy models (KNN, SLIM,
+        # EASE, pop) index host arrays with the loader's CPU tensors, torch models get tensors on their parameters'
+        # device — exactly as the reference calls it; only the returned scores go to the GPU, where masking, top-k and the
+        # metrics run (eval_batch)
         dev = torch.device('cuda' if str(device) == 'cpu' else device)
+        alg_dev = torch.device('cpu')
+        if isinstance(alg, torch.nn.Module):
+            alg_dev = next((p.device for p in alg.parameters()), torch.device(device))
         exclude = getattr(dataset.exclude_data, 'm', dataset.exclude_data)
         for u_idxs, i_idxs, labels in (tqdm(eval_loader) if verbose else eval_loader):
-            out = alg.predict(u_idxs.to(dev), i_idxs.to(dev))
+            out = alg.predict(u_idxs.to(alg_dev), i_idxs.to(alg_dev))
             if not isinstance(out, torch.Tensor):
-                out = torch.tensor(out)
+                out = torch.as_tensor(np.asarray(out))
             out = out.to(dev, torch.float32)
             batch_mask = torch.from_numpy(exclude[u_idxs.cpu().numpy()].toarray().astype(bool)).to(dev)
             out[batch_mask] = -torch.inf

@@ -8,6 +8,9 @@ Differences from the reference, all deliberate:
   * the three `.item()` syncs per step (trainer.py:141-143) become one device-side fp64 accumulator read once per
     epoch; the reported `epoch_train_*` values are the same quantities
   * device 'cpu' is rejected loudly — there is no CPU path
+  * models / losses outside this path (ACF, ProtoMF, DeepMF, ECF ...; any loss without a fused kernel): after
+    `hassaku_b200.install()` the reference's own Trainer is still reachable and `Trainer(...)` hands such a model to it
+    unchanged, so the rest of `AlgorithmsEnum` keeps training as before
 """
 import logging
 
@@ -23,11 +26,30 @@ from hassaku_b200.train.rec_losses import RecommenderSystemLoss
 from hassaku_b200.train.trainer_step import FusedMFTrainStep
 
 
+def _reference_trainer():
+    """The reference's own `train.trainer.Trainer`, if `hassaku_b200.install()` replaced it (else None)."""
+    import hassaku_b200
+    for obj, name, val in hassaku_b200._ORIGINALS:
+        if name == 'Trainer' and getattr(obj, '__name__', '') == 'train.trainer':
+            return val
+    return None
+
+
 class Trainer:
     """Same surface as the reference `Trainer` (train/trainer.py:15-200): constructor arguments, the attributes
     `best_value / best_metrics / best_epoch / pointer_to_model / optimizer`, `fit()` and `val()`."""
 
     _OPTIMIZERS = {'adamw': True, 'adam': False, 'adagrad': None}  # name -> decoupled weight decay? (trainer.py:48-53)
+
+    def __new__(cls, model=None, train_loader=None, val_loader=None, rec_loss=None, conf=None):
+        fused = isinstance(model, SGDMatrixFactorization) and getattr(rec_loss, 'loss_kind', None) in _C.LOSS_KINDS
+        if cls is Trainer and not fused:
+            ref = _reference_trainer()
+            if ref is not None:   # not an instance of cls: Python then skips cls.__init__
+                logging.info(f'{type(model).__name__} / {type(rec_loss).__name__} is outside the fused MF path: '
+                             f'handing it to the reference Trainer')
+                return ref(model, train_loader, val_loader, rec_loss, conf)
+        return super().__new__(cls)
 
     def __init__(self, model: SGDMatrixFactorization, train_loader: data.DataLoader, val_loader: data.DataLoader,
                  rec_loss: RecommenderSystemLoss, conf: dict):

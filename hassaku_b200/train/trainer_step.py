@@ -53,7 +53,7 @@ class FusedMFTrainStep:
             slot, u, i = self._stage(u_idxs, i_idxs)
         _C.mf_train_fused(self.model._tables(), self.optimizer.grad_tables, u, i, self.kind, self.shift,
                           self.loss_accum if loss_out is None else loss_out, status=self.model._status())
-        if self.optimizer.mode == 'lazy':
+        if hasattr(self.optimizer, 'mark'):
             self.optimizer.mark(u, i)
         self.optimizer.step_fused()
         if slot is not None:

@@ -16,7 +16,9 @@
  *     d <= 1024
  *   - indices are int64 like the reference loaders emit (data/dataloader.py:126-129)
  *   - `status` (nullable) is a device int32 bit-field: bit 0 is set when a kernel met an out-of-range user or
- *     item index (the offending sample is skipped; the reference would raise from torch at that point)
+ *     item index (the offending sample is skipped; the reference would raise from torch at that point), bit 1 when a
+ *     fixed-capacity exchange buffer of the item-sharded step overflowed (hsk_route_items), bit 2 when
+ *     hsk_sample_negatives gave up on a row after its round cap (flagged slots were emitted)
  *   - the library is re-entrant and holds no mutable global state (nn.DataParallel calls forward from one
  *     Python thread per GPU, train/trainer.py:38-40); the current device of the calling thread is used
  */
@@ -40,8 +42,10 @@ typedef void* hsk_stream_t; /* cudaStream_t */
 
 enum { HSK_OK = 0, HSK_ERR_INVALID = -1, HSK_ERR_CUDA = -2, HSK_ERR_UNSUPPORTED = -3 };
 enum { HSK_LOSS_BPR = 0, HSK_LOSS_SAMPLED_SOFTMAX = 1, HSK_LOSS_BCE = 2 }; /* train/rec_losses.py:142-145 */
-enum { HSK_STATUS_BAD_INDEX = 1 };
+enum { HSK_STATUS_BAD_INDEX = 1, HSK_STATUS_CAPACITY = 2, HSK_STATUS_SAMPLER_ROUNDS = 4 };
 enum { HSK_PREC_FP32 = 0, HSK_PREC_TF32 = 1, HSK_PREC_BF16 = 2 }; /* evaluator scoring precision */
+/* kernel selection of hsk_mf_train_fused_v: every variant computes the same step (parity tests, A/B measurements) */
+enum { HSK_TRAIN_AUTO = 0, HSK_TRAIN_REGS = 1, HSK_TRAIN_RING = 2, HSK_TRAIN_QWARP = 3 };
 
 /* The embedding tables of one SGDMatrixFactorization (algorithms/sgd_alg.py:127-138).  Nullable: Ub, Ib, Gb. */
 typedef struct hsk_mf_tables {
@@ -99,12 +103,44 @@ HSK_API int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables* g,
                                  int B, int N1, int64_t B_global, int loss_kind, float neg_shift, double* loss_accum,
                                  float* scores_out, float* dscores_out, int32_t* status, hsk_stream_t stream);
 
+/* The same step with an explicit kernel choice: HSK_TRAIN_AUTO (what the two entry points above use: by shape, from the
+ * B200 measurements), HSK_TRAIN_REGS (warp-per-row register gather), HSK_TRAIN_RING (bulk-copy / TMA row ring, bpr and
+ * bce), HSK_TRAIN_QWARP (quarter-warp per sample, rows <= 128 floats).  A variant that does not support the shape falls
+ * back to AUTO's choice.  Results agree within fp32 summation order. */
+HSK_API int hsk_mf_train_fused_v(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx, const int64_t* i_idx,
+                                 int B, int N1, int64_t B_global, int loss_kind, float neg_shift, double* loss_accum,
+                                 float* scores_out, float* dscores_out, int32_t* status, int variant, hsk_stream_t stream);
+
 /* Row gather / scatter-add for the all-to-all exchanges of the item-sharded step: dst[r, :] = src[idx[r], :] and
  * dst[idx[r], :] += src[r, :] (128-bit vector reductions), rows of ld fp32 (ld % 4 == 0, 16-byte aligned). */
 HSK_API int hsk_gather_rows(const float* src, int ld, const int64_t* idx, int64_t n, int64_t n_src, float* dst,
                             int32_t* status, hsk_stream_t stream);
 HSK_API int hsk_scatter_add_rows(float* dst, int ld, const int64_t* idx, int64_t n, int64_t n_dst, const float* src,
                                  int32_t* status, hsk_stream_t stream);
+
+/* ---- device-side routing of the item-sharded step's SPARSE exchange: fixed shapes, no host sync, so the
+ * whole step — these kernels, the NCCL all-to-alls between them, hsk_mf_train_fused_n, hsk_adamw_dense_rows — is one
+ * CUDA graph.  World G: item i lives on rank i % G as local row i / G.
+ *   hsk_route_items   (requester) the DISTINCT item ids among i_idx [n] (global ids), grouped by owner and numbered in
+ *       ascending local-row order: req_rows [G, capq] int32 local rows wanted from each owner (-1 padded), req_count [G]
+ *       (clamped to capq; an overflow sets HSK_STATUS_CAPACITY and the overflowing ids get compact index -1, which the
+ *       train kernel reports as a bad index), compact_idx [n] int64 = q * block_rows + slot: the row of every batch slot in
+ *       the compact table [G * block_rows, ld] of fetched rows, block_rows = hsk_shard_block_rows(capq, ld).
+ *       No sort: presence flags over the owner-major id space + a 3-kernel exclusive scan (deterministic numbering).
+ *   hsk_shard_pack    (owner) rows [G, capq] (what the peers sent after the id all-to-all) -> out [G, block_rows, ld]:
+ *       block q = the requested rows of V, then from row capq on their item biases flat (Ib nullable).
+ *   hsk_shard_unpack_add (owner) in [G, block_rows, ld] = the peers' row / bias gradients in the same layout:
+ *       gV[row] += ..., gIb[row] += ..., stamps[row] = hsk_row_stamp(step) (nullable; for hsk_adamw_dense_rows). */
+HSK_API int64_t hsk_shard_block_rows(int capq, int ld);
+HSK_API int64_t hsk_route_scratch_bytes(int64_t n_items, int G);
+HSK_API int hsk_route_items(const int64_t* i_idx, int64_t n, int64_t n_items, int G, int capq, int ld, int32_t* req_rows,
+                            int32_t* req_count, int64_t* compact_idx, void* scratch, int64_t scratch_bytes,
+                            int32_t* status, hsk_stream_t stream);
+HSK_API int hsk_shard_pack(const float* V, const float* Ib /* nullable */, int ld, int64_t n_local, const int32_t* rows, int G,
+                           int capq, float* out, int32_t* status, hsk_stream_t stream);
+HSK_API int hsk_shard_unpack_add(const float* in, int ld, int64_t n_local, const int32_t* rows, int G, int capq, float* gV,
+                                 float* gIb /* nullable */, uint8_t* stamps /* nullable */, int64_t step,
+                                 const int64_t* step_dev /* nullable: overrides step */, int32_t* status, hsk_stream_t stream);
 
 /* Owner-sharded index arithmetic of the multi-GPU step (row i lives on rank i % world at local row i / world):
  * out[e] = (idx[e] % world) * rank_stride + idx[e] / world.  rank_stride = rows per rank of a rank-major replica
@@ -123,6 +159,34 @@ HSK_API int hsk_shard_local_index(const int64_t* idx, int64_t n, int world, int6
 HSK_API int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n, double lr, double beta1, double beta2,
                     double eps, double weight_decay, int64_t step, int arith, int adam_l2, int zero_grad,
                     hsk_stream_t stream);
+
+/* ---- the same dense update, skipping the gradient traffic of rows that received no gradient this step ---------------
+ * Identical results to hsk_adamw_dense (bit for bit: an untouched row's gradient IS zero), but for the rows of the given
+ * segments whose stamp byte differs from this step's stamp g is neither read nor re-zeroed: 24 B / element instead of
+ * 32 B.  Contract: g is all-zero outside the rows stamped this step — hsk_adamw_dense_rows leaves it so, and every
+ * caller that scatters gradients into rows calls hsk_mark_rows on their indices with the same step.  Everything
+ * outside the segments (bias vectors, padding) takes the plain dense path.  The stamp of step t is hsk_row_stamp(t) =
+ * 1 + t % 255: the stamp arrays are never cleared (start them at 0).
+ * Graph mode (both non-null): consts_dev = the 8 fp32 of hsk_adamw_consts for the step, step_dev = the 1-based step
+ * count in device memory (it selects the stamp), so that one captured launch serves every step; lr ... step are then
+ * ignored.  Only decoupled AdamW / Adam(L2) / plain Adam like hsk_adamw_dense; the gradient is always zeroed. */
+typedef struct hsk_row_segment {
+    int64_t offset;          /* first element of the segment inside p / m / v / g (multiple of 4) */
+    int64_t n_rows;
+    int32_t ld;              /* elements per row (multiple of 4) */
+    const uint8_t* stamps;   /* [n_rows] device bytes */
+} hsk_row_segment;
+HSK_API int hsk_row_stamp(int64_t step);
+HSK_API int hsk_mark_rows(const int64_t* idx, int64_t n, int64_t n_rows, uint8_t* stamps, int64_t step,
+                          const int64_t* step_dev /* nullable: overrides step */, hsk_stream_t stream);
+/* both tables of one training batch in one launch: stamps_users[u_idx[b]] = stamps_items[i_idx[b, j]] = stamp (nullable each) */
+HSK_API int hsk_mark_batch(const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t n_users, int64_t n_items,
+                           uint8_t* stamps_users, uint8_t* stamps_items, int64_t step, const int64_t* step_dev,
+                           hsk_stream_t stream);
+HSK_API int hsk_adamw_dense_rows(float* p, float* m, float* v, float* g, int64_t n, const hsk_row_segment* segments /* host */,
+                                 int n_segments /* <= 4 */, double lr, double beta1, double beta2, double eps,
+                                 double weight_decay, int64_t step, const float* consts_dev, const int64_t* step_dev,
+                                 int arith, int adam_l2, hsk_stream_t stream);
 
 /* ---- a10: uniform negative sampling on the device (data/dataloader.py:56-57, 92-129) -------------------------------
  * For every batch row b: i_idx[b, 0] = pos_idx[b] (if pos_idx != NULL) and i_idx[b, 1..N] = N items drawn uniformly
@@ -173,6 +237,17 @@ HSK_API int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int preci
                              int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                              int32_t* status, hsk_stream_t stream);
 
+/* ---- fp32 re-scoring of tensor-core candidates: TF32 / BF16 ranking, fp32 scores and order ------------------------------
+ * cand_ids [Be, n_cand] (n_cand <= 128; global item ids as hsk_eval_topk_tc returns them, < 0 = empty, exclusions already
+ * removed): every candidate is scored again from the fp32 tables `t` (score = <Uw[u_rows[r]], Vw[(id - id_offset) /
+ * id_stride]> (+ Ub[u_rows[r]]) (+ Ib) (+ Gb), eval/eval.py:247-248) and the k best are returned ordered like
+ * hsk_eval_topk (score descending, lower id first).  Call hsk_eval_topk_tc with k' = n_cand = min(128, k + 28), then
+ * this: the result differs from the fp32 evaluator only if a true top-k item fell below rank n_cand in the
+ * low-precision pass.  u_rows [Be] = rows of t->Uw / t->Ub (< t->n_users). */
+HSK_API int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,
+                             const int32_t* cand_ids, int n_cand, int k, float* top_scores, int32_t* top_ids,
+                             int32_t* status, hsk_stream_t stream);
+
 /* ---- merge of G per-shard top-k lists (item-sharded evaluation: all-gather, then this) --------------------------
  * scores/ids: [G, rows, k] (id < 0 = empty slot) -> out [rows, k], same ordering rule as hsk_eval_topk. */
 HSK_API int hsk_topk_merge(const float* scores, const int32_t* ids, int G, int rows, int k, float* out_scores,
@@ -214,10 +289,6 @@ HSK_API int hsk_mark_touched(const int64_t* u_idx, const int64_t* i_idx, int B, 
 HSK_API int hsk_adamw_rows_lazy(float* p, float* m, float* v, float* g, int64_t n_rows, int ld, float* p_bias, float* m_bias,
                                 float* v_bias, float* g_bias, uint8_t* touched, double lr, double beta1, double beta2,
                                 double eps, double weight_decay, int64_t step, hsk_stream_t stream);
-
-/* ---- measurement hook (scripts/kbench.py): if set to a device array of 16 uint64, hsk_eval_topk_tc adds the cycle counts
- * of its epilogue phases and list-cut sub-phases to it; NULL (default) disables the counters. */
-HSK_API void hsk_debug_eval_tc_profile(unsigned long long* dev_counters);
 
 /* ---- CUDA-graph friendly AdamW: the step-dependent scalars live in device memory --------------------------------------
  * hsk_adamw_consts fills 8 fp32 (HOST) for step `step`; the caller copies them to `consts_dev` (captured as a memcpy

@@ -137,7 +137,7 @@ SHAPES_Q = [
     (300, 200, 40, 33, 3, 'bpr', (True, True, True), 'q'),
     (300, 200, 7, 33, 3, 'bpr', (True, False, True), 'q'),
     (300, 200, 7, 5, 1, 'bce', (False, False, False), 'q'),
-    (5000, 3000, 128, 256, 50, 'bpr', (False, True, False), 'tma'),    # the warp-per-row kernels stay covered at d <= 128
+    (5000, 3000, 128, 256, 50, 'bpr', (False, True, False), 'ring'),    # the warp-per-row kernels stay covered at d <= 128
     (20000, 10677, 128, 512, 100, 'sampled_softmax', (False, True, False), 'regs'),
 ]
 
@@ -145,10 +145,8 @@ SHAPES_Q = [
 @pytest.mark.parametrize('U,I,d,B,N,kind,biases,variant', [s + (None,) for s in SHAPES] + SHAPES_Q)
 def test_fused_step_vs_oracle(U, I, d, B, N, kind, biases, variant, monkeypatch):
     """One full step (forward, loss, backward, AdamW) against the oracle on the same seeded batch."""
-    if variant:
-        monkeypatch.setenv('HSK_TRAIN_FUSED', variant)
-    else:
-        monkeypatch.delenv('HSK_TRAIN_FUSED', raising=False)
+    from hassaku_b200 import _C
+    monkeypatch.setattr(_C, 'TRAIN_VARIANT', variant or 'auto')
     from oracle import mf_oracle as O
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
     from hassaku_b200.train.optim import DenseAdam
