@@ -64,7 +64,7 @@ def _declare(lib):
         'hsk_mark_rows': (i32, [vp, i64, i64, vp, i64, vp, vp]),
         'hsk_mark_batch': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, i64, vp, vp]),
         'hsk_adamw_dense_rows': (i32, [vp, vp, vp, vp, i64, C.POINTER(RowSegment), i32, f64, f64, f64, f64, f64, i64, vp, vp, i32, i32, vp]),
-        'hsk_rescore_topk': (i32, [T, vp, i32, i64, i64, vp, i32, i32, vp, vp, vp, vp]),
+        'hsk_rescore_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, i32, vp, vp, vp, vp]),
         'hsk_shard_block_rows': (i64, [i32, i32]),
         'hsk_route_scratch_bytes': (i64, [i64, i32]),
         'hsk_route_items': (i32, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp]),
@@ -475,16 +475,22 @@ def eval_topk_tc(Uq, Vq, precision: int, u_idx, n_users: int, k: int, top_scores
 
 
 def rescore_topk(tables: MfTables, u_rows, cand_ids, k: int, top_scores, top_ids, id_offset: int = 0, id_stride: int = 1,
-                 status=None):
-    """fp32 re-scoring of tensor-core candidates: cand_ids int32 [Be, n_cand <= 128] -> exact top-k of the candidates."""
+                 status=None, cand_scores=None):
+    """fp32 re-scoring of tensor-core candidates: cand_ids int32 [Be, n_cand <= 128] -> exact top-k of the candidates;
+    cand_scores (the low-precision scores): -inf marks an excluded item, which stays -inf."""
     _req(u_rows, torch.int64, 'u_rows'); _req(cand_ids, torch.int32, 'cand_ids')
     _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
     Be, n_cand = cand_ids.shape
     if tuple(top_scores.shape) != (Be, k) or tuple(top_ids.shape) != (Be, k):
         raise HskError(f'rescore_topk: outputs must be [{Be}, {k}]')
-    with _on_device_of(u_rows, cand_ids, top_scores, top_ids, status) as st:
-        _check(lib().hsk_rescore_topk(C.byref(tables), u_rows.data_ptr(), Be, id_offset, id_stride, cand_ids.data_ptr(), n_cand,
-                                      k, top_scores.data_ptr(), top_ids.data_ptr(), _ptr(status), st), 'hsk_rescore_topk')
+    if cand_scores is not None:
+        _req(cand_scores, torch.float32, 'cand_scores')
+        if cand_scores.shape != cand_ids.shape:
+            raise HskError('rescore_topk: cand_scores must have the shape of cand_ids')
+    with _on_device_of(u_rows, cand_ids, cand_scores, top_scores, top_ids, status) as st:
+        _check(lib().hsk_rescore_topk(C.byref(tables), u_rows.data_ptr(), Be, id_offset, id_stride, cand_ids.data_ptr(),
+                                      _ptr(cand_scores), n_cand, k, top_scores.data_ptr(), top_ids.data_ptr(), _ptr(status),
+                                      st), 'hsk_rescore_topk')
 
 
 def topk_merge(scores, ids, out_scores, out_ids):

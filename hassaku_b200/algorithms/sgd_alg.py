@@ -29,32 +29,21 @@ class ArenaLayout:
     ALIGN = 32
 
     def __init__(self, n_users: int, n_items: int, d: int, use_user_bias: bool, use_item_bias: bool,
-                 use_global_bias: bool, item_block_rows: int = 0, item_bias_row: int = 0):
-        """`item_block_rows` > 0 (sharded step, in-place exchange): the item segment is a block of that many rows whose
-        rows [0, n_items) are the item embeddings and whose rows from `item_bias_row` on hold the item biases flat —
-        the block is then sent / received by the collectives as it lies in the arena (hassaku_b200/sharded.py)."""
+                 use_global_bias: bool):
         self.n_users, self.n_items, self.d = n_users, n_items, d
         self.ld = _align_up(d, 4)
         off = 0
         self.off_U = off
         off = _align_up(off + n_users * self.ld, self.ALIGN)
         self.off_V = off
-        self.item_block_rows, self.item_bias_row = item_block_rows, item_bias_row
-        if item_block_rows:
-            assert n_items <= item_bias_row and item_bias_row * self.ld + item_bias_row <= item_block_rows * self.ld
-            off = _align_up(off + item_block_rows * self.ld, self.ALIGN)
-        else:
-            off = _align_up(off + n_items * self.ld, self.ALIGN)
+        off = _align_up(off + n_items * self.ld, self.ALIGN)
         self.off_Ub = self.off_Ib = self.off_Gb = -1
         if use_user_bias:
             self.off_Ub = off
             off = _align_up(off + n_users, self.ALIGN)
         if use_item_bias:
-            if item_block_rows:
-                self.off_Ib = self.off_V + item_bias_row * self.ld
-            else:
-                self.off_Ib = off
-                off = _align_up(off + n_items, self.ALIGN)
+            self.off_Ib = off
+            off = _align_up(off + n_items, self.ALIGN)
         if use_global_bias:
             self.off_Gb = off
             off = _align_up(off + 1, self.ALIGN)
@@ -105,7 +94,8 @@ class SGDMatrixFactorization(SGDBasedRecommenderAlgorithm):
     the reference (algorithms/sgd_alg.py:110-184); `forward` runs the fused gather-score kernel."""
 
     def __init__(self, n_users: int, n_items: int, embedding_dim: int = 100, use_user_bias: bool = False,
-                 use_item_bias: bool = False, use_global_bias: bool = False):
+                 use_item_bias: bool = False, use_global_bias: bool = False, *, _device=None, _seed: int = 64,
+                 _std=None):
         super().__init__()
         self.n_users = n_users
         self.n_items = n_items
@@ -116,28 +106,48 @@ class SGDMatrixFactorization(SGDBasedRecommenderAlgorithm):
         if embedding_dim > 1024:
             raise ValueError('hassaku_b200 supports embedding_dim <= 1024')
 
-        # Same module construction + init order as the reference (sgd_alg.py:127-138, train/utils.py:11-13), so the
-        # same torch seed yields bit-identical initial weights.
-        self.user_embeddings = nn.Embedding(self.n_users, self.embedding_dim)
-        self.item_embeddings = nn.Embedding(self.n_items, self.embedding_dim)
-        if self.use_user_bias:
-            self.user_bias = nn.Embedding(self.n_users, 1)
-        if self.use_item_bias:
-            self.item_bias = nn.Embedding(self.n_items, 1)
-        self.apply(general_weight_init)
-        if self.use_global_bias:
-            self.global_bias = nn.Parameter(torch.zeros(1), requires_grad=True)
-
         self.layout = ArenaLayout(n_users, n_items, embedding_dim, use_user_bias, use_item_bias, use_global_bias)
-        arena = torch.zeros(self.layout.n_total, dtype=torch.float32)
-        Uw, Vw, Ub, Ib, Gb = self.layout.views(arena)
-        with torch.no_grad():
-            Uw.copy_(self.user_embeddings.weight)
-            Vw.copy_(self.item_embeddings.weight)
-            if Ub is not None:
-                Ub.copy_(self.user_bias.weight)
-            if Ib is not None:
-                Ib.copy_(self.item_bias.weight)
+        if _device is not None:
+            # large tables (cfg4: 385 M, cfg5: 2.8 G parameters): no host copy — the modules are created without storage
+            # and the arena is drawn directly on the device with the reference's distribution N(0, (0.1 / shape[-1])^2)
+            # (train/utils.py:11-13).  Same distribution, NOT the same bits as the host constructor (different generator).
+            with torch.device('meta'):
+                self.user_embeddings = nn.Embedding(self.n_users, self.embedding_dim)
+                self.item_embeddings = nn.Embedding(self.n_items, self.embedding_dim)
+                if self.use_user_bias:
+                    self.user_bias = nn.Embedding(self.n_users, 1)
+                if self.use_item_bias:
+                    self.item_bias = nn.Embedding(self.n_items, 1)
+                if self.use_global_bias:
+                    self.global_bias = nn.Parameter(torch.zeros(1), requires_grad=True)
+            arena = torch.zeros(self.layout.n_total, dtype=torch.float32, device=_device)
+            gen = torch.Generator(device=arena.device)
+            gen.manual_seed(int(_seed))
+            for j, view in enumerate(self.layout.views(arena)[:4]):     # Uw, Vw, Ub, Ib
+                if view is not None:
+                    std = 0.1 / view.shape[-1] if _std is None else _std[0 if j < 2 else 1]
+                    view.normal_(0., std, generator=gen)
+        else:
+            # Same module construction + init order as the reference (sgd_alg.py:127-138, train/utils.py:11-13), so the
+            # same torch seed yields bit-identical initial weights.
+            self.user_embeddings = nn.Embedding(self.n_users, self.embedding_dim)
+            self.item_embeddings = nn.Embedding(self.n_items, self.embedding_dim)
+            if self.use_user_bias:
+                self.user_bias = nn.Embedding(self.n_users, 1)
+            if self.use_item_bias:
+                self.item_bias = nn.Embedding(self.n_items, 1)
+            self.apply(general_weight_init)
+            if self.use_global_bias:
+                self.global_bias = nn.Parameter(torch.zeros(1), requires_grad=True)
+            arena = torch.zeros(self.layout.n_total, dtype=torch.float32)
+            Uw, Vw, Ub, Ib, Gb = self.layout.views(arena)
+            with torch.no_grad():
+                Uw.copy_(self.user_embeddings.weight)
+                Vw.copy_(self.item_embeddings.weight)
+                if Ub is not None:
+                    Ub.copy_(self.user_bias.weight)
+                if Ib is not None:
+                    Ib.copy_(self.item_bias.weight)
         self._status_flag = None
         self._set_arena(arena)
 
@@ -147,6 +157,15 @@ class SGDMatrixFactorization(SGDBasedRecommenderAlgorithm):
                      f'- use_user_bias: {self.use_user_bias} \n'
                      f'- use_item_bias: {self.use_item_bias} \n'
                      f'- use_global_bias: {self.use_global_bias}')
+
+    @classmethod
+    def on_device(cls, n_users: int, n_items: int, embedding_dim: int, use_user_bias: bool = False,
+                  use_item_bias: bool = False, use_global_bias: bool = False, device='cuda', seed: int = 64, std=None):
+        """The model with its arena allocated and initialised ON `device` (for tables too large to build on the host).
+        `std` = (embedding std, bias std) overrides the reference's 0.1 / shape[-1] (evaluation benchmarks use
+        (1 / sqrt(d), 0.05): with the training init every user's ranking would be the item-bias ranking)."""
+        return cls(n_users, n_items, embedding_dim, use_user_bias, use_item_bias, use_global_bias, _device=device, _seed=seed,
+                   _std=std)
 
     # ---- arena plumbing ----
     def _set_arena(self, arena: torch.Tensor):

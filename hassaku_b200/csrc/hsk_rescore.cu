@@ -24,6 +24,7 @@ struct RescoreArgs {
     const float* __restrict__ Gb;
     const int64_t* __restrict__ u_idx;    // row of Uw / Ub per batch entry
     const int32_t* __restrict__ cand;     // [Be, n_cand] global item ids, < 0 = empty
+    const float* __restrict__ cand_scores;   // [Be, n_cand] or null: -inf marks an EXCLUDED item (stays -inf)
     int64_t n_users, n_local, id_offset, id_stride;
     int Be, n_cand, k, ld, nvec;
     float* out_scores;
@@ -54,10 +55,14 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
     // lane l looks up candidate r * 32 + l: id -> local row (id = id_offset + local * id_stride)
     int64_t loc[kRescoreKPL];
     int32_t gid[kRescoreKPL];
+    bool masked[kRescoreKPL];
 #pragma unroll
     for (int r = 0; r < kRescoreKPL; ++r) {
         const int c = r * 32 + lane;
         gid[r] = (c < a.n_cand) ? cand[c] : -1;
+        // an item of the user's exclusion row that surfaced because fewer than n_cand admissible items exist: the
+        // low-precision pass reports it with score -inf, and -inf it stays (eval/eval.py:250-251)
+        masked[r] = a.cand_scores && c < a.n_cand && a.cand_scores[(int64_t)row * a.n_cand + c] == -INFINITY;
         loc[r] = -1;
         if (gid[r] >= 0) {
             const int64_t rel = (int64_t)gid[r] - a.id_offset;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
         }
         if (loc[r] >= 0) {
             if (a.Ib) sc += __ldg(a.Ib + loc[r]);
-            key[r] = make_key(sc, (uint32_t)gid[r]);
+            key[r] = make_key(masked[r] ? -INFINITY : sc, (uint32_t)gid[r]);
         }
     }
     warp_sort_desc<kRescoreKPL>(key, lane);
@@ -99,7 +104,8 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
     for (int r = 0; r < kRescoreKPL; ++r) {
         const int e = r * 32 + lane;
         if (e < a.k) {
-            os[e] = key[r] ? key_score(key[r]) + base : -INFINITY;
+            const float sc = key[r] ? key_score(key[r]) : -INFINITY;
+            os[e] = sc == -INFINITY ? sc : sc + base;
             oi[e] = key_id(key[r]);
         }
     }
@@ -110,8 +116,8 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
 using namespace hsk;
 
 extern "C" int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,
-                                const int32_t* cand_ids, int n_cand, int k, float* top_scores, int32_t* top_ids,
-                                int32_t* status, hsk_stream_t stream) {
+                                const int32_t* cand_ids, const float* cand_scores, int n_cand, int k, float* top_scores,
+                                int32_t* top_ids, int32_t* status, hsk_stream_t stream) {
     HSK_REQUIRE(t && t->Uw && t->Vw && u_rows && cand_ids && top_scores && top_ids, "hsk_rescore_topk: null pointer");
     HSK_REQUIRE(t->d >= 1 && t->ld >= t->d && t->ld % 4 == 0 && t->ld <= 1024, "hsk_rescore_topk: bad table shape");
     HSK_REQUIRE(aligned16(t->Uw) && aligned16(t->Vw), "hsk_rescore_topk: tables must be 16-byte aligned");
@@ -121,7 +127,7 @@ extern "C" int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, i
     RescoreArgs a;
     memset(&a, 0, sizeof(a));
     a.Uw = t->Uw; a.Vw = t->Vw; a.Ub = t->Ub; a.Ib = t->Ib; a.Gb = t->Gb;
-    a.u_idx = u_rows; a.cand = cand_ids;
+    a.u_idx = u_rows; a.cand = cand_ids; a.cand_scores = cand_scores;
     a.n_users = t->n_users; a.n_local = t->n_items; a.id_offset = id_offset; a.id_stride = id_stride;
     a.Be = Be; a.n_cand = n_cand; a.k = k; a.ld = t->ld; a.nvec = t->ld / 4;
     a.out_scores = top_scores; a.out_ids = top_ids; a.status = status;

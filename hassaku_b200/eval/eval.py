@@ -27,6 +27,15 @@ METRIC_ORDER = ('precision@{}', 'recall@{}', 'ndcg@{}')  # eval.py:78-80; column
 class DeviceCSR:
     """A scipy CSR matrix as (indptr int64, indices int32) device tensors with sorted rows."""
 
+    @classmethod
+    def from_tensors(cls, indptr: torch.Tensor, indices: torch.Tensor, shape):
+        """Adopt device tensors (int64 indptr [rows + 1], int32 indices sorted per row), e.g. of
+        hassaku_b200.data.synthetic.make_device_interactions."""
+        self = cls.__new__(cls)
+        assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and indptr.numel() == shape[0] + 1
+        self.shape, self.indptr, self.indices = tuple(shape), indptr.contiguous(), indices.contiguous()
+        return self
+
     def __init__(self, m, device):
         m = getattr(m, 'm', m)  # unwrap oracle/ref_shim CsrCompat-style adapters
         m = m.tocsr()
@@ -365,7 +374,7 @@ class TopKScorer:
                             Gb=alg.global_bias.detach() if alg.use_global_bias else None,
                             excl_indptr=ex_p, excl_indices=ex_i, status=alg._status())
             if self.rescore:
-                _C.rescore_topk(alg._tables(), u_idxs, ci, self.k, scores, ids, status=alg._status())
+                _C.rescore_topk(alg._tables(), u_idxs, ci, self.k, scores, ids, status=alg._status(), cand_scores=cs)
         return scores, ids
 
 
@@ -447,6 +456,29 @@ def factor_model_of(alg, device='cuda') -> Optional[SGDMatrixFactorization]:
     return None
 
 
+def evaluate_mf_sweep(alg: SGDMatrixFactorization, labels: DeviceCSR, exclude: Optional[DeviceCSR], evaluator: FullEvaluator,
+                      n_users: int, batch_size: int = 8192, verbose: bool = False, user_batches=None):
+    """The SGD branch of evaluate_recommender_algorithm (eval/eval.py:237-253) on device-resident CSR matrices: per user
+    batch one scoring + mask + top-k launch (TopKScorer; precision = `alg.eval_precision`, default fp32-exact) and one
+    metrics launch; the accumulators stay on the device (the caller reads them with evaluator.get_results()).
+    `user_batches` (optional): an iterable of int64 user-id tensors (host or device) instead of arange(n_users) in
+    batches — host tensors are copied to the device per batch, like the reference loader's u_idxs."""
+    dev = alg.arena.device
+    if alg.n_items < max(evaluator.K_VALUES):
+        raise RuntimeError('selected index k out of range')  # what torch.topk raises in the reference (eval.py:63)
+    scorer = TopKScorer(alg, min(batch_size, n_users), max(evaluator.K_VALUES), getattr(alg, 'eval_precision', 'fp32'))
+    if user_batches is None:
+        starts = range(0, n_users, batch_size)
+        user_batches = (torch.arange(s, min(s + batch_size, n_users), dtype=torch.int64, device=dev)
+                        for s in (tqdm(starts) if verbose else starts))
+    with torch.no_grad():
+        for u_idxs in user_batches:
+            u_idxs = u_idxs.to(dev, torch.int64, non_blocking=True)
+            _, ids = scorer(u_idxs, exclude)
+            evaluator.eval_batch_topk(u_idxs, ids, labels)
+    alg.check_status()
+
+
 def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evaluator: FullEvaluator, device='cpu',
                                    verbose=False):
     """Evaluation procedure that calls FullEvaluator on the dataset (eval/eval.py:211-258)."""
@@ -457,20 +489,10 @@ def evaluate_recommender_algorithm(alg: RecommenderAlgorithm, eval_loader, evalu
         if not alg.arena.is_cuda:  # the reference's run_test evaluates with device='cpu' (experiment_helper.py:116)
             alg.to('cuda')
         dev = alg.arena.device
-        if dataset.n_items < max(evaluator.K_VALUES):
-            raise RuntimeError('selected index k out of range')  # what torch.topk raises in the reference (eval.py:63)
         labels = device_csr(dataset, 'iteration_matrix', dev)
         exclude = device_csr(dataset, 'exclude_data', dev)
         bs = getattr(eval_loader, 'batch_size', None) or 8192
-        scorer = TopKScorer(alg, min(bs, dataset.n_users), max(evaluator.K_VALUES),
-                            getattr(alg, 'eval_precision', 'fp32'))
-        starts = range(0, dataset.n_users, bs)
-        with torch.no_grad():
-            for s in (tqdm(starts) if verbose else starts):
-                u_idxs = torch.arange(s, min(s + bs, dataset.n_users), dtype=torch.int64, device=dev)
-                _, ids = scorer(u_idxs, exclude)
-                evaluator.eval_batch_topk(u_idxs, ids, labels)
-        alg.check_status()
+        evaluate_mf_sweep(alg, labels, exclude, evaluator, dataset.n_users, bs, verbose=verbose)
     else:
         # generic algorithms (eval.py:224-236): `predict` runs where the algorithm lives — numpy / scipy models (KNN, SLIM,
         # EASE, pop) index host arrays with the loader's CPU tensors, torch models get tensors on their parameters'

@@ -243,10 +243,12 @@ HSK_API int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int preci
  * id_stride]> (+ Ub[u_rows[r]]) (+ Ib) (+ Gb), eval/eval.py:247-248) and the k best are returned ordered like
  * hsk_eval_topk (score descending, lower id first).  Call hsk_eval_topk_tc with k' = n_cand = min(128, k + 28), then
  * this: the result differs from the fp32 evaluator only if a true top-k item fell below rank n_cand in the
- * low-precision pass.  u_rows [Be] = rows of t->Uw / t->Ub (< t->n_users). */
+ * low-precision pass.  u_rows [Be] = rows of t->Uw / t->Ub (< t->n_users).  cand_scores (nullable, [Be, n_cand]: the
+ * low-precision scores): a candidate whose score is -inf is an item of the user's exclusion row that surfaced because
+ * fewer than n_cand admissible items exist; it keeps -inf (and so sorts after every admissible item). */
 HSK_API int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,
-                             const int32_t* cand_ids, int n_cand, int k, float* top_scores, int32_t* top_ids,
-                             int32_t* status, hsk_stream_t stream);
+                             const int32_t* cand_ids, const float* cand_scores /* nullable */, int n_cand, int k,
+                             float* top_scores, int32_t* top_ids, int32_t* status, hsk_stream_t stream);
 
 /* ---- merge of G per-shard top-k lists (item-sharded evaluation: all-gather, then this) --------------------------
  * scores/ids: [G, rows, k] (id < 0 = empty slot) -> out [rows, k], same ordering rule as hsk_eval_topk. */

@@ -1,7 +1,9 @@
 """GPU: tensor-core evaluator modes (tcgen05, TF32 / BF16) against the fp32-exact kernel.
 
 Tolerance (BASELINE.json north_star): in the TF32/BF16 tensor-core eval mode scores agree with fp32 within the stated
-tolerance below and the top-k recall overlap is >= 0.999."""
+tolerance below and the top-k recall overlap is >= 0.999.  The shipped mode (`rescore=True`, the default) ranks in low
+precision and re-scores its k + 28 best candidates in fp32 (hsk_rescore_topk): overlap >= 0.999 is gated on EVERY shape,
+scores to 1e-5.  The raw low-precision ranking (`rescore=False`) is checked against the operand-rounding bound."""
 import math
 
 import numpy as np
@@ -35,6 +37,7 @@ def _excl(U, I, per_user, seed=1):
     return m
 
 
+@pytest.mark.parametrize('rescore', [True, False])
 @pytest.mark.parametrize('prec', ['bf16', 'tf32'])
 @pytest.mark.parametrize('U,I,d,B', [
     (2000, 5000, 128, 512),      # cfg4 d
@@ -42,7 +45,7 @@ def _excl(U, I, per_user, seed=1):
     (6040, 3706, 402, 1024),     # cfg2 shape (bf16 only: tf32 supports d <= 256)
     (300, 129, 16, 300),         # tiny, partial tiles
 ])
-def test_tc_topk_vs_fp32_exact(prec, U, I, d, B):
+def test_tc_topk_vs_fp32_exact(prec, U, I, d, B, rescore):
     from hassaku_b200 import _C
     from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
     if prec == 'tf32' and d > 256:
@@ -56,18 +59,28 @@ def test_tc_topk_vs_fp32_exact(prec, U, I, d, B):
     k = 100
     s_ref, i_ref = TopKScorer(model, B, k, 'fp32')(users, ex)
     s_ref, i_ref = s_ref.clone(), i_ref.clone()
-    s_tc, i_tc = TopKScorer(model, B, k, prec)(users, ex)
+    s_tc, i_tc = TopKScorer(model, B, k, prec, rescore=rescore)(users, ex)
     torch.cuda.synchronize()
     model.check_status()
     i_ref_np, i_tc_np = i_ref.cpu().numpy(), i_tc.cpu().numpy()
     overlap = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(i_ref_np, i_tc_np)])
-    assert overlap >= 0.999 or (prec == 'bf16' and overlap >= 0.97), overlap  # see score-noise check below
+    if rescore:     # the shipped mode: north_star's gate, on every shape
+        assert overlap >= 0.999, overlap
+        # ... and wherever the fp32 scores are not tied the ids are the fp32 evaluator's ids in the same order
+        fin = torch.isfinite(s_ref)
+        gap = (s_ref[:, :-1] - s_ref[:, 1:]).abs() > 1e-5 * s_ref[fin].abs().max()    # (-inf) - (-inf) = nan -> False
+        clear = fin.clone()
+        clear[:, :-1] &= gap; clear[:, 1:] &= gap; clear[:, -1] = False     # the k-th boundary may swap with rank k + 1
+        assert int(clear.sum()) > 0 and float((i_tc == i_ref)[clear].float().mean()) >= 0.9999
+        assert torch.equal(torch.isfinite(s_tc), fin)                      # the same number of admissible items per user
+    else:           # raw low-precision ranking: bounded by the score noise, checked below
+        assert overlap >= 0.999 or (prec == 'bf16' and overlap >= 0.97), overlap
     # scores of the returned items agree with the exact fp32 scores of the same items
     full = model(users.repeat_interleave(1), torch.arange(I, device='cuda').repeat(B, 1)).detach()
     got = torch.gather(full, 1, i_tc.long().clamp_min(0))
     finite = torch.isfinite(s_tc)
     scale = float(full[torch.isfinite(full)].abs().max())
-    assert float((s_tc[finite] - got[finite]).abs().max()) <= TOL[prec] * scale
+    assert float((s_tc[finite] - got[finite]).abs().max()) <= (1e-5 if rescore else TOL[prec]) * scale
     # every id the tensor-core mode returns that the exact mode does not is a near-tie of the exact k-th score
     kth = s_ref[:, -1:]
     miss = (got < kth - 2 * TOL[prec] * scale) & finite
@@ -80,7 +93,8 @@ def test_tc_topk_vs_fp32_exact(prec, U, I, d, B):
 
 
 def test_tc_recall_overlap_with_separated_scores():
-    """With O(1) score gaps (trained-model regime) the ranked ids of the bf16 / tf32 modes match fp32 to >= 0.999."""
+    """With O(1) score gaps (trained-model regime) the ranked ids of the bf16 / tf32 modes match fp32 to >= 0.999
+    (re-scored, the default) and the raw low-precision ranking to >= 0.999 (tf32) / 0.99 (bf16)."""
     from hassaku_b200.eval.eval import TopKScorer
     U, I, d, B, k = 512, 8000, 128, 512, 100
     model = _model(U, I, d, biases=(False, True, False), scale=0.5)
@@ -88,9 +102,10 @@ def test_tc_recall_overlap_with_separated_scores():
     _, i_ref = TopKScorer(model, B, k, 'fp32')(users, None)
     i_ref = i_ref.clone()
     for prec in ('tf32', 'bf16'):
-        _, i_tc = TopKScorer(model, B, k, prec)(users, None)
-        ov = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(i_ref.cpu().numpy(), i_tc.cpu().numpy())])
-        assert ov >= (0.999 if prec == 'tf32' else 0.99), (prec, ov)
+        for rescore in (True, False):
+            _, i_tc = TopKScorer(model, B, k, prec, rescore=rescore)(users, None)
+            ov = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(i_ref.cpu().numpy(), i_tc.cpu().numpy())])
+            assert ov >= (0.999 if (rescore or prec == 'tf32') else 0.99), (prec, rescore, ov)
 
 
 def test_evaluate_with_tc_precision_metrics_close_to_fp32():
@@ -108,6 +123,6 @@ def test_evaluate_with_tc_precision_metrics_close_to_fp32():
     for prec in ('fp32', 'tf32', 'bf16'):
         model.eval_precision = prec
         res[prec] = evaluate_recommender_algorithm(model, L, FullEvaluator(True, 2, ds.user_to_user_group), 'cuda')
-    for prec, tol in (('tf32', 2e-3), ('bf16', 1e-2)):
+    for prec, tol in (('tf32', 1e-4), ('bf16', 1e-4)):     # re-scored modes: the fp32 metrics up to tie flips
         for key, v in res['fp32'].items():
             assert abs(res[prec][key] - v) <= tol, (prec, key, res[prec][key], v)

@@ -126,7 +126,9 @@ def test_calibration_decorator_over_device_evaluator_vs_reference_fixture(aggr):
             assert np.isclose(res[k], v, rtol=1e-5, atol=1e-7, equal_nan=True), (k, res[k], v)
     else:
         for k in g['peruser/names']:
-            assert np.allclose(res[k], g[f'peruser/{k}'], rtol=1e-5, atol=1e-7, equal_nan=True), k
+            # atol: the Jensen-Shannon / KL values of near-identical distributions are differences of logs (cancellation):
+            # the GPU's logf and the fixture's CPU logf agree to ~1e-6 absolute there (measured 2.2e-6 at a value of 2.7e-3)
+            assert np.allclose(res[k], g[f'peruser/{k}'], rtol=1e-5, atol=5e-6, equal_nan=True), k
 
 
 def test_shard_local_index_matches_formula():

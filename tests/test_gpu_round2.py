@@ -1,0 +1,327 @@
+"""GPU (1 device): the kernels added in round 2 against torch / oracle restatements —
+  hsk_adamw_dense_rows + hsk_mark_batch   bitwise equal to hsk_adamw_dense (hence to torch.optim.AdamW on CUDA)
+  hsk_rescore_topk                        fp32 re-scoring of tensor-core candidates vs a CPU fp32 matmul
+  hsk_route_items / hsk_shard_pack / hsk_shard_unpack_add   vs their torch contracts (tests/test_sharded_gloo.py)
+  ShardedMF at world 1                    the whole sparse / dense / graph-captured step vs the single-GPU step
+  cfg5-shaped tensor-core evaluation      64 users x 1 M items x 256 against a CPU fp32 oracle
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('U,I,d,B,N,flags', [
+    (5000, 3000, 128, 64, 5, (False, True, False)),      # sparse batch: both tables stamped
+    (5000, 3000, 402, 64, 5, (True, True, True)),        # ld 404 (101 float4 per row): rows straddle thread blocks
+    (300, 200, 7, 512, 50, (False, True, False)),        # batch covers the tables: plain dense pass is chosen
+])
+def test_row_stamped_adamw_is_bitwise_the_dense_adamw(U, I, d, B, N, flags):
+    """Two copies of one model take the same 6 steps on the SAME gradient (the fused kernel's vector reductions are not
+    bitwise reproducible run to run, so the gradient arena of the first copy is copied to the second); one optimizer skips
+    the gradient traffic of untouched rows (hsk_adamw_dense_rows), the other streams everything (hsk_adamw_dense): p, m,
+    v must be bit-identical and the gradient arena all-zero after every step."""
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.train.optim import DenseAdam
+    torch.manual_seed(0)
+    a = SGDMatrixFactorization(U, I, d, *flags)
+    b = SGDMatrixFactorization(U, I, d, *flags)
+    b.load_state_dict(a.state_dict())
+    a.to('cuda'); b.to('cuda')
+    oa = DenseAdam(a, lr=1e-2, weight_decay=1e-3)
+    ob = DenseAdam(b, lr=1e-2, weight_decay=1e-3)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(1)
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    used_rows_kernel = False
+    for s in range(6):
+        u = torch.randint(0, U, (B,), device='cuda', generator=gen)
+        i = torch.randint(0, I, (B, N + 1), device='cuda', generator=gen)
+        _C.mf_train_fused(a._tables(), oa.grad_tables, u, i, 0, 0.0, acc)
+        ob.g.copy_(oa.g)
+        oa.mark(u, i)
+        used_rows_kernel |= len(oa._segments) > 0
+        oa.step_fused()
+        ob.step_fused()
+        assert torch.equal(a.arena, b.arena) and torch.equal(oa.m, ob.m) and torch.equal(oa.v, ob.v), s
+        assert float(oa.g.abs().max()) == 0.0 and float(ob.g.abs().max()) == 0.0
+    assert used_rows_kernel == (B * (N + 1) <= I or 4 * B <= U)
+    # stamps wrap after 255 steps without losing gradients: jump the step counter across the wrap
+    if used_rows_kernel:
+        for t0 in (254, 509):
+            oa.t = ob.t = t0
+            for s in range(3):
+                u = torch.randint(0, U, (B,), device='cuda', generator=gen)
+                i = torch.randint(0, I, (B, N + 1), device='cuda', generator=gen)
+                _C.mf_train_fused(a._tables(), oa.grad_tables, u, i, 0, 0.0, acc)
+                ob.g.copy_(oa.g)
+                oa.mark(u, i)
+                oa.step_fused()
+                ob.step_fused()
+                assert torch.equal(a.arena, b.arena) and float(oa.g.abs().max()) == 0.0
+
+
+def test_rescore_topk_against_cpu_fp32():
+    from hassaku_b200 import _C
+    U, I, d, Be, n_cand, k, G, r = 300, 5000, 200, 77, 128, 100, 3, 1
+    gen = torch.Generator().manual_seed(0)
+    Uw = torch.randn((U, d), generator=gen) / math.sqrt(d)
+    Vfull = torch.randn((I, d), generator=gen) / math.sqrt(d)
+    Ibfull = torch.randn(I, generator=gen) * 0.1
+    Ub = torch.randn(U, generator=gen) * 0.1
+    Gb = torch.tensor([0.3])
+    Vloc, Ibloc = Vfull[r::G].contiguous(), Ibfull[r::G].contiguous()      # shard r of G: global id = r + local * G
+    users = torch.randperm(U, generator=gen)[:Be]
+    n_loc = Vloc.shape[0]
+    cand = torch.stack([torch.randperm(n_loc, generator=gen)[:n_cand] * G + r for _ in range(Be)]).to(torch.int32)
+    cand[3, 100:] = -1                       # short list
+    cand[5, :] = -1                          # empty list
+    t = _C.make_tables(Uw.cuda(), Vloc.cuda(), Ub.cuda(), Ibloc.cuda(), Gb.cuda(), d)
+    keep = (Uw.cuda(), Vloc.cuda(), Ub.cuda(), Ibloc.cuda(), Gb.cuda())
+    t = _C.make_tables(keep[0], keep[1], keep[2], keep[3], keep[4], d)
+    s = torch.empty((Be, k), device='cuda'); ids = torch.empty((Be, k), dtype=torch.int32, device='cuda')
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    _C.rescore_topk(t, users.cuda(), cand.cuda(), k, s, ids, id_offset=r, id_stride=G, status=st)
+    assert int(st.item()) == 0
+    s, ids = s.cpu(), ids.cpu()
+    for b in range(Be):
+        c = cand[b][cand[b] >= 0].long()
+        sc = (Vfull[c].double() @ Uw[users[b]].double()) + Ub[users[b]].double() + Ibfull[c].double() + 0.3
+        order = np.lexsort((c.numpy(), -sc.numpy()))[:k]
+        n = len(order)
+        assert ids[b, :n].tolist() == c[order].tolist(), b
+        assert n == 0 or rel_err(s[b, :n].numpy(), sc[order].numpy()) < 1e-5
+        assert (ids[b, n:] == -1).all() and torch.isinf(s[b, n:]).all()
+    # an id that is not of this shard is reported, not dereferenced
+    bad = cand.clone(); bad[0, 0] = r + 1
+    _C.rescore_topk(t, users.cuda(), bad.cuda(), k, torch.empty((Be, k), device='cuda'),
+                    torch.empty((Be, k), dtype=torch.int32, device='cuda'), id_offset=r, id_stride=G, status=st)
+    assert int(st.item()) & _C.STATUS_BAD_INDEX
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _route_ref(i_global, n_items, G, capq, ld):
+    br = capq + math.ceil(capq / ld)
+    flat = i_global.reshape(-1).cpu()
+    req = torch.full((G, capq), -1, dtype=torch.int32)
+    cnt = torch.zeros(G, dtype=torch.int32)
+    out = torch.full_like(flat, -1)
+    for q in range(G):
+        sel = (flat % G) == q
+        ids_all = torch.unique(flat[sel], sorted=True)
+        ids = ids_all[:capq]
+        req[q, :len(ids)] = (ids // G).to(torch.int32)
+        cnt[q] = len(ids)
+        if len(ids):
+            pos = torch.searchsorted(ids, flat[sel])
+            ok = (pos < len(ids)) & (ids[pos.clamp(max=len(ids) - 1)] == flat[sel])
+            out[sel] = torch.where(ok, q * br + pos, torch.full_like(pos, -1))
+    return req, cnt, out.view(i_global.shape)
+
+
+@pytest.mark.parametrize('n_items,G,B,N1,capq', [
+    (1_000_003, 8, 8192, 51, None),       # cfg4-like, ragged shards
+    (1_000_003, 1, 4096, 51, None),
+    (3706, 2, 8192, 51, None),            # every item requested
+    (41, 3, 24, 6, None),
+    (100_000, 4, 2048, 51, 5000),         # capacity overflow: flagged, overflowing ids -> -1
+])
+def test_route_items_matches_the_torch_contract(n_items, G, B, N1, capq):
+    from hassaku_b200 import _C
+    from hassaku_b200.sharded import exchange_capacity
+    ld = 128
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    i = torch.randint(0, n_items, (B, N1), device='cuda', generator=gen)
+    i[:, 2] = i[:, 1]
+    cq = capq or exchange_capacity(B * N1, n_items, G)
+    req = torch.zeros((G, cq), dtype=torch.int32, device='cuda')
+    cnt = torch.zeros(G, dtype=torch.int32, device='cuda')
+    comp = torch.empty_like(i)
+    scr = torch.empty(_C.route_scratch_bytes(n_items, G), dtype=torch.uint8, device='cuda')
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    for _ in range(2):      # twice: the scratch is reused without clearing by the caller
+        _C.route_items(i, n_items, G, cq, ld, req, cnt, comp, scr, st)
+    w_req, w_cnt, w_comp = _route_ref(i, n_items, G, cq, ld)
+    assert torch.equal(req.cpu(), w_req) and torch.equal(cnt.cpu(), w_cnt) and torch.equal(comp.cpu(), w_comp)
+    overflow = capq is not None
+    assert bool(int(st.item()) & _C.STATUS_CAPACITY) == overflow
+    assert bool((comp < 0).any()) == overflow
+    # a bad index is reported and maps to -1
+    i2 = i.clone(); i2[0, 0] = n_items + 3
+    st.zero_()
+    _C.route_items(i2, n_items, G, cq, ld, req, cnt, comp, scr, st)
+    assert int(st.item()) & _C.STATUS_BAD_INDEX and int(comp[0, 0]) == -1
+
+
+def test_shard_pack_and_unpack_add_match_the_torch_contract():
+    from hassaku_b200 import _C
+    G, capq, ld, n_local = 3, 37, 8, 50
+    br = _C.shard_block_rows(capq, ld)
+    assert br == capq + math.ceil(capq / ld)
+    gen = torch.Generator().manual_seed(0)
+    V = torch.randn((n_local, ld), generator=gen)
+    Ib = torch.randn(n_local, generator=gen)
+    rows = torch.full((G, capq), -1, dtype=torch.int32)
+    for q in range(G):
+        n = [37, 10, 0][q]
+        rows[q, :n] = torch.sort(torch.randperm(n_local, generator=gen)[:n]).values.to(torch.int32)
+    out = torch.zeros((G, br, ld), device='cuda')
+    _C.shard_pack(V.cuda(), Ib.cuda(), rows.cuda(), G, capq, out)
+    want = torch.zeros((G, br, ld))
+    for q in range(G):
+        for k in range(capq):
+            r = int(rows[q, k])
+            if r >= 0:
+                want[q, k] = V[r]
+                want[q].view(-1)[capq * ld + k] = Ib[r]
+    assert torch.equal(out.cpu(), want)
+    # the way back: gradients of the same layout are ADDED (two peers may hold the same row), rows stamped
+    inp = torch.randn((G, br, ld), generator=gen)
+    gV = torch.randn((n_local, ld), generator=gen)
+    gIb = torch.randn(n_local, generator=gen)
+    stamps = torch.zeros(n_local, dtype=torch.uint8)
+    gV_d, gIb_d, st_d = gV.cuda(), gIb.cuda(), stamps.cuda()
+    step = 700
+    _C.shard_unpack_add(inp.cuda(), rows.cuda(), G, capq, gV_d, gIb_d, st_d, step=step)
+    wV, wIb, wst = gV.clone().double(), gIb.clone().double(), stamps.clone()
+    for q in range(G):
+        for k in range(capq):
+            r = int(rows[q, k])
+            if r >= 0:
+                wV[r] += inp[q, k].double()
+                wIb[r] += inp[q].view(-1)[capq * ld + k].double()
+                wst[r] = _C.row_stamp(step)
+    assert rel_err(gV_d.cpu().numpy(), wV.numpy()) < 1e-6 and rel_err(gIb_d.cpu().numpy(), wIb.numpy()) < 1e-6
+    assert torch.equal(st_d.cpu(), wst) and _C.row_stamp(step) == 1 + step % 255
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('exchange', ['sparse', 'sparse_graph', 'dense', 'dense_graph'])
+@pytest.mark.parametrize('kind,flags', [('bpr', (False, True, False)), ('sampled_softmax', (True, True, False)),
+                                        ('bce', (True, True, True))])
+def test_sharded_step_at_world_1_equals_the_single_gpu_step(exchange, kind, flags):
+    """ShardedMF with world 1 (no process group: every exchange is the identity) runs the complete routed pipeline —
+    hsk_route_items, pack, compact table, fused kernel with global normalisers, unpack-add, row-stamped AdamW, eager and
+    as a captured CUDA graph — and must reproduce FusedMFTrainStep on the same batches.  (No global bias under sampled
+    softmax: its gradient sum_j (softmax_j - [j = 0]) is mathematically zero, so Adam normalises pure rounding noise.)"""
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.sharded import ShardedMF
+    from hassaku_b200.train.optim import DenseAdam
+    from hassaku_b200.train.rec_losses import RecommenderSystemLossesEnum
+    from hassaku_b200.train.trainer_step import FusedMFTrainStep
+    U, I, d, B, N = 3001, 20011, 128, 256, 20
+    torch.manual_seed(3)
+    single = SGDMatrixFactorization(U, I, d, *flags)
+    with torch.no_grad():
+        for p in single.parameters():
+            p.copy_(torch.randn_like(p) * (1 / math.sqrt(d) if p.shape[-1] == d else 0.1))
+    sd0 = {k_: v.clone() for k_, v in single.state_dict().items()}
+    single.to('cuda')
+    lr, wd = 1e-3, 1e-4
+
+    class _DS:
+        n_items = I
+
+    loss_fn = RecommenderSystemLossesEnum[kind].value.build_from_conf({'train_neg_strategy': 'uniform', 'neg_train': N}, _DS())
+    opt = DenseAdam(single, lr=lr, weight_decay=wd)
+    step = FusedMFTrainStep(single, loss_fn, opt)
+    smf = ShardedMF(U, I, d, *flags, world=1, rank=0, device='cuda')
+    smf.load_full_state_dict(sd0)
+    shift = float(loss_fn.neg_shift())
+    rng = np.random.RandomState(9)
+    try:
+        for s in range(5):
+            u = torch.from_numpy(rng.randint(0, U, B).astype(np.int64)).cuda()
+            i = torch.from_numpy(rng.randint(0, I, (B, N + 1)).astype(np.int64)).cuda()
+            i[:, 2] = i[:, 1]
+            step(u, i)
+            smf.step(u, i, B, kind, shift, lr, wd, exchange=exchange)
+            l_single, l_sh = step.pop_loss_sum(), smf.pop_loss()
+            assert abs(l_single - l_sh) <= 1e-5 * abs(l_single), (s, l_single, l_sh)
+        smf.check_status()
+        sd = smf.full_state_dict()
+        for n, p in single.state_dict().items():
+            err = rel_err(sd[n].numpy(), p.detach().cpu().numpy())
+            assert err < 1e-5 + 2e-3 * lr, (n, err)
+        assert float(smf.g.abs().max()) == 0.0
+    finally:
+        smf.close()
+
+
+def test_sharded_evaluate_at_world_1_equals_the_single_gpu_sweep():
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.data.synthetic import make_interactions
+    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+    from hassaku_b200.sharded import ShardedMF
+    U, I, d = 1201, 4007, 64
+    torch.manual_seed(5)
+    single = SGDMatrixFactorization(U, I, d, True, True, True)
+    with torch.no_grad():
+        for p in single.parameters():
+            p.copy_(torch.randn_like(p) * (0.4 if p.shape[-1] == d else 0.1))
+    sd0 = {k_: v.clone() for k_, v in single.state_dict().items()}
+    single.to('cuda')
+    data = make_interactions(U, I, 40000, seed=2, n_user_groups=2)
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+
+    class L:
+        dataset, batch_size = ds, 256
+
+    smf = ShardedMF(U, I, d, True, True, True, world=1, rank=0, device='cuda')
+    smf.load_full_state_dict(sd0)
+    for prec in ('fp32', 'bf16', 'tf32'):
+        single.eval_precision = prec
+        ref = evaluate_recommender_algorithm(single, L, FullEvaluator(True, 2, ds.user_to_user_group), 'cuda')
+        got = smf.evaluate(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=200, precision=prec)
+        assert sorted(got) == sorted(ref)
+        for k_, v in ref.items():
+            assert abs(got[k_] - v) <= 1e-9, (prec, k_, got[k_], v)
+    smf.check_status()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+def test_tensor_core_evaluator_at_cfg5_shape_against_a_cpu_fp32_oracle(prec):
+    """64 users x 1 M items x d 256 (the cfg5 item table), 80 exclusions per user, top-100: the ids of the tensor-core
+    mode (with fp32 re-scoring) against a CPU fp32 matmul + mask + sort — the oracle's A.7 on this slice."""
+    from scipy import sparse as sp
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
+    U, I, d, k = 64, 1_000_000, 256, 100
+    torch.manual_seed(11)
+    m = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+    with torch.no_grad():
+        m.user_embeddings.weight.copy_(torch.randn(U, d) / math.sqrt(d))
+        m.item_embeddings.weight.copy_(torch.randn(I, d) / math.sqrt(d) * 2.0)
+        m.item_bias.weight.copy_(torch.randn(I, 1) * 0.05)
+    Uw, Vw, Ib = m.user_embeddings.weight.detach().clone(), m.item_embeddings.weight.detach().clone(), m.item_bias.weight.detach().clone()
+    rng = np.random.RandomState(0)
+    rows = np.repeat(np.arange(U), 80)
+    ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+    ex.sum_duplicates(); ex.sort_indices()
+    # CPU oracle: fp32 scores (eval.py:247-248), -inf on exclusions (:250-251), top-k with (score desc, id asc)
+    scores = (Uw @ Vw.t()) + Ib.view(1, -1)
+    scores[torch.from_numpy(ex.tocoo().row.astype(np.int64)), torch.from_numpy(ex.tocoo().col.astype(np.int64))] = -torch.inf
+    top_s, top_i = torch.topk(scores, k + 1, dim=1)
+    m.to('cuda')
+    s_tc, i_tc = TopKScorer(m, U, k, prec)(torch.arange(U, device='cuda'), DeviceCSR(ex, 'cuda'))
+    m.check_status()
+    s_tc, i_tc = s_tc.cpu(), i_tc.cpu().long()
+    overlap = np.mean([len(np.intersect1d(a, b)) / k for a, b in zip(top_i[:, :k].numpy(), i_tc.numpy())])
+    assert overlap >= 0.999, overlap
+    assert rel_err(s_tc.numpy(), top_s[:, :k].numpy()) < 1e-5
+    # ids identical wherever neighbouring fp32 scores are separated by more than the summation-order noise
+    gap = (top_s[:, :-1] - top_s[:, 1:]) > 1e-5 * float(top_s.abs().max())
+    clear = gap[:, :k].clone()
+    clear[:, 1:] &= gap[:, :k - 1]
+    assert bool((i_tc == top_i[:, :k])[clear].all())

@@ -16,16 +16,50 @@ from hsk_testutil import ROOT  # noqa: F401
 
 
 class TorchRefOps:
-    """Test-only stand-in for hassaku_b200.sharded.CudaOps."""
-
-    def gather_rows(self, table2d, idx):
-        return table2d[idx].contiguous()
+    """Test-only stand-in for hassaku_b200.sharded.CudaOps: torch restatements of the routing kernels' contracts
+    (include/hassaku_b200.h: hsk_route_items, hsk_shard_pack, hsk_shard_unpack_add, hsk_mark_rows) and of the arithmetic."""
 
     def local_index(self, idx, world, rank_stride):
         return (idx % world) * rank_stride + torch.div(idx, world, rounding_mode='floor')
 
-    def scatter_add_rows(self, table2d, idx, rows):
-        table2d.index_add_(0, idx, rows)
+    def route(self, i_global, n_items, world, capq, ld, req_rows, req_count, compact_idx, scratch):
+        br = capq + math.ceil(capq / ld)
+        flat = i_global.reshape(-1)
+        out = torch.full_like(flat, -1)
+        req_rows.fill_(-1)
+        for q in range(world):
+            sel = (flat % world) == q
+            ids = torch.unique(flat[sel], sorted=True)[:capq]          # ascending local rows
+            req_rows[q, :len(ids)] = torch.div(ids, world, rounding_mode='floor').to(torch.int32)
+            req_count[q] = len(ids)
+            pos = torch.searchsorted(ids, flat[sel])
+            ok = (pos < len(ids)) & (ids[pos.clamp(max=max(len(ids) - 1, 0))] == flat[sel]) if len(ids) else torch.zeros_like(pos, dtype=torch.bool)
+            out[sel] = torch.where(ok, q * br + pos, torch.full_like(pos, -1))
+        compact_idx.copy_(out.view_as(compact_idx))
+
+    def pack(self, V2d, Ib, rows, world, capq, out):
+        ld = V2d.shape[1]
+        for q in range(world):
+            for k in range(capq):
+                r = int(rows[q, k])
+                if r >= 0:
+                    out[q, k] = V2d[r]
+                    if Ib is not None:
+                        out[q].view(-1)[capq * ld + k] = Ib[r]
+
+    def unpack_add(self, inp, rows, world, capq, gV2d, gIb, stamps, step, step_dev):
+        ld = gV2d.shape[1]
+        for q in range(world):
+            for k in range(capq):
+                r = int(rows[q, k])
+                if r >= 0:
+                    gV2d[r] += inp[q, k]
+                    if gIb is not None:
+                        gIb[r] += inp[q].view(-1)[capq * ld + k]
+                    stamps[r] = 1 + step % 255
+
+    def mark_rows(self, idx, n_rows, stamps, step, step_dev):
+        stamps[idx] = 1 + step % 255
 
     def train_fused(self, lay, arena, g_arena, Vc, Ibc, gVc, gIbc, u_local, compact_idx, B_global, kind, shift, loss_accum):
         Uw, _, Ub, _, Gb = lay.views(arena)
@@ -65,7 +99,11 @@ class TorchRefOps:
             gGb += leaves['Gb'].grad
         loss_accum += loss.detach()
 
-    def adamw(self, arena, m, v, g, lr, wd, t, decoupled=True):
+    def adamw(self, arena, m, v, g, segments, lr, wd, t, decoupled=True, consts_dev=None, step_dev=None):
+        # contract of hsk_adamw_dense_rows: the gradient is zero outside the rows stamped this step
+        for off, rows, ld, stamps in segments:
+            untouched = stamps[:rows] != 1 + t % 255
+            assert float(g[off:off + rows * ld].view(rows, ld)[untouched].abs().sum()) == 0.0
         b1, b2, eps = 0.9, 0.999, 1e-8
         grad = g if decoupled else g + wd * arena
         if decoupled:
@@ -82,7 +120,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse', inplace=False):
+def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse', capq=None):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
@@ -96,8 +134,7 @@ def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse', inplace=
             for p in ref.parameters():
                 p.copy_(torch.randn_like(p) * 0.3)
         lr, wd = 1e-2, 1e-3
-        smf = ShardedMF(U, I, d, *flags, world=world, rank=rank, device='cpu', ops=TorchRefOps(), inplace_exchange=inplace)
-        assert smf.inplace_exchange == inplace
+        smf = ShardedMF(U, I, d, *flags, world=world, rank=rank, device='cpu', ops=TorchRefOps())
         smf.load_full_state_dict(ref.state_dict())
         tr = O.OracleTrainer(ref, kind, lr, wd, 'adamw', neg_train=N)
         rng = np.random.RandomState(3)
@@ -111,7 +148,7 @@ def _worker(rank, world, port, kind, flags, out_dir, exchange='sparse', inplace=
                 u[:6] = u[0]
             losses_ref.append(float(tr.step(u, i)['loss']))
             ul, il = partition_batch_by_user_owner(u, i, world, rank)
-            smf.step(ul, il, B, kind, shift, lr, wd, exchange=exchange)
+            smf.step(ul, il, B, kind, shift, lr, wd, exchange=exchange, capq=capq)
             losses.append(smf.pop_loss())
         sd = smf.full_state_dict()
         if rank == 0:
@@ -149,26 +186,12 @@ def test_sharded_step_world3_ragged_shards_matches_oracle(exchange, flags, tmp_p
     assert (tmp_path / 'ok').exists()
 
 
-@pytest.mark.parametrize('world,exchange,flags', [(2, 'dense', (True, True, True)), (3, 'dense', (False, False, False)),
-                                                  (3, 'dense', (False, True, False)), (2, 'sparse', (False, True, False))])
-def test_sharded_step_inplace_exchange_layout_matches_oracle(world, exchange, flags, tmp_path):
-    """inplace_exchange=True: the item rows + biases live in the arena as the [capP, ld] block the collectives move
-    (no staging copies); dense and sparse steps, state_dict round trip and AdamW over the padded block all still match
-    the single-process oracle."""
-    mp.spawn(_worker, args=(world, _free_port(), 'bce', flags, str(tmp_path), exchange, True), nprocs=world, join=True)
-    assert (tmp_path / 'ok').exists()
-
-
-def test_inplace_layout_offsets():
-    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
-    lay = ArenaLayout(7, 5, 6, True, True, True, item_block_rows=8, item_bias_row=7)    # ld 8: 7 bias floats fit row 7
-    a = torch.arange(lay.n_total, dtype=torch.float32)
-    Uw, Vw, Ub, Ib, Gb = lay.views(a)
-    assert Vw.shape == (5, 6) and Ib.shape == (5, 1)
-    assert int(Ib[0, 0]) == lay.off_V + 7 * 8 and int(Vw[0, 0]) == lay.off_V
-    assert lay.off_Ub >= lay.off_V + 8 * 8 and lay.off_Gb > lay.off_Ub          # nothing overlaps the item block
-    plain = ArenaLayout(7, 5, 6, True, True, True)
-    assert plain.off_Ib > plain.off_Ub and plain.n_total != lay.n_total
+def test_exchange_capacity_bounds():
+    from hassaku_b200.sharded import exchange_capacity
+    assert exchange_capacity(8192 * 51, 1_000_000, 8) <= 125_000                  # cfg4: ~43 k expected per owner
+    assert 40_000 < exchange_capacity(8192 * 51, 1_000_000, 8) < 50_000
+    assert exchange_capacity(8192 * 51, 3706, 2) == 1853                          # cfg2: the whole shard
+    assert exchange_capacity(10, 41, 3) == 14
 
 
 def test_partition_and_shard_spec():
