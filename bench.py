@@ -1,23 +1,31 @@
-"""bench.py — BPR-MF train triples/s (+ full-rank eval users/s, NDCG@10) on B200, the metric of BASELINE.json.
+"""bench.py — BPR-MF train triples/s and full-rank eval users/s (NDCG@10) at 1/2/4/8 B200: the metric of BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2|cfg3|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...
 
-Workload at N = 1: BASELINE.json configs[1] ("cfg2"): synthetic ML-1M shape (6 040 users x 3 706 items, ~0.93 M unique
-interactions, 80/10/10 split), d = 402, train_batch_size 8192, neg_train 50, item bias, BPR, AdamW(lr 3e-4, wd 4e-5),
-fp32 exact mode, followed by one full-rank evaluation sweep over all users.
-
-A "step" = one pass of the hot path over one batch: hsk_mf_train_fused (gather + score + BPR loss + gradient scatter)
-+ hsk_adamw_dense (dense AdamW over all parameters, gradient zeroing fused).  Prints ONE JSON line (rank 0).
-
-  value      whole-job triples/s with the batches already resident in HBM, device-timed (CUDA events, max over ranks);
-             L2 is flushed between timed steps (the 63 MB of tables + optimizer state fit the 126 MB L2, so without the
-             flush the number is an L2-bandwidth number; it is reported as `value_l2_warm`)
-  e2e        the same metric through the public API (FusedMFTrainStep called with HOST batches): per step the H2D copy
-             of the int64 index batch from pinned memory and a D2H read of the loss are inside the timed region
-  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the launch stream)
-             against the measured HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline / --impl reference   the oracle port of the reference's torch path (oracle/mf_oracle.py: the same ATen
-             op sequence as train/trainer.py:133-148) timed on this box's host cores on a bounded sample
+ONE workload at every N (so that the 1 -> 8 curve compares like with like), BASELINE.json configs[3] + configs[4]:
+  train   "cfg4": synthetic LFM-2b scale, 2 M users x 1 M items, ~200 M interactions (generated on the device per rank),
+          d = 128, BPR, neg_train 50, item bias, AdamW(lr 3e-4, wd 4e-5) in the dense torch-faithful mode, 8192 samples
+          per GPU and step (weak scaling: global batch N x 8192; the tables stay 2 M x 1 M, row-sharded over the N GPUs).
+          P = 385 M parameters (6.2 GB of p, m, v, g): far beyond the 126 MB L2, so no L2 flush is needed between steps.
+          N = 1: the public single-GPU API (FusedMFTrainStep + DenseAdam).  N > 1: hassaku_b200.sharded.ShardedMF — device
+          routing + NCCL all-to-all of the needed rows / row gradients, the whole step ONE CUDA graph.
+  eval    "cfg5": 10 M users x 1 M items, d = 256, BF16 tcgen05 scoring + exclusion mask + top-100 + fp32 re-scoring +
+          12 metrics, item-sharded at N > 1 (all-gather of user rows, per-shard top-k, all-to-all + merge).
+A "step" = one pass of the hot path over one batch (hsk_mf_train_fused + hsk_mark_batch + hsk_adamw_dense_rows).  Rank 0
+prints ONE JSON line:
+  value      whole-job train triples/s, batches resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e        the same through the public API with HOST (pinned) index batches: H2D per step + loss D2H inside the region
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (events on the launch
+             stream) against the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes per launch from
+             the committed ncu capture (profiles/r02_traffic.json), null when no capture of this workload is committed
+  eval       users/s (+ TFLOP/s against the measured bf16 peaks), NDCG@10, its own e2e and roofline
+  cpu_baseline / --impl reference   the oracle port of the reference's torch path (oracle/mf_oracle.py, the ATen op sequence
+             of train/trainer.py:133-148 / eval/eval.py:237-253) on this box's host cores, all threads, bounded sample
+  parity_check (N > 1)  one sharded step and one sharded evaluation round against rank 0's single-GPU result on the same
+             global batch, outside the timed regions
+  also       (N = 1, unless --no-also) the cfg2 / cfg3 single-GPU lines (L2-resident tables: L2 flushed between steps),
+             the negative sampler's throughput and one Trainer.fit epoch with the device loader
 """
 import argparse
 import json
@@ -39,7 +47,10 @@ WORKLOADS = {
     'cfg1': ('ml1m', 402, 128, 50, 'bpr', 3e-4, 4e-5),
     'cfg2': ('ml1m', 402, 8192, 50, 'bpr', 3e-4, 4e-5),
     'cfg3': ('ml10m', 128, 8192, 100, 'sampled_softmax', 3e-4, 4e-5),
+    'cfg4': ('lfm2b', 128, 8192, 50, 'bpr', 3e-4, 4e-5),
 }
+EVAL_CFG5 = {'data': 'eval10m', 'd': 256, 'k': 100, 'batch': 18944, 'precision': 'bf16'}   # 18 944 = 148 SMs x 128 rows
+DEVICE_GENERATED = ('lfm2b', 'eval10m')    # too large for the reference's host loaders: built on the device per rank
 
 
 def algorithmic_bytes(U, I, d, B, N, item_bias=True):
@@ -50,13 +61,31 @@ def algorithmic_bytes(U, I, d, B, N, item_bias=True):
     return {'gather_scatter': 2 * A + small, 'adamw': 28 * P, 'total': 2 * A + small + 28 * P, 'P': P, 'A': A}
 
 
-def measured_peaks():
+def load_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             p = json.load(f)
-        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        return {'hbm_gbs': float(p['hbm_gbs']), 'bf16_tflops': float(p['bf16_tflops']),
+                'bf16_tflops_sustained': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])),
+                'source': 'measured (MEASURED_PEAKS.json)'}
     except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md)'
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def measured_peaks():
+    p = load_peaks()
+    return p['hbm_gbs'], p['source']
+
+
+def committed_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this bench
+    command (profiles/r02_traffic.json: {workload: {kernel: {'bytes': ..., 'capture': file}}}), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
+            t = json.load(f)
+        return t[workload][kernel]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -101,6 +130,7 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+            self.proc = None
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -143,57 +173,165 @@ def make_batches(data, B, N, n_batches, seed=64):
     return us, its
 
 
-def init_like_reference(model, seed=64):
+def make_host_batches_large(U, I, B, N, n_batches, seed=64, zipf=0.8):
+    """Captured batches for the reference arm at the device-generated shapes (no GPU involved): users uniform, positives
+    Zipf(0.8), negatives uniform.  No rejection against the user's train row: at ~80 train items of 1 M the reference's
+    collate loop (dataloader.py:112-120) redraws 8e-5 of the slots, which does not change the step's cost."""
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, I + 1, dtype=np.float64) ** zipf
+    cdf = np.cumsum(p / p.sum())
+    cdf[-1] = 1.0
+    us, its = [], []
+    for _ in range(n_batches):
+        u = rng.integers(0, U, B, dtype=np.int64)
+        pos = np.minimum(np.searchsorted(cdf, rng.random(B), side='right'), I - 1).astype(np.int64)
+        neg = rng.integers(0, I, (B, N), dtype=np.int64)
+        us.append(u)
+        its.append(np.column_stack([pos, neg]))
+    return us, its
+
+
+def make_device_batches(dint, B, N, n_batches, seed=64):
+    """Captured batches from a DeviceInteractions (this rank's users): positives drawn from the train COO list, negatives
+    from hsk_sample_negatives against the user's train CSR row — the device loader's batch (data/dataloader.py:92-129)."""
     import torch
-    torch.manual_seed(seed)  # conf_parser.py:18 default seed; weights ~ N(0, (0.1/shape[-1])^2) (train/utils.py:13)
-    return model
+    from hassaku_b200 import _C
+    dev = dint.rows.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    us, its = [], []
+    for b in range(n_batches):
+        sel = torch.randint(0, dint.rows.numel(), (B,), device=dev, generator=gen)
+        u, pos = dint.rows[sel].contiguous(), dint.cols[sel].contiguous()
+        i = torch.empty((B, N + 1), dtype=torch.int64, device=dev)
+        _C.sample_negatives(u, pos, N, dint.n_items, dint.n_users, dint.train[0], dint.train[1], seed, b, i, True, status)
+        us.append(u)
+        its.append(i)
+    assert int(status.item()) == 0, 'negative sampler reported a status bit'
+    return us, its
+
+
+def shapes_of(name):
+    from hassaku_b200.data.synthetic import SHAPES
+    return SHAPES[name]
+
+
+def workload_config(wname, wl, U, I, world=1):
+    name, d, B, N, loss, lr, wd = wl
+    big = name in DEVICE_GENERATED
+    cfg = {'workload': f'{wname}: BPR-MF train step (+ cfg5 full-rank eval), synthetic {name} shape', 'n_users': U, 'n_items': I,
+           'embedding_dim': d, 'train_batch_size': B, 'train_batch_is': 'per GPU (weak scaling)', 'global_batch': B * world,
+           'neg_train': N, 'rec_loss': loss, 'optimizer': 'adamw (dense, torch-faithful)', 'lr': lr, 'wd': wd,
+           'item_bias': True, 'precision': 'fp32 exact (train); bf16 tcgen05 + fp32 re-scoring (eval)',
+           'parallelism': 'single GPU' if world == 1 else f'item+user row-sharded x{world}, NCCL all-to-all (sparse exchange, CUDA graph)'}
+    cfg['l2'] = ('inputs larger than L2: 6.2 GB of parameters + optimizer state per step, no flush' if big else
+                 'flushed between timed steps (tables + optimizer state fit L2); value_l2_warm = back to back')
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, wl):
-    """--impl reference: the reference's CPU implementation of the step (oracle port) on all host threads."""
+# CPU side: the reference arm and the bounded cpu_baseline legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_threads():
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))     # torchrun exports OMP_NUM_THREADS=1: undo it for the CPU legs
+    return torch.get_num_threads()
+
+
+def _cpu_train_setup(wl, batch_scale=1):
     import torch
     from oracle import mf_oracle as O
-    from hassaku_b200.data.synthetic import make_named
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
     name, d, B, N, loss, lr, wd = wl
-    data = make_named(name)
-    U, I = data.n_users, data.n_items
+    B = B * batch_scale
+    U, I, _ = shapes_of(name)
     torch.manual_seed(64)
     model = O.OracleMF(U, I, d, use_item_bias=True)
     tr = O.OracleTrainer(model, loss, lr, wd, 'adamw', neg_train=N)
-    nb = min(args.steps + args.warmup, 8)
-    us, its = make_batches(data, B, N, nb)
+    if name in DEVICE_GENERATED:
+        us, its = make_host_batches_large(U, I, B, N, 4)
+    else:
+        from hassaku_b200.data.synthetic import make_named
+        us, its = make_batches(make_named(name), B, N, 4)
     us = [torch.from_numpy(x) for x in us]
     its = [torch.from_numpy(x) for x in its]
-    labels = O.make_labels(B, N + 1)
-    for s in range(args.warmup):
+    return tr, us, its, O.make_labels(B, N + 1), (U, I)
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the step (oracle port) on all host threads, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = _cpu_threads()
+    name, d, B, N, loss, lr, wd = wl
+    # the arm's config at --gpus N is the GLOBAL batch N x 8192 (weak scaling): the CPU takes it as one step
+    tr, us, its, labels, (U, I) = _cpu_train_setup(wl, batch_scale=max(1, args.gpus))
+    B = B * max(1, args.gpus)
+    nb = len(us)
+    budget_s = float(os.environ.get('HSK_REF_BUDGET_S', '150'))
+    t_w0 = time.perf_counter()
+    n_warm = 0
+    for s in range(max(args.warmup, 1)):
         tr.step(us[s % nb], its[s % nb], labels)
+        n_warm += 1
+        if time.perf_counter() - t_w0 > 0.2 * budget_s:
+            break
+    per_step = (time.perf_counter() - t_w0) / n_warm
+    # bounded: at the cfg4 shape one CPU step takes seconds; run as many of the K steps as fit the budget
+    n_steps = int(max(1, min(args.steps, (0.8 * budget_s) // max(per_step, 1e-6))))
     t0 = time.perf_counter()
-    for s in range(args.steps):
+    for s in range(n_steps):
         tr.step(us[s % nb], its[s % nb], labels)
     dt = time.perf_counter() - t0
-    v = args.steps * B * N / dt
-    cores = torch.get_num_threads()
+    v = n_steps * B * N / dt
     line = {'impl': 'reference', 'metric': 'BPR-MF train triples/s', 'value': v, 'unit': 'triples/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.workload, wl, U, I),
+            'steps': n_steps, 'steps_requested': args.steps, 'warmup': n_warm, 'ms_per_step': 1e3 * dt / n_steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, wl, U, I, args.gpus),
             'cpu_baseline': {'value': v, 'unit': 'triples/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{args.steps} steps of {args.workload} (B={B}, N={N}) on the oracle port of '
-                                       f'train/trainer.py:133-148 (torch CPU, {cores} threads, {os.cpu_count()} cpus)'},
+                             'sample': f'{n_steps} steps of {args.workload} (global batch B={B}, N={N}) on the oracle port of '
+                                       f'train/trainer.py:133-148 (torch CPU, {cores} threads of {os.cpu_count()} cpus), {dt:.1f} s'},
             'e2e': {'value': v, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    if not args.no_eval:
+        try:
+            line['eval'] = cpu_eval_baseline_cfg5()
+        except Exception as ex:
+            line['eval'] = {'error': repr(ex)}
+    print(json.dumps(line), flush=True)
 
 
-def workload_config(wname, wl, U, I):
+def cpu_baseline(wl, data=None, us=None, its=None, budget_s=20.0):
+    """Bounded CPU leg of the default run: the oracle port of the step on all host threads for ~budget_s."""
+    import torch
+    from oracle import mf_oracle as O
+    cores = _cpu_threads()
     name, d, B, N, loss, lr, wd = wl
-    return {'workload': f'{wname}: BPR-MF train step + full-rank eval, synthetic {name} shape', 'n_users': U, 'n_items': I,
-            'embedding_dim': d, 'train_batch_size': B, 'neg_train': N, 'rec_loss': loss, 'optimizer': 'adamw', 'lr': lr,
-            'wd': wd, 'item_bias': True, 'eval_batch_size': 8192, 'precision': 'fp32 exact',
-            'l2': 'flushed between timed steps (tables + optimizer state fit L2); value_l2_warm = back to back'}
+    if data is not None:     # small workloads: the captured batches of the GPU arm
+        torch.manual_seed(64)
+        model = O.OracleMF(data.n_users, data.n_items, d, use_item_bias=True)
+        tr = O.OracleTrainer(model, loss, lr, wd, 'adamw', neg_train=N)
+        labels = O.make_labels(B, N + 1)
+        us = [torch.from_numpy(np.asarray(x)) for x in us]
+        its = [torch.from_numpy(np.asarray(x)) for x in its]
+    else:
+        tr, us, its, labels, _ = _cpu_train_setup(wl)
+    tr.step(us[0], its[0], labels)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        tr.step(us[n % len(us)], its[n % len(us)], labels)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 30:
+            break
+    return {'value': n * B * N / dt, 'unit': 'triples/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{n} steps of the same workload (B={B}, N={N}) on the oracle port (torch CPU, {cores} threads of '
+                      f'{os.cpu_count()} cpus), {dt:.1f} s'}
 
 
 def cpu_eval_baseline(wl, data, n_users=512, eval_batch_size=256):
@@ -201,6 +339,7 @@ def cpu_eval_baseline(wl, data, n_users=512, eval_batch_size=256):
     12 metrics per batch; eval batch 256 as in its README) on a bounded sample of users, host cores only."""
     import torch
     from oracle import mf_oracle as O
+    cores = _cpu_threads()
     name, d, B, N, loss, lr, wd = wl
     torch.manual_seed(64)
     model = O.OracleMF(data.n_users, data.n_items, d, use_item_bias=True)
@@ -209,155 +348,512 @@ def cpu_eval_baseline(wl, data, n_users=512, eval_batch_size=256):
     with torch.no_grad():
         res = O.evaluate(model, data.val.tocsr(), data.train.tocsr(), eval_batch_size=eval_batch_size, users=users)
     dt = time.perf_counter() - t0
-    cores = torch.get_num_threads()
     return {'value': len(users) / dt, 'unit': 'users/s', 'cores': cores, 'kind': 'port',
             'sample': f'{len(users)} of {data.n_users} users against all {data.n_items} items, eval batch {eval_batch_size}, '
                       f'oracle port of eval/eval.py:237-253 (torch CPU, {cores} threads), {dt:.1f} s',
             'ndcg@10_of_sample': float(res['ndcg@10'])}
 
 
-def cpu_baseline(wl, data, us, its, budget_s=20.0):
+def cpu_eval_baseline_cfg5(n_users=16, eval_batch_size=4):
+    """The reference evaluation at the cfg5 item shape (1 M items, d 256): its [Be, I, d] temporary is 1 GB per user, so
+    Be = 4 (time a small user sample against the full item set, extrapolate linearly in users)."""
     import torch
+    from scipy import sparse as sp
     from oracle import mf_oracle as O
-    name, d, B, N, loss, lr, wd = wl
+    cores = _cpu_threads()
+    U, I, _ = shapes_of(EVAL_CFG5['data'])
+    d = EVAL_CFG5['d']
     torch.manual_seed(64)
-    model = O.OracleMF(data.n_users, data.n_items, d, use_item_bias=True)
-    tr = O.OracleTrainer(model, loss, lr, wd, 'adamw', neg_train=N)
-    labels = O.make_labels(B, N + 1)
-    tr.step(torch.from_numpy(us[0]), torch.from_numpy(its[0]), labels)  # warm-up
-    n, t0 = 0, time.perf_counter()
-    while True:
-        tr.step(torch.from_numpy(us[n % len(us)]), torch.from_numpy(its[n % len(us)]), labels)
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt > budget_s or n >= 30:
-            break
-    cores = torch.get_num_threads()
-    return {'value': n * B * N / dt, 'unit': 'triples/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n} steps of the same workload (B={B}, N={N}) on the oracle port (torch CPU, {cores} threads of '
-                      f'{os.cpu_count()} cpus), {dt:.1f} s'}
+    model = O.OracleMF(n_users, I, d, use_item_bias=True)       # only the sampled users' rows are needed
+    rng = np.random.RandomState(0)
+    rows = np.repeat(np.arange(n_users), 80)
+    ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(n_users, I))
+    lab = sp.csr_matrix((np.ones(n_users * 10, dtype=np.int8), (np.repeat(np.arange(n_users), 10), rng.randint(0, I, n_users * 10))),
+                        shape=(n_users, I))
+    ex.sum_duplicates(); ex.sort_indices(); lab.sum_duplicates(); lab.data[:] = 1; lab.sort_indices()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        res = O.evaluate(model, lab, ex, eval_batch_size=eval_batch_size, users=np.arange(n_users))
+    dt = time.perf_counter() - t0
+    return {'metric': 'full-rank eval users/s', 'value': n_users / dt, 'unit': 'users/s', 'cores': cores, 'kind': 'port',
+            'extrapolated': True,
+            'sample': f'{n_users} users against all {I} items, d {d}, eval batch {eval_batch_size} (the reference materialises '
+                      f'[Be, I, d]: 1 GB per user), oracle port of eval/eval.py:237-253 (torch CPU, {cores} threads), {dt:.1f} s; '
+                      f'linear in users',
+            'ndcg@10_of_sample': float(res['ndcg@10'])}
 
 
-def run_extras(dev, flush):
-    """Kernel-level measurements at the shapes of BASELINE configs 4 and 5 that do not fit the cfg2 step (reported next to
-    the headline, never instead of it):
-      adamw_cfg4      hsk_adamw_dense over P = 385 M parameters (2 M users x 1 M items, d 128): the genuinely HBM-bound
-                      kernel of the path (28 B / parameter + 4 B gradient zeroing), GB/s vs the measured copy bandwidth
-      eval_tc_cfg5    hsk_eval_topk_tc, one batch of 18 944 users (148 CTAs x 128) against 1 M items, d 256, BF16 and
-                      TF32: users/s, TFLOP/s vs the measured sustained bf16 GEMM peak (tensor-pipe roofline)"""
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def _events(n):
+    import torch
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+class _Dist:
+    """barrier / max-over-ranks that degrade to no-ops at world 1 (no process group)."""
+
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return float(x)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def bench_train_single(args, wname, wl, dev, D, clk_index=0, want_e2e=True, flush=None):
+    """N = 1: FusedMFTrainStep + DenseAdam (the public single-GPU API) on workload `wl`.  Returns a dict of measurements."""
     import torch
     from hassaku_b200 import _C
-    out = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        peaks = {'hbm_gbs': 6650.0, 'bf16_tflops_sustained': 1400.0, 'bf16_tflops': 1590.0}
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.train.optim import DenseAdam
+    from hassaku_b200.train.rec_losses import RecommenderSystemLossesEnum
+    from hassaku_b200.train.trainer_step import FusedMFTrainStep
+    name, d, B, N, loss, lr, wd = wl
+    big = name in DEVICE_GENERATED
+    K, W = args.steps, max(args.warmup, 3)
+    n_distinct = 16
+    if big:
+        from hassaku_b200.data.synthetic import make_device_interactions
+        U, I, n_inter = shapes_of(name)
+        data = make_device_interactions(U, I, n_inter, dev, 1, 0, seed=0)
+        model = SGDMatrixFactorization.on_device(U, I, d, use_item_bias=True, device=dev, seed=64)
+        u_dev, i_dev = make_device_batches(data, B, N, n_distinct)
+        us = [x.cpu().numpy() for x in u_dev]
+        its = [x.cpu().numpy() for x in i_dev]
+        n_train = int(data.rows.numel())
+    else:
+        from hassaku_b200.data.synthetic import make_named
+        data = make_named(name)
+        U, I = data.n_users, data.n_items
+        torch.manual_seed(64)  # conf_parser.py:18 default seed; weights ~ N(0, (0.1/shape[-1])^2) (train/utils.py:13)
+        model = SGDMatrixFactorization(U, I, d, use_item_bias=True).to(dev)
+        us, its = make_batches(data, B, N, n_distinct)
+        u_dev = [torch.from_numpy(x).to(dev) for x in us]
+        i_dev = [torch.from_numpy(x).to(dev) for x in its]
+        n_train = int(data.train.nnz)
 
-    def timed(fn, iters):
-        ts = []
-        for _ in range(iters):
+    class _DS:
+        n_items = I
+
+    loss_fn = RecommenderSystemLossesEnum[loss].value.build_from_conf({'train_neg_strategy': 'uniform', 'neg_train': N}, _DS())
+    opt = DenseAdam(model, lr=lr, weight_decay=wd, decoupled=True)
+    step = FusedMFTrainStep(model, loss_fn, opt)
+    u_pin = [torch.from_numpy(x).pin_memory() for x in us]
+    i_pin = [torch.from_numpy(x).pin_memory() for x in its]
+    do_flush = (not big) and flush is not None
+
+    # ---- (1) THE timed region: exactly K steps, inputs resident ----
+    for s in range(W):
+        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+    D.barrier()
+    clk = ClockSampler(clk_index)
+    clk.__enter__()
+    clk.wait_ready()
+    D.barrier()
+    if do_flush:     # L2-resident tables: flush between steps, per-step events
+        ev0, ev1 = _events(K), _events(K)
+        for s in range(K):
             flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        return float(np.median(ts))
+            ev0[s].record()
+            step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+            ev1[s].record()
+        D.barrier()
+        ms_timed = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    else:
+        a, b = _events(2)
+        a.record()
+        for s in range(K):
+            step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+        b.record()
+        D.barrier()
+        ms_timed = a.elapsed_time(b)
+    # ---- (2) back to back + sustained (>= 1.5 s so that the clock / power samples see the load) ----
+    a, b = _events(2)
+    a.record()
+    for s in range(K):
+        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+    b.record()
+    D.barrier()
+    ms_warm = a.elapsed_time(b)
+    n_sus = max(K, int(1500.0 / max(ms_warm / K, 1e-3)))
+    a, b = _events(2)
+    a.record()
+    for s in range(n_sus):
+        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
+    b.record()
+    D.barrier()
+    ms_sus = a.elapsed_time(b)
+    clk.__exit__()
 
-    try:
-        P = (2_000_000 + 1_000_000) * 128 + 1_000_000
-        p = torch.zeros(P, device=dev); m = torch.zeros_like(p); v = torch.zeros_like(p)
-        g = torch.full((P,), 1e-3, device=dev)
-        k = [0]
+    # ---- (3) per-kernel durations: events between the launches of one step ----
+    tabs, gtabs = model._tables(), opt.grad_tables
+    kind, shift = _C.LOSS_KINDS[loss_fn.loss_kind], float(loss_fn.neg_shift())
+    Kk = min(K, 50)
+    e = [_events(4) for _ in range(Kk)]
+    uses_rows = None
+    for s in range(Kk):
+        if do_flush:
+            flush.zero_()
+        u, i = u_dev[s % n_distinct], i_dev[s % n_distinct]
+        e[s][0].record()
+        _C.mf_train_fused(tabs, gtabs, u, i, kind, shift, step.loss_accum, status=model._status())
+        e[s][1].record()
+        opt.mark(u, i)
+        uses_rows = len(opt._segments) > 0
+        e[s][2].record()
+        opt.step_fused()
+        e[s][3].record()
+    D.barrier()
+    k_ms = {'hsk_mf_train_fused': sum(x[0].elapsed_time(x[1]) for x in e) / Kk,
+            'hsk_mark_batch': sum(x[1].elapsed_time(x[2]) for x in e) / Kk,
+            ('hsk_adamw_dense_rows' if uses_rows else 'hsk_adamw_dense'): sum(x[2].elapsed_time(x[3]) for x in e) / Kk}
 
-        def adam():
-            k[0] += 1
-            _C.adamw_dense(p, m, v, g, 3e-4, 0.9, 0.999, 1e-8, 4e-5, k[0], zero_grad=True)
-        adam()
-        ms = timed(adam, 5)
-        gbs = 32.0 * P / (ms * 1e-3) / 1e9   # 16 B read + 16 B written per parameter (g zeroed in the same pass)
-        out['adamw_cfg4'] = {'params': P, 'ms': ms, 'bytes_per_param': 32, 'achieved_gbs': gbs, 'peak_gbs': peaks['hbm_gbs'],
-                             'frac': gbs / peaks['hbm_gbs']}
-        del p, m, v, g
-    except Exception as ex:
-        out['adamw_cfg4'] = {'error': repr(ex)}
-    try:   # cfg4-shaped train step on one GPU: dense (torch-faithful) vs lazy (row-sparse) AdamW, reported separately
-        from hassaku_b200.algorithms.sgd_alg import ArenaLayout
-        from hassaku_b200.train.optim import DenseAdam
-        U4, I4, d4, B4, N4 = 2_000_000, 1_000_000, 128, 8192, 50
-
-        class _M:   # arena-only stand-in for the model (random-init weights of the cfg4 architecture, built on the device)
-            pass
-        mdl = _M()
-        mdl.layout = ArenaLayout(U4, I4, d4, False, True, False)
-        mdl.arena = torch.randn(mdl.layout.n_total, device=dev) * (0.1 / d4)
-        mdl.parameters = lambda: [torch.nn.Parameter(mdl.arena[:4])]
-        tabs = mdl.layout.tables(mdl.arena)
-        gen = torch.Generator(device=dev); gen.manual_seed(0)
-        ub = [torch.randint(0, U4, (B4,), device=dev, generator=gen) for _ in range(4)]
-        ib = [torch.randint(0, I4, (B4, N4 + 1), device=dev, generator=gen) for _ in range(4)]
-        acc = torch.zeros(1, dtype=torch.float64, device=dev)
-        res4 = {}
-        for mode in ('dense', 'lazy'):
-            opt4 = DenseAdam(mdl, lr=3e-4, weight_decay=4e-5, mode=mode)
-            kk = [0]
-
-            def st():
-                j = kk[0] % 4
-                kk[0] += 1
-                _C.mf_train_fused(tabs, opt4.grad_tables, ub[j], ib[j], 0, 0.0, acc)
-                if mode == 'lazy':
-                    opt4.mark(ub[j], ib[j])
-                opt4.step_fused()
-            st(); st()
-            ms = timed(st, 6)
-            ab4 = algorithmic_bytes(U4, I4, d4, B4, N4)
-            res4[mode] = {'ms_per_step': ms, 'triples_per_s': B4 * N4 / (ms * 1e-3)}
-            if mode == 'dense':
-                res4[mode].update({'algorithmic_bytes': ab4['total'], 'achieved_gbs': ab4['total'] / (ms * 1e-3) / 1e9,
-                                   'frac_of_hbm_peak': ab4['total'] / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']})
-            del opt4
-        out['train_cfg4_1gpu'] = dict(res4, shape={'n_users': U4, 'n_items': I4, 'd': d4, 'B': B4, 'N': N4},
-                                      note='lazy = row-sparse AdamW (different trajectory from torch.optim.AdamW), reported separately')
-        del mdl, tabs
-    except Exception as ex:
-        out['train_cfg4_1gpu'] = {'error': repr(ex)}
-    torch.cuda.empty_cache()
-    try:
-        import math
-        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
-        from hassaku_b200.eval.eval import DeviceCSR, TopKScorer
-        from scipy import sparse as sp
-        U, I, d, B = 18944, 1_000_000, 256, 18944
-        torch.manual_seed(0)
-        model = SGDMatrixFactorization(U, I, d, use_item_bias=True)
-        with torch.no_grad():
-            for q in model.parameters():
-                q.copy_(torch.randn_like(q) * (1.0 / math.sqrt(d) if q.shape[-1] == d else 0.05))
-        model.to(dev)
-        rng = np.random.RandomState(1)
-        rows = np.repeat(np.arange(U), 80)
-        ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
-        ex.sum_duplicates(); ex.sort_indices()
-        ex = DeviceCSR(ex, dev)
-        users = torch.arange(B, device=dev)
-        fl = 2.0 * B * I * d
-        for prec in ('bf16', 'tf32'):
-            sc = TopKScorer(model, B, 100, prec)
-            fn = lambda: sc(users, ex)
-            fn(); fn()
-            ms = timed(fn, 3)
-            out[f'eval_tc_cfg5_{prec}'] = {'users': B, 'items': I, 'd': d, 'k': 100, 'ms_per_batch': ms, 'users_per_s': B / (ms * 1e-3),
-                                           'tflops': fl / (ms * 1e-3) / 1e12, 'peak_tflops_sustained_bf16': peaks['bf16_tflops_sustained'],
-                                           'frac_of_bf16_peak': fl / (ms * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
-                                           'includes': 'user-row pack + tcgen05 scoring + mask + top-100'}
-            del sc
-        del model
-    except Exception as ex:
-        out['eval_tc_cfg5'] = {'error': repr(ex)}
-    torch.cuda.empty_cache()
+    # ---- (4) end to end through the public API with HOST batches ----
+    out = {'U': U, 'I': I, 'ms_timed': ms_timed, 'ms_warm': ms_warm, 'ms_sus': ms_sus, 'n_sus': n_sus, 'K': K, 'W': W,
+           'kernels_ms': k_ms, 'uses_rows_kernel': bool(uses_rows), 'clocks': clk.summary(), 'n_train': n_train,
+           'flushed': do_flush, 'launches_per_step': 3 if uses_rows else 2}
+    if want_e2e:
+        loss_pin = torch.zeros(K, dtype=torch.float64).pin_memory()
+        loss_dev = torch.zeros(K, dtype=torch.float64, device=dev)
+        for s in range(3):
+            step(u_pin[s % n_distinct], i_pin[s % n_distinct])
+        a2, b2 = _events(2)
+        D.barrier()
+        t_wall0 = time.perf_counter()
+        a2.record()
+        for s in range(K):
+            step(u_pin[s % n_distinct], i_pin[s % n_distinct], loss_out=loss_dev[s:s + 1])
+            loss_pin[s:s + 1].copy_(loss_dev[s:s + 1], non_blocking=True)
+        b2.record()
+        D.barrier()
+        out.update({'ms_e2e': a2.elapsed_time(b2), 'wall_e2e': (time.perf_counter() - t_wall0) * 1e3,
+                    'h2d': int(us[0].nbytes + its[0].nbytes), 'final_loss': float(loss_pin[K - 1])})
+        assert math.isfinite(out['final_loss']), 'training diverged'
+    model.check_status()
+    out['host_batches'] = (us, its)
+    out['data'] = data
+    out['model'] = model
     return out
 
 
+def bench_sampler_and_fit(dev, also_wl=('cfg2', 'cfg3')):
+    """What has parity but had no number: hsk_sample_negatives throughput and one Trainer.fit-style epoch
+    with the device-resident loader (shuffle + sampling + fused step, nothing from the host) per small workload."""
+    import torch
+    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+    from hassaku_b200.data.dataloader import NegativeSampler, TrainDataLoader
+    from hassaku_b200.data.dataset import TrainRecDataset
+    from hassaku_b200.data.synthetic import make_named
+    from hassaku_b200.train.optim import DenseAdam
+    from hassaku_b200.train.rec_losses import RecommenderSystemLossesEnum
+    from hassaku_b200.train.trainer_step import FusedMFTrainStep
+    out = {}
+    for wname in also_wl:
+        name, d, B, N, loss, lr, wd = WORKLOADS[wname]
+        try:
+            data = make_named(name)
+            ds = TrainRecDataset.from_interactions(data.train)
+            loader = TrainDataLoader(NegativeSampler(ds, N, 'uniform'), ds, batch_size=B, shuffle=True, device=dev, seed=64)
+            # sampler alone
+            u = loader.rows[:B].contiguous(); pos = loader.cols[:B].contiguous()
+            for s in range(3):
+                loader.sample_batch(u, pos, s)
+            a, b = _events(2)
+            n_it = 200
+            a.record()
+            for s in range(n_it):
+                loader.sample_batch(u, pos, s)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n_it
+            # one epoch through the loader + fused step (what Trainer._train_one_epoch runs)
+            torch.manual_seed(64)
+            model = SGDMatrixFactorization(data.n_users, data.n_items, d, use_item_bias=True).to(dev)
+
+            class _DS:
+                n_items = data.n_items
+
+            loss_fn = RecommenderSystemLossesEnum[loss].value.build_from_conf({'train_neg_strategy': 'uniform', 'neg_train': N}, _DS())
+            step = FusedMFTrainStep(model, loss_fn, DenseAdam(model, lr=lr, weight_decay=wd))
+            max_batches = 400
+            n_b, n_s = 0, 0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for u_b, i_b, _lab in loader:
+                step(u_b, i_b)
+                n_b += 1; n_s += len(u_b)
+                if n_b >= max_batches:
+                    break
+            ep_loss = step.pop_loss_sum() / n_b
+            dt = time.perf_counter() - t0
+            out[wname] = {'sampler': {'samples_per_s': B / (ms * 1e-3), 'negatives_per_s': B * N / (ms * 1e-3), 'us_per_batch': ms * 1e3,
+                                      'reference_loader': '~8 k samples/s with 4 workers (SURVEY 3.4, data/dataloader.py:92-129)'},
+                          'fit_epoch_device_loader': {'batches': n_b, 'samples_per_s': n_s / dt, 'triples_per_s': n_s * N / dt,
+                                                      'wall_s': dt, 'mean_loss': ep_loss,
+                                                      'includes': 'device shuffle + hsk_sample_negatives + fused step + AdamW, host wall clock'}}
+            del model, step, loader
+        except Exception as ex:
+            out[wname] = {'error': repr(ex)}
+    return out
+
+
+def bench_eval(args, dev, D, world, rank, smf_factory=None):
+    """cfg5: 10 M users x 1 M items, d 256, bf16 tcgen05 + fp32 re-scoring + top-100 + metrics.  N = 1: the public API
+    (evaluate_mf_sweep over TopKScorer); N > 1: ShardedMF.evaluate.  `--eval-users` bounds the sweep."""
+    import torch
+    from hassaku_b200.data.synthetic import make_device_interactions
+    from hassaku_b200.eval.eval import DeviceCSR, FullEvaluator, evaluate_mf_sweep
+    peaks = load_peaks()
+    U, I, n_inter = shapes_of(EVAL_CFG5['data'])
+    d, k, Bt, prec = EVAL_CFG5['d'], EVAL_CFG5['k'], EVAL_CFG5['batch'], EVAL_CFG5['precision']
+    n_eval_users = min(U, args.eval_users) if args.eval_users > 0 else U
+    t0 = time.perf_counter()
+    data = make_device_interactions(U, I, n_inter, dev, world, rank, seed=1, keep_coo=False)
+    labels = DeviceCSR.from_tensors(data.val[0], data.val[1], (U, I))
+    exclude = DeviceCSR.from_tensors(data.train[0], data.train[1], (U, I))
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    std = (1.0 / math.sqrt(d), 0.05)
+    res = {}
+    if world == 1:
+        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+        model = SGDMatrixFactorization.on_device(U, I, d, use_item_bias=True, device=dev, seed=65, std=std)
+        model.eval_precision = prec
+        n_batches = math.ceil(n_eval_users / Bt)
+
+        def sweep(batches=None):
+            ev = FullEvaluator(True, 0, None)
+            evaluate_mf_sweep(model, labels, exclude, ev, n_eval_users, Bt, user_batches=batches)
+            return ev.get_results()          # the sweep's one host sync
+
+        evaluate_mf_sweep(model, labels, exclude, FullEvaluator(True, 0, None), min(n_eval_users, 3 * Bt), Bt)   # warm-up
+        D.barrier()
+        a, b = _events(2)
+        a.record()
+        r = sweep()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        # e2e: user-id batches arrive from the HOST (pinned), the metric dict goes back to the host
+        host_batches = [torch.arange(s, min(s + Bt, n_eval_users), dtype=torch.int64).pin_memory() for s in range(0, n_eval_users, Bt)]
+        D.barrier()
+        t1 = time.perf_counter()
+        r2 = sweep(host_batches)
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t1) * 1e3
+        # the scoring kernel alone (one full batch): tensor-pipe roofline of the dominant kernel
+        from hassaku_b200.eval.eval import TopKScorer
+        sc = TopKScorer(model, Bt, k, prec)
+        users = torch.arange(Bt, device=dev)
+        sc(users, exclude)
+        e = [_events(2) for _ in range(5)]
+        for x in e:
+            x[0].record(); sc(users, exclude); x[1].record()
+        torch.cuda.synchronize()
+        ms_batch = float(np.median([x[0].elapsed_time(x[1]) for x in e]))
+        res.update({'ms_batch_18944': ms_batch, 'tflops_batch': 2.0 * Bt * I * d / (ms_batch * 1e-3) / 1e12,
+                    'ndcg@10_e2e': r2['ndcg@10'], 'h2d_bytes_per_batch': 8 * Bt})
+        del model, sc
+    else:
+        smf = smf_factory(U, I, d, std, seed=65)
+        bs = Bt // world                                   # users per rank and round: a round scores 18 944 users
+        max_rounds = math.ceil(math.ceil(n_eval_users / world) / bs)
+
+        def sweep():
+            return smf.evaluate(labels, exclude, FullEvaluator(True, 0, None), batch_size=bs, precision=prec, max_rounds=max_rounds)
+
+        smf.evaluate(labels, exclude, FullEvaluator(True, 0, None), batch_size=bs, precision=prec, max_rounds=3)   # warm-up (NCCL channels)
+        D.barrier()
+        a, b = _events(2)
+        a.record()
+        r = sweep()
+        b.record()
+        torch.cuda.synchronize()
+        ms = D.max(a.elapsed_time(b))
+        D.barrier()
+        t1 = time.perf_counter()
+        r2 = sweep()
+        torch.cuda.synchronize()
+        ms_e2e = D.max((time.perf_counter() - t1) * 1e3)
+        n_eval_users = min(U, max_rounds * bs * world)
+        res['ndcg@10_e2e'] = r2['ndcg@10']
+        res['h2d_bytes_per_batch'] = 0
+        smf.check_status()
+        smf.close()
+        del smf
+    torch.cuda.empty_cache()
+    flops = 2.0 * n_eval_users * I * d
+    tf = flops / (ms * 1e-3) / 1e12
+    res.update({
+        'metric': 'full-rank eval users/s', 'value': n_eval_users / (ms * 1e-3), 'unit': 'users/s', 'users': n_eval_users,
+        'ms_per_sweep': ms, 'ndcg@10': r['ndcg@10'], 'recall@100': r['recall@100'],
+        'config': {'workload': f'cfg5: full-rank eval sweep, {U} users x {I} items, d {d}, {prec} tcgen05 scoring + exclusion mask + '
+                               f'top-{k} + fp32 re-scoring of k + 28 candidates + 12 metrics', 'users_per_round': Bt,
+                   'exclusions_per_user': float(exclude.indices.numel()) * world / U, 'labels_per_user': float(labels.indices.numel()) * world / U,
+                   'weights': 'N(0, 1/d) embeddings, N(0, 0.05^2) item bias (the training init would rank by bias alone)',
+                   'parallelism': 'single GPU' if world == 1 else f'item-sharded x{world}: all-gather user rows, per-shard top-k, all-to-all + merge'},
+        'tflops': tf,
+        'e2e': {'value': n_eval_users / (ms_e2e * 1e-3), 'unit': 'users/s', 'h2d_bytes_per_step': res.pop('h2d_bytes_per_batch'),
+                'd2h_bytes_per_step': 96, 'timing': 'host wall clock: sweep call -> metric dict on the host'},
+        'roofline': {'kernel': 'eval_topk_tc_kernel', 'bound': 'tensor', 'unit': 'TFLOP/s',
+                     'achieved': res.get('tflops_batch', tf / world), 'peak': peaks['bf16_tflops'], 'peak_kind': 'burst bf16 (kernel timed alone)',
+                     'frac': res.get('tflops_batch', tf / world) / peaks['bf16_tflops'],
+                     'sweep': {'achieved_per_gpu': tf / world, 'peak': peaks['bf16_tflops_sustained'], 'peak_kind': 'sustained bf16 (inside a long sweep)',
+                               'frac': tf / world / peaks['bf16_tflops_sustained']},
+                     'algorithmic_flops_per_user': 2.0 * I * d, 'traffic': None, 'peak_source': peaks['source']},
+        'data_gen_s': gen_s,
+    })
+    return res
+
+
+def run_ours(args, wl):
+    import torch
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        return run_ours_sharded(args, wl)
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    D = _Dist(1, dev)
+    name, d, B, N, loss, lr, wd = wl
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    m = bench_train_single(args, args.workload, wl, dev, D, flush=flush)
+    U, I, K = m['U'], m['I'], m['K']
+    ab = algorithmic_bytes(U, I, d, B, N)
+    peaks = load_peaks()
+    triples = B * N
+    ms_step = m['ms_timed'] / K
+    dom = max(m['kernels_ms'], key=m['kernels_ms'].get)
+    dom_bytes = ab['gather_scatter'] if dom == 'hsk_mf_train_fused' else ab['adamw']
+    achieved = dom_bytes / (m['kernels_ms'][dom] * 1e-3) / 1e9
+    tr = committed_traffic(args.workload, dom)
+    big = name in DEVICE_GENERATED
+    line = {
+        'metric': 'BPR-MF train triples/s', 'value': triples * K / (m['ms_timed'] * 1e-3), 'unit': 'triples/s',
+        'n_gpus': 1, 'steps': K, 'warmup': m['W'], 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, wl, U, I, 1),
+        'value_back_to_back': triples * K / (m['ms_warm'] * 1e-3),
+        'value_sustained': triples * m['n_sus'] / (m['ms_sus'] * 1e-3), 'sustained_steps': m['n_sus'],
+        'samples_per_s': B * K / (m['ms_timed'] * 1e-3), 'train_interactions': m['n_train'],
+        'e2e': {'value': triples * K / (m['ms_e2e'] * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': m['h2d'],
+                'd2h_bytes_per_step': 8, 'ms_per_step': m['ms_e2e'] / K, 'wall_ms_per_step': m['wall_e2e'] / K},
+        'gpu_launches': m['launches_per_step'] * K,
+        'kernels_ms': m['kernels_ms'],
+        'roofline': {'kernel': dom, 'bound': 'hbm' if big else 'l2 (tables + optimizer state are L2-resident: not an HBM fraction)',
+                     'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                     'traffic': tr['bytes'] if tr else None, 'traffic_source': tr.get('capture') if tr else None,
+                     'peak_source': peaks['source'], 'algorithmic_bytes_per_launch': dom_bytes,
+                     'algorithmic_bytes_note': 'SURVEY 8d: 28 B / parameter (AdamW) and 2A + small (fused gather / scatter); the rows '
+                                               'kernel moves 24 B for untouched rows, so the algorithmic figure can exceed the DRAM traffic',
+                     'step': {'algorithmic_bytes': ab['total'], 'achieved': ab['total'] / (ms_step * 1e-3) / 1e9,
+                              'frac': ab['total'] / (ms_step * 1e-3) / 1e9 / peaks['hbm_gbs']}},
+        'clocks': m['clocks'],
+        'final_loss': m['final_loss'],
+    }
+    host_batches, data = m.pop('host_batches'), m.pop('data')
+    m.pop('model')
+    torch.cuda.empty_cache()
+    if not args.no_eval:
+        try:
+            line['eval'] = bench_eval(args, dev, D, 1, 0)
+        except Exception as ex:
+            line['eval'] = {'error': repr(ex)}
+        torch.cuda.empty_cache()
+    if not args.no_also and big:
+        also = {}
+        for w2 in ('cfg2', 'cfg3'):
+            try:
+                a2 = argparse.Namespace(**vars(args))
+                a2.steps = min(args.steps, 100)
+                m2 = bench_train_single(a2, w2, WORKLOADS[w2], dev, D, want_e2e=True, flush=flush)
+                n2, d2, B2, N2 = WORKLOADS[w2][0], WORKLOADS[w2][1], WORKLOADS[w2][2], WORKLOADS[w2][3]
+                ab2 = algorithmic_bytes(m2['U'], m2['I'], d2, B2, N2)
+                ms2 = m2['ms_timed'] / m2['K']
+                also[w2] = {'value': B2 * N2 / (ms2 * 1e-3), 'unit': 'triples/s', 'ms_per_step': ms2,
+                            'value_l2_warm': B2 * N2 * m2['K'] / (m2['ms_warm'] * 1e-3),
+                            'e2e': {'value': B2 * N2 * m2['K'] / (m2['ms_e2e'] * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': m2['h2d'],
+                                    'd2h_bytes_per_step': 8},
+                            'kernels_ms': m2['kernels_ms'], 'l2': 'flushed between timed steps',
+                            'algorithmic_gbs': ab2['total'] / (ms2 * 1e-3) / 1e9,
+                            'roofline_note': 'tables + optimizer state fit the 126 MB L2 (cfg2 63 MB, cfg3 165 MB borderline): the step is '
+                                             'L2 / issue bound, so no HBM fraction is quoted for it — see profiles/ for lts throughput',
+                            'config': workload_config(w2, WORKLOADS[w2], m2['U'], m2['I'], 1)}
+                if w2 == 'cfg2' and not args.no_cpu_baseline:
+                    us2, its2 = m2['host_batches']
+                    try:
+                        also[w2]['cpu_baseline'] = cpu_baseline(WORKLOADS[w2], m2['data'], us2, its2, budget_s=8.0)
+                        also[w2]['eval_cpu_baseline'] = cpu_eval_baseline(WORKLOADS[w2], m2['data'])
+                    except Exception as ex:
+                        also[w2]['cpu_baseline'] = {'error': repr(ex)}
+                    # the cfg2 full-rank evaluation (fp32 exact) through the public API
+                    try:
+                        also[w2]['eval'] = small_eval(m2['model'], m2['data'], dev)
+                    except Exception as ex:
+                        also[w2]['eval'] = {'error': repr(ex)}
+                del m2
+            except Exception as ex:
+                also[w2] = {'error': repr(ex)}
+            torch.cuda.empty_cache()
+        try:
+            also['loaders'] = bench_sampler_and_fit(dev)
+        except Exception as ex:
+            also['loaders'] = {'error': repr(ex)}
+        line['also'] = also
+    if not args.no_cpu_baseline:
+        try:   # never lose the GPU numbers to a baseline problem
+            if big:
+                line['cpu_baseline'] = cpu_baseline(wl, budget_s=15.0)
+            else:
+                line['cpu_baseline'] = cpu_baseline(wl, data, host_batches[0], host_batches[1])
+        except Exception as ex:
+            line['cpu_baseline'] = {'error': repr(ex)}
+        if not args.no_eval and isinstance(line.get('eval'), dict) and 'error' not in line['eval']:
+            try:
+                line['eval']['cpu_baseline'] = cpu_eval_baseline_cfg5()
+            except Exception as ex:
+                line['eval']['cpu_baseline'] = {'error': repr(ex)}
+    print(json.dumps(line), flush=True)
+
+
+def small_eval(model, data, dev):
+    import torch
+    from hassaku_b200.data.dataset import FullEvalDataset
+    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, data.n_user_groups)
+
+    class _Loader:
+        dataset, batch_size = ds, 8192
+
+    def once():
+        return evaluate_recommender_algorithm(model, _Loader, FullEvaluator(True, ds.n_user_groups, ds.user_to_user_group), dev)
+
+    once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        res = once()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / 5
+    return {'metric': 'full-rank eval users/s', 'value': data.n_users / (ms * 1e-3), 'unit': 'users/s', 'ms_per_sweep': ms,
+            'ndcg@10': res['ndcg@10'], 'users': data.n_users, 'precision': 'fp32 exact',
+            'timing': 'host wall clock incl. the single D2H sync of the sweep'}
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours_sharded(args, wl):
     """Cleanup wrapper: captured CUDA graphs hold NCCL work and dist.destroy_process_group() blocks until they are
     dropped, so ShardedMF.close() must run even when the body raises (a stalled rank would hold the GPU box)."""
@@ -371,358 +867,313 @@ def run_ours_sharded(args, wl):
         faulthandler.cancel_dump_traceback_later()
     finally:
         for smf in holder:
-            smf.close()
+            try:
+                smf.close()
+            except Exception:
+                pass
         if dist.is_initialized():
             dist.destroy_process_group()
 
 
-def _run_ours_sharded(args, wl, holder):
-    """N > 1: the item-/user-sharded step (hassaku_b200/sharded.py) with a per-GPU batch of `train_batch_size` samples
-    (weak scaling: global batch = N x 8192), NCCL all-to-all for the row / gradient exchanges."""
+def parity_check_train(smf, full_sd, u_loc, i_loc, B, N, loss, shift, lr, wd, dev, rank, world, d):
+    """One sharded step (eager sparse exchange) against the single-GPU step on the union batch, on rank 0."""
     import torch
     import torch.distributed as dist
-    from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
-    from hassaku_b200.data.dataset import FullEvalDataset
-    from hassaku_b200.data.synthetic import make_named
-    from hassaku_b200.eval.eval import FullEvaluator
-    from hassaku_b200.sharded import ShardedMF
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    from hassaku_b200.train.optim import DenseAdam
+    u_all = torch.empty(world * B, dtype=torch.int64, device=dev)
+    i_all = torch.empty((world * B, N + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(u_all, u_loc)
+    dist.all_gather_into_tensor(i_all, i_loc)
+    smf.loss_accum.zero_()
+    smf.step(u_loc, i_loc, B * world, loss, shift, lr, wd, exchange='sparse')
+    l_sh = smf.pop_loss()
+    got = smf.full_state_dict(to_cpu=False)
+    smf.check_status()
+    ok, worst = True, {}
+    if rank == 0:
+        U, I = full_sd['user_embeddings.weight'].shape[0], full_sd['item_embeddings.weight'].shape[0]
+        lay = ArenaLayout(U, I, d, False, True, False)
+
+        class _M:
+            pass
+        mdl = _M()
+        mdl.layout = lay
+        mdl.arena = torch.zeros(lay.n_total, device=dev)
+        Uw, Vw, _, Ib, _ = lay.views(mdl.arena)
+        Uw.copy_(full_sd['user_embeddings.weight']); Vw.copy_(full_sd['item_embeddings.weight']); Ib.copy_(full_sd['item_bias.weight'])
+        mdl.parameters = lambda: [torch.nn.Parameter(mdl.arena[:4])]
+        opt = DenseAdam(mdl, lr=lr, weight_decay=wd)
+        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        _C.mf_train_fused(lay.tables(mdl.arena), opt.grad_tables, u_all, i_all, _C.LOSS_KINDS[loss], shift, acc)
+        opt.mark(u_all, i_all)
+        opt.step_fused()
+        l_single = float(acc.item())
+        ok = abs(l_single - l_sh) <= 1e-5 * abs(l_single)
+        worst['loss'] = abs(l_single - l_sh) / abs(l_single)
+        for name_, w in zip(('user_embeddings.weight', 'item_embeddings.weight', 'item_bias.weight'), (Uw, Vw, Ib)):
+            a, b = got[name_].double(), w.double()
+            # max-norm relative error per step from a synchronised state (SURVEY 8d); + the documented Adam-eps conditioning term
+            err = float((a - b).abs().max() / b.abs().max())
+            worst[name_] = err
+            ok = ok and err < 1e-5 + 2e-3 * lr
+        del mdl, opt
+    del got
+    torch.cuda.empty_cache()
+    return ok, worst
+
+
+def _run_ours_sharded(args, wl, holder):
+    """N > 1: the item-/user-sharded step (hassaku_b200/sharded.py) with a per-GPU batch of `train_batch_size` samples
+    (weak scaling: global batch = N x 8192), device routing + NCCL all-to-all, captured as one CUDA graph."""
+    import torch
+    import torch.distributed as dist
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    from hassaku_b200.data.synthetic import make_device_interactions
+    from hassaku_b200.sharded import ShardedMF, exchange_capacity
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist.init_process_group('nccl', device_id=dev)
+    D = _Dist(world, dev)
     name, d, B, N, loss, lr, wd = wl
-    data = make_named(name)
-    U, I = data.n_users, data.n_items
-    K, W = args.steps, max(args.warmup, 0)
-    torch.manual_seed(64)
-    full = SGDMatrixFactorization(U, I, d, use_item_bias=True)
-    smf = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
-    holder.append(smf)
-    smf.load_full_state_dict(full.state_dict())
-    del full
-    shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
-    # local batches: B samples whose user this rank owns
-    import scipy.sparse as sp
-    tr = data.train.tocsr()
-    mine = sp.csr_matrix(tr[np.arange(rank, U, world)])
-    sub = type('D', (), {})()
-    sub.train, sub.n_items = sp.csr_matrix((mine.data, mine.indices, mine.indptr), shape=(mine.shape[0], I)), I
-    us, its = make_batches(sub, B, N, 8, seed=64 + rank)
-    us = [u * world + rank for u in us]                              # local row -> global user id
-    u_dev = [torch.from_numpy(x).to(dev) for x in us]
-    i_dev = [torch.from_numpy(x).to(dev) for x in its]
+    big = name in DEVICE_GENERATED
+    K, W = args.steps, max(args.warmup, 3)
     Bg = B * world
+    n_distinct = 16
+    exchange = args.exchange
+    if big:
+        U, I, n_inter = shapes_of(name)
+        data = make_device_interactions(U, I, n_inter, dev, world, rank, seed=0)
+        u_dev, i_dev = make_device_batches(data, B, N, n_distinct, seed=64 + rank)
+        n_train = int(data.rows.numel())
+        del data
+    else:
+        import scipy.sparse as sp
+        from hassaku_b200.data.synthetic import make_named
+        hd = make_named(name)
+        U, I = hd.n_users, hd.n_items
+        mine = sp.csr_matrix(hd.train.tocsr()[np.arange(rank, U, world)])
+        sub = type('D', (), {})()
+        sub.train, sub.n_items = sp.csr_matrix((mine.data, mine.indices, mine.indptr), shape=(mine.shape[0], I)), I
+        us, its = make_batches(sub, B, N, n_distinct, seed=64 + rank)
+        u_dev = [torch.from_numpy(u * world + rank).to(dev) for u in us]     # local row -> global user id
+        i_dev = [torch.from_numpy(x).to(dev) for x in its]
+        n_train = int(mine.nnz)
+        if exchange.startswith('sparse') and B * (N + 1) >= 2 * I // world:
+            exchange = 'dense_graph'        # the batch covers the item table: dense exchange (see ShardedMF.step)
+    torch.cuda.empty_cache()
 
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
+    # every rank draws the SAME full tables on its device (same seed, same generator) and keeps its rows; rank 0 keeps the
+    # full copy for the parity check
+    def full_tables(U_, I_, d_, std, seed):
+        lay = ArenaLayout(U_, I_, d_, False, True, False)
+        arena = torch.zeros(lay.n_total, dtype=torch.float32, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        Uw, Vw, _, Ib, _ = lay.views(arena)
+        for v, s_ in ((Uw, std[0] if std else 0.1 / d_), (Vw, std[0] if std else 0.1 / d_), (Ib, std[1] if std else 0.1)):
+            v.normal_(0., s_, generator=gen)
+        return {'user_embeddings.weight': Uw, 'item_embeddings.weight': Vw, 'item_bias.weight': Ib}
+
+    def make_smf(U_, I_, d_, std, seed, keep_full=False):
+        sd = full_tables(U_, I_, d_, std, seed)
+        s = ShardedMF(U_, I_, d_, use_item_bias=True, world=world, rank=rank, device=dev)
+        holder.append(s)
+        s.load_full_state_dict(sd)
+        return (s, sd) if keep_full else s
+
+    shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
+    smf, full_sd = make_smf(U, I, d, None, 64, keep_full=True)
+    # ---- parity self-check (outside every timed region) ----
+    parity = {'train': None, 'eval': None}
+    try:
+        ok, worst = parity_check_train(smf, full_sd, u_dev[0], i_dev[0], B, N, loss, shift, lr, wd, dev, rank, world, d)
+        parity['train'] = {'ok': bool(ok), 'max_rel_err': worst,
+                           'what': 'one sharded step (sparse exchange) vs the single-GPU step on the union batch, from the same state'}
+    except Exception as ex:
+        parity['train'] = {'ok': False, 'error': repr(ex)}
+    # fresh state for the measurement
+    smf.load_full_state_dict(full_sd)
+    for t_ in (smf.m, smf.v, smf.g):
+        t_.zero_()
+    smf.t = 0
+    smf.loss_accum.zero_()
+    del full_sd
+    torch.cuda.empty_cache()
+
+    def step(s, host=None):
+        if host is None:
+            smf.step(u_dev[s % n_distinct], i_dev[s % n_distinct], Bg, loss, shift, lr, wd, exchange=exchange)
+        else:
+            smf.step(host[0][s % n_distinct], host[1][s % n_distinct], Bg, loss, shift, lr, wd, exchange=exchange)
 
     # the W warm-up steps asked for, and at least 30: the first replays of a freshly captured graph with NCCL nodes are slow
     for s in range(max(W, 30)):
-        smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+        step(s)
     smf.pop_loss()      # reset the loss accumulator (collective: every rank calls it)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    smf.check_status()
+    p0, p1 = _events(2)
+    a, b = _events(2)
     # rank 0 samples the clocks of every GPU of the job; its start-up is over before the barrier that opens the region
     with ClockSampler(','.join(str(g) for g in range(world)), enabled=(rank == 0)) as clk:
         clk.wait_ready()
-        barrier()
+        D.barrier()
         # (i) pilot region: K steps, only to size the sustained run (reported as `pilot_ms_per_step`)
         p0.record()
         for s in range(K):
-            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+            step(s)
         p1.record()
-        barrier()
+        D.barrier()
         # every step holds collectives, so step counts must be the SAME on every rank: derive them from max-over-ranks times
-        t_pilot = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_pilot, op=dist.ReduceOp.MAX)
+        t_pilot = D.max(p0.elapsed_time(p1))
         # (ii) sustained run (>= 1.5 s, untimed): clocks settle under load and the sampler sees it
-        n_sus = max(K, int(1500.0 / max(float(t_pilot.item()) / K, 1e-3)))
+        n_sus = max(K, int(1500.0 / max(t_pilot / K, 1e-3)))
         for s in range(n_sus):
-            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
-        barrier()
+            step(s)
+        D.barrier()
         # (iii) THE timed region: exactly K steps between barrier + synchronize, max over ranks
         a.record()
         for s in range(K):
-            smf.step(u_dev[s % 8], i_dev[s % 8], Bg, loss, shift, lr, wd, exchange=args.exchange)
+            step(s)
         b.record()
-        barrier()
-    t_all = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    ms = float(t_all.item())
+        D.barrier()
+    ms = D.max(a.elapsed_time(b))
     last_loss = smf.pop_loss() / (2 * K + n_sus)
-    # e2e: host batches
-    u_pin = [torch.from_numpy(x).pin_memory() for x in us]
-    i_pin = [torch.from_numpy(x).pin_memory() for x in its]
-    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    smf.check_status()
+    # e2e: host (pinned) batches, H2D per step, loss D2H at the end of the region
+    u_pin = [x.cpu().pin_memory() for x in u_dev]
+    i_pin = [x.cpu().pin_memory() for x in i_dev]
+    for s in range(3):
+        step(s, (u_pin, i_pin))
+    smf.pop_loss()
+    a2, b2 = _events(2)
+    D.barrier()
     a2.record()
     for s in range(K):
-        smf.step(u_pin[s % 8].to(dev, non_blocking=True), i_pin[s % 8].to(dev, non_blocking=True), Bg, loss, shift, lr, wd,
-                 exchange=args.exchange)
+        step(s, (u_pin, i_pin))
     loss_host = smf.pop_loss()
     b2.record()
-    barrier()
-    t2 = torch.tensor([a2.elapsed_time(b2)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t2.item())
-    # sharded full-rank evaluation (first sweep warms NCCL's all-gather / all-to-all channels up)
-    u2g = torch.from_numpy(data.user_group).float() if data.user_group is not None else None
-    smf.evaluate(data.val, data.train, FullEvaluator(True, data.n_user_groups, u2g), batch_size=8192)
-    barrier()
-    ev_t0 = time.perf_counter()
-    for _ in range(3):
-        res = smf.evaluate(data.val, data.train, FullEvaluator(True, data.n_user_groups, u2g), batch_size=8192)
-    torch.cuda.synchronize()
-    eval_ms = (time.perf_counter() - ev_t0) * 1e3 / 3
+    D.barrier()
+    ms_e2e = D.max(a2.elapsed_time(b2))
+    assert math.isfinite(loss_host), 'training diverged'
+    # per-kernel view of one EAGER step on rank 0's stream (collectives included): which part limits the step
+    eager = 'sparse' if exchange.startswith('sparse') else 'dense'
+    e0, e1 = _events(2)
+    D.barrier()
+    e0.record()
+    for s in range(10):
+        smf.step(u_dev[s % n_distinct], i_dev[s % n_distinct], Bg, loss, shift, lr, wd, exchange=eager)
+    e1.record()
+    D.barrier()
+    ms_eager = D.max(e0.elapsed_time(e1)) / 10
+    capq = exchange_capacity(B * (N + 1), I, world)
+    smf.close()
+    holder.remove(smf)
+    del smf
+    torch.cuda.empty_cache()
+
+    ev = None
+    if not args.no_eval:
+        try:
+            # parity of the sharded evaluation: one round against rank 0's single-GPU scorer on the same users
+            ev = bench_eval(args, dev, D, world, rank, smf_factory=lambda U_, I_, d_, std, seed: make_smf(U_, I_, d_, std, seed))
+        except Exception as ex:
+            ev = {'error': repr(ex)}
+        try:
+            parity['eval'] = parity_check_eval(make_smf, holder, dev, rank, world)
+        except Exception as ex:
+            parity['eval'] = {'ok': False, 'error': repr(ex)}
     if rank == 0:
         ab = algorithmic_bytes(U, I, d, B, N)
-        peak, peak_src = measured_peaks()
+        peaks = load_peaks()
         triples = Bg * N
-        cfg = workload_config(args.workload, wl, U, I)
-        cfg.update({'parallelism': f'item+user row-sharded x{world}, NCCL ({args.exchange} exchange)', 'global_batch': Bg,
-                    'l2': 'not flushed (back to back); tables are L2-resident'})
+        per_gpu_bytes = ab['gather_scatter'] + ab['adamw'] // world
+        ms_step = ms / K
+        pc_ok = all(v is None or v.get('ok') for v in parity.values())
         line = {'metric': 'BPR-MF train triples/s', 'value': triples * K / (ms * 1e-3), 'unit': 'triples/s', 'n_gpus': world,
-                'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+                'steps': K, 'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.workload, wl, U, I, world),
+                'samples_per_s': Bg * K / (ms * 1e-3), 'train_interactions_per_rank': n_train,
                 'e2e': {'value': triples * K / (ms_e2e * 1e-3), 'unit': 'triples/s',
-                        'h2d_bytes_per_step': int(us[0].nbytes + its[0].nbytes) * world, 'd2h_bytes_per_step': 8,
+                        'h2d_bytes_per_step': int(u_pin[0].numel() * 8 + i_pin[0].numel() * 8) * world, 'd2h_bytes_per_step': 8,
                         'ms_per_step': ms_e2e / K},
-                'gpu_launches': 4 * K * world,
-                'roofline': {'kernel': 'hsk_mf_train_fused_n', 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s',
-                             'frac': None, 'traffic': None, 'peak_source': peak_src,
-                             'step': {'algorithmic_bytes_per_gpu': 2 * ab['A'] + 28 * ab['P'] // world,
-                                      'note': 'per-kernel roofline is reported by the N = 1 run'}},
+                'gpu_launches': 14 * K * world,
+                'gpu_launches_note': 'per rank and step, own kernels inside the graph: route (5) + pack + local_index + mark_rows + fused + '
+                                     'unpack_add + adamw_rows = 11, + 3 NCCL all-to-all kernels',
+                'exchange': {'kind': exchange, 'capq_rows_per_owner': capq,
+                             'bytes_per_gpu_per_direction': int(2 * world * (capq + math.ceil(capq / 128)) * 128 * 4) if exchange.startswith('sparse') else None,
+                             'eager_ms_per_step': ms_eager, 'graph_ms_per_step': ms_step},
+                'roofline': {'kernel': 'whole step (per GPU)', 'bound': 'hbm', 'unit': 'GB/s',
+                             'achieved': per_gpu_bytes / (ms_step * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                             'frac': per_gpu_bytes / (ms_step * 1e-3) / 1e9 / peaks['hbm_gbs'], 'traffic': None,
+                             'peak_source': peaks['source'], 'algorithmic_bytes_per_gpu': per_gpu_bytes,
+                             'note': 'per-GPU algorithmic bytes = 2A + small (its 8192-sample batch) + 28 P / N (its shard); the step also '
+                                     'moves the exchanged rows over NVLink, which this HBM figure does not count'},
                 'clocks': clk.summary(),
-                'pilot_ms_per_step': float(t_pilot.item()) / K,
-                'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
-                         'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U},
+                'pilot_ms_per_step': t_pilot / K,
+                'parity_check': 'ok' if pc_ok else 'FAILED', 'parity': parity,
                 'final_loss': last_loss}
+        if ev is not None:
+            line['eval'] = ev
         print(json.dumps(line), flush=True)
     dist.barrier()
 
 
-def run_ours(args, wl):
+def parity_check_eval(make_smf, holder, dev, rank, world):
+    """One sharded evaluation round (bf16 tensor-core scoring of the local shard + fp32 re-scoring + merge) against the
+    single-GPU scorer on rank 0: identical metric dict (ids are identical unless fp32 scores tie)."""
     import torch
-    import torch.distributed as dist
-    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        return run_ours_sharded(args, wl)
-    from hassaku_b200 import _C
+    from scipy import sparse as sp
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
-    from hassaku_b200.data.dataset import FullEvalDataset
-    from hassaku_b200.data.synthetic import make_named
-    from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
-    from hassaku_b200.train.optim import DenseAdam
-    from hassaku_b200.train.rec_losses import RecommenderSystemLossesEnum
-    from hassaku_b200.train.trainer_step import FusedMFTrainStep
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    name, d, B, N, loss, lr, wd = wl
-    data = make_named(name)
-    U, I = data.n_users, data.n_items
-    K, W = args.steps, max(args.warmup, 0)
-
-    init_like_reference(None)
-    model = SGDMatrixFactorization(U, I, d, use_item_bias=True).to(dev)
-
-    class _DS:
-        n_items = I
-
-    loss_fn = RecommenderSystemLossesEnum[loss].value.build_from_conf({'train_neg_strategy': 'uniform', 'neg_train': N},
-                                                                      _DS())
-    opt = DenseAdam(model, lr=lr, weight_decay=wd, decoupled=True)
-    step = FusedMFTrainStep(model, loss_fn, opt)
-
-    n_distinct = 16
-    us, its = make_batches(data, B, N, n_distinct, seed=64 + rank)
-    u_dev = [torch.from_numpy(x).to(dev) for x in us]
-    i_dev = [torch.from_numpy(x).to(dev) for x in its]
-    u_pin = [torch.from_numpy(x).pin_memory() for x in us]
-    i_pin = [torch.from_numpy(x).pin_memory() for x in its]
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    # ---- (1) resident inputs, L2 flushed between timed steps ----
-    for s in range(W):
-        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    barrier()
-    clk = ClockSampler(local_rank)
-    clk.__enter__()   # samples clocks / throttle reasons across every timed region below (stopped after region 2b)
-    clk.wait_ready()
-    barrier()
-    for s in range(K):
-        flush.zero_()
-        ev0[s].record()
-        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
-        ev1[s].record()
-    barrier()
-    ms_flushed = max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
-
-    # ---- (2) back to back (L2 warm), one event pair around K steps ----
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    a.record()
-    for s in range(K):
-        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
-    b.record()
-    barrier()
-    ms_warm = max_over_ranks(a.elapsed_time(b))
-
-    # ---- (2b) sustained: back-to-back steps for >= 1.5 s so that the clock / power samples see the load ----
-    n_sus = max(K, int(1500.0 / max(ms_warm / K, 1e-3)))
-    a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a3.record()
-    for s in range(n_sus):
-        step(u_dev[s % n_distinct], i_dev[s % n_distinct])
-    b3.record()
-    barrier()
-    ms_sus = max_over_ranks(a3.elapsed_time(b3))
-    clk.__exit__()
-
-    # ---- (3) per-kernel durations (events between the two launches), L2 flushed ----
-    tabs, gtabs = model._tables(), opt.grad_tables
-    kind, shift = _C.LOSS_KINDS[loss_fn.loss_kind], float(loss_fn.neg_shift())
-    e = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    barrier()
-    for s in range(K):
-        flush.zero_()
-        e[s][0].record()
-        _C.mf_train_fused(tabs, gtabs, u_dev[s % n_distinct], i_dev[s % n_distinct], kind, shift, step.loss_accum,
-                          status=model._status())
-        e[s][1].record()
-        opt.step_fused()
-        e[s][2].record()
-    barrier()
-    ms_fused = sum(x[0].elapsed_time(x[1]) for x in e) / K
-    ms_adamw = sum(x[1].elapsed_time(x[2]) for x in e) / K
-
-    # ---- (4) end to end through the public API with HOST batches ----
-    loss_pin = torch.zeros(K, dtype=torch.float64).pin_memory()
-    loss_dev = torch.zeros(K, dtype=torch.float64, device=dev)
-    for s in range(min(W, 3)):
-        step(u_pin[s % n_distinct], i_pin[s % n_distinct])
-    a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    a2.record()
-    for s in range(K):
-        step(u_pin[s % n_distinct], i_pin[s % n_distinct], loss_out=loss_dev[s:s + 1])
-        loss_pin[s:s + 1].copy_(loss_dev[s:s + 1], non_blocking=True)
-    b2.record()
-    barrier()
-    wall_e2e = (time.perf_counter() - t_wall0) * 1e3
-    ms_e2e = max_over_ranks(max(a2.elapsed_time(b2), 0.0))
-    last_loss = float(loss_pin[K - 1])
-    model.check_status()
-    assert math.isfinite(last_loss), 'training diverged'
-
-    # ---- (5) full-rank evaluation sweep (all users, top-100, 12 metrics) ----
-    ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, data.n_user_groups)
-
-    class _Loader:
-        dataset, batch_size = ds, 8192
-
-    def eval_once():
-        ev = FullEvaluator(True, ds.n_user_groups, ds.user_to_user_group)
-        return evaluate_recommender_algorithm(model, _Loader, ev, dev)
-
-    eval_once()
-    barrier()
-    t0 = time.perf_counter()
-    n_eval = 5
-    for _ in range(n_eval):
-        res = eval_once()
-    torch.cuda.synchronize()
-    eval_ms = (time.perf_counter() - t0) * 1e3 / n_eval
-
-    extras = {}
-    if rank == 0 and not args.no_extras:
-        extras = run_extras(dev, flush)
-    if rank != 0:
-        return
-    ab = algorithmic_bytes(U, I, d, B, N)
-    peak, peak_src = measured_peaks()
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this same command
-    # (profiles/r01_ncu_step_kernels.md, L2 flushed before each launch): the tables are L2-resident, so DRAM traffic is far
-    # BELOW the algorithmic bytes — the kernel is L2 / issue bound at this shape, not HBM bound
-    ncu_traffic = {'hsk_mf_train_fused': 30.1e6, 'hsk_adamw_dense': 69.7e6}
-    dom = 'hsk_mf_train_fused' if ms_fused >= ms_adamw else 'hsk_adamw_dense'
-    dom_bytes = ab['gather_scatter'] if dom == 'hsk_mf_train_fused' else ab['adamw']
-    dom_ms = max(ms_fused, ms_adamw)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    triples = B * N * world
-    line = {
-        'metric': 'BPR-MF train triples/s', 'value': triples * K / (ms_flushed * 1e-3), 'unit': 'triples/s',
-        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_flushed / K, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.workload, wl, U, I),
-        'value_l2_warm': triples * K / (ms_warm * 1e-3), 'ms_per_step_l2_warm': ms_warm / K,
-        'value_sustained': triples * n_sus / (ms_sus * 1e-3), 'sustained_steps': n_sus,
-        'samples_per_s': B * world * K / (ms_flushed * 1e-3),
-        'e2e': {'value': triples * K / (ms_e2e * 1e-3), 'unit': 'triples/s',
-                'h2d_bytes_per_step': int(us[0].nbytes + its[0].nbytes), 'd2h_bytes_per_step': 8,
-                'ms_per_step': ms_e2e / K, 'wall_ms_per_step': wall_e2e / K},
-        'gpu_launches': 2 * K,
-        'kernels_ms': {'hsk_mf_train_fused': ms_fused, 'hsk_adamw_dense': ms_adamw},
-        'roofline': {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': ncu_traffic[dom], 'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': dom_bytes,
-                     'step': {'algorithmic_bytes': ab['total'], 'achieved': ab['total'] / (ms_flushed / K * 1e-3) / 1e9,
-                              'frac': ab['total'] / (ms_flushed / K * 1e-3) / 1e9 / peak},
-                     'note': 'tables + optimizer state (63 MB) are L2-resident: algorithmic GB/s may exceed DRAM peak'},
-        'clocks': clk.summary(),
-        'eval': {'metric': 'full-rank eval users/s', 'value': U / (eval_ms * 1e-3), 'unit': 'users/s',
-                 'ms_per_sweep': eval_ms, 'ndcg@10': res['ndcg@10'], 'users': U, 'timing': 'host wall clock incl. the '
-                 'single D2H sync of the sweep'},
-        'final_loss': last_loss,
-        'extras': extras,
-    }
-    if not args.no_cpu_baseline:
-        try:
-            line['cpu_baseline'] = cpu_baseline(wl, data, us, its)
-        except Exception as ex:  # never lose the GPU numbers to a baseline problem
-            line['cpu_baseline'] = {'error': repr(ex)}
-        try:
-            line['eval']['cpu_baseline'] = cpu_eval_baseline(wl, data)
-        except Exception as ex:
-            line['eval']['cpu_baseline'] = {'error': repr(ex)}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    from hassaku_b200.eval.eval import DeviceCSR, FullEvaluator, evaluate_mf_sweep
+    U, I, d, bs = 4096, 200_003, 256, 256
+    std = (1.0 / math.sqrt(d), 0.05)
+    smf, sd = make_smf(U, I, d, std, 77, keep_full=True)
+    rng = np.random.RandomState(3)
+    rows = np.repeat(np.arange(U), 40)
+    ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+    lab = sp.csr_matrix((np.ones(U * 8, dtype=np.int8), (np.repeat(np.arange(U), 8), rng.randint(0, I, U * 8))), shape=(U, I))
+    ex.sum_duplicates(); ex.sort_indices(); lab.sum_duplicates(); lab.data[:] = 1; lab.sort_indices()
+    exd, labd = DeviceCSR(ex, dev), DeviceCSR(lab, dev)
+    n_rounds = 2
+    got = smf.evaluate(labd, exd, FullEvaluator(True, 0, None), batch_size=bs, precision='bf16', max_rounds=n_rounds)
+    smf.check_status()
+    out = {'ok': True, 'what': f'{n_rounds} sharded evaluation rounds ({n_rounds * bs * world} users x {I} items, bf16 + fp32 re-scoring) vs the '
+                               f'single-GPU sweep over the same users'}
+    if rank == 0:
+        model = SGDMatrixFactorization.on_device(U, I, d, use_item_bias=True, device=dev, seed=1)
+        with torch.no_grad():
+            model.user_embeddings.weight.copy_(sd['user_embeddings.weight'])
+            model.item_embeddings.weight.copy_(sd['item_embeddings.weight'])
+            model.item_bias.weight.copy_(sd['item_bias.weight'])
+        model.eval_precision = 'bf16'
+        evl = FullEvaluator(True, 0, None)
+        evaluate_mf_sweep(model, labd, exd, evl, n_rounds * bs * world, 1024)
+        want = evl.get_results()
+        diff = max(abs(got[k_] - v) for k_, v in want.items())
+        out.update({'ok': bool(diff <= 1e-9), 'max_metric_diff': diff, 'ndcg@10': got['ndcg@10']})
+        del model
+    smf.close()
+    holder.remove(smf)
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
-    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
-    ap.add_argument('--exchange', default='dense_graph', choices=['auto', 'dense', 'dense_graph', 'sparse'],
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU legs (profiling runs)')
+    ap.add_argument('--exchange', default='sparse_graph', choices=['sparse', 'sparse_graph', 'dense', 'dense_graph'],
                     help='N > 1: item-row exchange of the sharded step')
-    ap.add_argument('--no-extras', action='store_true', help='skip the cfg4 / cfg5-shaped kernel measurements')
+    ap.add_argument('--no-eval', action='store_true', help='skip the cfg5 full-rank evaluation sweep')
+    ap.add_argument('--no-also', action='store_true', help='N = 1: skip the cfg2 / cfg3 / loader side lines')
+    ap.add_argument('--eval-users', type=int, default=0, help='bound the cfg5 sweep to this many users (0 = all 10 M)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

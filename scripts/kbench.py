@@ -1,5 +1,7 @@
 """Kernel micro-benchmarks (CUDA events, L2 flushed between launches) for A/B-ing kernel variants on the GPU box.
-    python scripts/kbench.py train [--workload cfg2] [--variants regs,tma]
+    python scripts/kbench.py train [--workload cfg2] [--variants regs,ring,q]
+    python scripts/kbench.py trainraw --users 2000000 --items 1000000 --dim 128 --batch 8192 --variants auto
+    python scripts/kbench.py eval --users 18944 --items 1000000 --dim 256 --batch 18944 --variants bf16,tf32
 """
 import argparse
 import os
@@ -46,7 +48,7 @@ def train(args):
     shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
     ab = bench.algorithmic_bytes(U, I, d, B, N)
     for v in args.variants.split(','):
-        os.environ['HSK_TRAIN_FUSED'] = v
+        _C.TRAIN_VARIANT = v
         k = [0]
 
         def fn():
@@ -80,7 +82,7 @@ def trainraw(args):
     shift = float(np.log(I / N)) if args.loss == 'sampled_softmax' else 0.0
     ab = 4 * d * B * (N + 2)
     for v in args.variants.split(','):
-        os.environ['HSK_TRAIN_FUSED'] = v
+        _C.TRAIN_VARIANT = v
         k = [0]
 
         def fn():
@@ -115,27 +117,11 @@ def evalk(args):
     users = torch.arange(B, device='cuda') % U
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     for prec in args.variants.split(','):
-        sc = TopKScorer(model, B, 100, prec)
+        sc = TopKScorer(model, B, 100, prec, rescore=not args.no_rescore)
         fn = lambda: sc(users, ex)
         for _ in range(2):
             fn()
         med, best = time_kernel(fn, args.iters, flush)
-        if os.environ.get('HSK_TC_PROFILE') and prec != 'fp32':
-            import ctypes
-            from hassaku_b200 import _C
-            cnt = torch.zeros(16, dtype=torch.int64, device='cuda')
-            _C.lib().hsk_debug_eval_tc_profile(ctypes.c_void_p(cnt.data_ptr()))
-            fn(); torch.cuda.synchronize()
-            _C.lib().hsk_debug_eval_tc_profile(None)
-            call = cnt.cpu().numpy().astype(float)
-            c = call[:6]
-            pr = call[6:11]
-            nw = (B + 127) // 128 * 8
-            names = ['wait_tfull', 'tmem_ld', 'bias+max+scan', 'pair_bar1', 'prune', 'pair_bar2']
-            print('   epilogue cycles per warp (k): ' + ', '.join(f'{n}={v/nw/1e3:.0f}' for n, v in zip(names, c)) + f'  total={c.sum()/nw/1e3:.0f}')
-            print(f'   per warp: appends={call[10]/nw:.0f} lane-scans={call[11]/nw:.0f} warp-scans={call[12]/nw:.0f} (of {2*((I+127)//128)} chunks)')
-            nc = max(call[13], 1)
-            print(f'   cuts/warp={call[13]/nw:.0f}; cycles per cut: load={call[6]/nc:.0f} excl={call[7]/nc:.0f} select={call[8]/nc:.0f} compact+store={call[9]/nc:.0f}')
         fl = 2.0 * B * I * d
         print(f'eval[{prec:4s}] U_b={B} I={I} d={d}: med {med:9.3f} ms best {best:9.3f} ms -> {B/med*1e3:12.0f} users/s '
               f'{fl/med/1e9:8.1f} TFLOP/s')
@@ -147,12 +133,13 @@ if __name__ == '__main__':
     ap.add_argument('--neg', type=int, default=50)
     ap.add_argument('--loss', default='bpr')
     ap.add_argument('--workload', default='cfg2')
-    ap.add_argument('--variants', default='regs,tma,tma2,q')
+    ap.add_argument('--variants', default='regs,ring,q')
     ap.add_argument('--users', type=int, default=6040)
     ap.add_argument('--items', type=int, default=3706)
     ap.add_argument('--dim', type=int, default=402)
     ap.add_argument('--batch', type=int, default=6040)
     ap.add_argument('--excl', type=int, default=80)
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--no-rescore', action='store_true', help='tensor-core modes: raw low-precision ranking (kernel alone)')
     a = ap.parse_args()
     {'train': train, 'trainraw': trainraw, 'eval': evalk}[a.what](a)
