@@ -24,6 +24,8 @@ TRAIN_VARIANTS = {'auto': 0, 'regs': 1, 'ring': 2, 'q': 3}   # HSK_TRAIN_* of hs
 # kernel choice used by mf_train_fused / mf_train_fused_n of THIS binding (parity tests and scripts/kbench.py set it; the
 # library itself holds no state: the variant is an argument of hsk_mf_train_fused_v)
 TRAIN_VARIANT = 'auto'
+EVAL_TC_VARIANTS = {'auto': 0, 'single': 1, 'pair': 2}      # HSK_EVAL_TC_* of hsk_eval_topk_tc_v
+EVAL_TC_VARIANT = 'auto'
 
 
 class HskError(RuntimeError):
@@ -84,6 +86,8 @@ def _declare(lib):
         'hsk_eval_topk_tc_scratch_bytes': (i64, [i32, i64, i32]),
         'hsk_eval_topk_tc': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp,
                                    i64, vp, vp]),
+        'hsk_eval_topk_tc_v': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp,
+                                     i64, vp, i32, vp]),
         'hsk_topk_merge': (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         'hsk_topk_dense': (i32, [vp, i32, i64, i64, i32, vp, vp, vp]),
         'hsk_rank_metrics': (i32, [vp, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
@@ -463,15 +467,15 @@ def eval_topk_tc_scratch_bytes(Be: int, n_local_items: int, k: int) -> int:
 
 def eval_topk_tc(Uq, Vq, precision: int, u_idx, n_users: int, k: int, top_scores, top_ids, scratch, Ub=None, Ib=None,
                  Gb=None, excl_indptr=None, excl_indices=None, id_offset: int = 0, id_stride: int = 1, status=None,
-                 u_rows=None):
+                 u_rows=None, variant: Optional[str] = None):
     _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
     Be, kpad = Uq.shape
     with _on_device_of(Uq, Vq, u_idx, top_scores, top_ids, scratch, Ub, Ib, Gb, excl_indptr, excl_indices, status, u_rows) as st:
-        _check(lib().hsk_eval_topk_tc(Uq.data_ptr(), Vq.data_ptr(), kpad, precision, _ptr(Ub), _ptr(Ib), _ptr(Gb),
-                                      u_idx.data_ptr(), _ptr(u_rows), Be, n_users, Vq.shape[0], id_offset, id_stride,
-                                      _ptr(excl_indptr), _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(),
-                                      scratch.data_ptr(), scratch.numel() * scratch.element_size(), _ptr(status), st),
-               'hsk_eval_topk_tc')
+        _check(lib().hsk_eval_topk_tc_v(Uq.data_ptr(), Vq.data_ptr(), kpad, precision, _ptr(Ub), _ptr(Ib), _ptr(Gb),
+                                        u_idx.data_ptr(), _ptr(u_rows), Be, n_users, Vq.shape[0], id_offset, id_stride,
+                                        _ptr(excl_indptr), _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(),
+                                        scratch.data_ptr(), scratch.numel() * scratch.element_size(), _ptr(status),
+                                        EVAL_TC_VARIANTS[variant or EVAL_TC_VARIANT], st), 'hsk_eval_topk_tc')
 
 
 def rescore_topk(tables: MfTables, u_rows, cand_ids, k: int, top_scores, top_ids, id_offset: int = 0, id_stride: int = 1,

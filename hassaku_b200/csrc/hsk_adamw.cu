@@ -213,56 +213,70 @@ struct AdamSegs {
 
 __host__ __device__ __forceinline__ int stamp_of_step(int64_t step) { return 1 + (int)(step % 255); }
 
-// One warp owns kRowsPerWarp consecutive rows per iteration: the stamp bytes are read first (one broadcast load per row),
-// then the p, m, v (and, for stamped rows only, g) loads of ALL its rows are issued before any arithmetic, so 12-16
-// independent 16-byte loads per lane are in flight (the per-element variant with a row lookup per float4 spent its time
-// in integer divisions and serialised stamp -> data loads: 1.88 ms instead of 1.5 ms at cfg4).  Rows longer than 32
-// float4 are walked in chunks of 32.
+// One warp owns kRowsPerWarp consecutive rows per iteration: the p, m, v loads of ALL its rows are issued before any
+// arithmetic (12 independent 16-byte loads per lane in flight), the g loads only for stamped rows; the stamp bytes are
+// fetched one iteration ahead.  Measured at cfg4 (385 M parameters, 0.35 M of 3 M rows stamped): a per-float4 variant
+// with a row lookup (integer division) per element 1.88 ms; this layout with the stamp load in front of the data loads
+// 2.34 ms (the latencies add up); see DESIGN.md for the current figure.  Rows longer than 32 float4 are walked in
+// chunks of 32.
 constexpr int kRowsPerWarp = 4;
 
+// row r of the concatenated segments -> (float4 index of its first vector, float4 per row, stamp byte); base -1 = no row
+__device__ __forceinline__ void adam_row_lookup(const AdamSegs& segs, int64_t r, int64_t& base, int& nvec, uint8_t& st) {
+    base = -1; nvec = 0; st = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < segs.n && r >= segs.s[k].row_begin && r < segs.s[k].row_begin + segs.s[k].n_rows) {
+            const int64_t rl = r - segs.s[k].row_begin;
+            nvec = segs.s[k].nvec;
+            base = (segs.s[k].offset >> 2) + rl * nvec;
+            st = __ldg(segs.s[k].stamps + rl);
+        }
+    }
+}
+
 template <int ARITH, bool L2, bool DECAY>
-__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                         float* __restrict__ g, AdamConsts c_host,
-                                                         const AdamConsts* __restrict__ c_dev, AdamSegs segs, int stamp_host,
-                                                         const int64_t* __restrict__ step_dev) {
+__global__ void __launch_bounds__(256, 2) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                            float* __restrict__ g, AdamConsts c_host,
+                                                            const AdamConsts* __restrict__ c_dev, AdamSegs segs, int stamp_host,
+                                                            const int64_t* __restrict__ step_dev) {
     const AdamConsts c = c_dev ? *c_dev : c_host;
     const uint8_t stamp = (uint8_t)(step_dev ? stamp_of_step(*step_dev) : stamp_host);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRowsPerWarp;
     const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * kRowsPerWarp;
+    // the row descriptors (incl. the stamp bytes) of the NEXT iteration are fetched while this one's rows stream, so the
+    // stamp load is never in front of the p / m / v loads
+    int64_t base[kRowsPerWarp], nbase[kRowsPerWarp];
+    int nvec[kRowsPerWarp], nnvec[kRowsPerWarp];
+    uint8_t st[kRowsPerWarp], nst[kRowsPerWarp];
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) adam_row_lookup(segs, warp0 + q, nbase[q], nnvec[q], nst[q]);
     for (int64_t r0 = warp0; r0 < segs.total_rows; r0 += stride) {
-        int64_t base[kRowsPerWarp];   // float4 index of the row's first vector, -1 = no row
-        int nvec[kRowsPerWarp];
-        bool touched[kRowsPerWarp];
         int max_nvec = 0;
 #pragma unroll
         for (int q = 0; q < kRowsPerWarp; ++q) {
-            const int64_t r = r0 + q;
-            base[q] = -1; nvec[q] = 0; touched[q] = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < segs.n && r >= segs.s[k].row_begin && r < segs.s[k].row_begin + segs.s[k].n_rows) {
-                    const int64_t rl = r - segs.s[k].row_begin;
-                    nvec[q] = segs.s[k].nvec;
-                    base[q] = (segs.s[k].offset >> 2) + rl * nvec[q];
-                    touched[q] = __ldg(segs.s[k].stamps + rl) == stamp;
-                }
-            }
+            base[q] = nbase[q]; nvec[q] = nnvec[q]; st[q] = nst[q];
             max_nvec = max(max_nvec, nvec[q]);
         }
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) adam_row_lookup(segs, r0 + stride + q, nbase[q], nnvec[q], nst[q]);
         for (int k0 = 0; k0 < max_nvec; k0 += 32) {
             const int kk = k0 + lane;
             float4 P[kRowsPerWarp], M[kRowsPerWarp], V[kRowsPerWarp], G[kRowsPerWarp];
 #pragma unroll
-            for (int q = 0; q < kRowsPerWarp; ++q) {
-                G[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < kRowsPerWarp; ++q) {      // unconditional loads first: 12 x 16 B in flight per lane
                 if (kk < nvec[q]) {
                     const int64_t i = base[q] + kk;
                     P[q] = reinterpret_cast<const float4*>(p)[i];
                     M[q] = reinterpret_cast<const float4*>(m)[i];
                     V[q] = reinterpret_cast<const float4*>(v)[i];
-                    if (touched[q]) G[q] = __ldcs(reinterpret_cast<const float4*>(g) + i);
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < kRowsPerWarp; ++q) {      // then the gradient of the (few) stamped rows
+                G[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kk < nvec[q] && st[q] == stamp) G[q] = __ldcs(reinterpret_cast<const float4*>(g) + base[q] + kk);
             }
 #pragma unroll
             for (int q = 0; q < kRowsPerWarp; ++q) {
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, 
                     reinterpret_cast<float4*>(p)[i] = P[q];
                     reinterpret_cast<float4*>(m)[i] = M[q];
                     reinterpret_cast<float4*>(v)[i] = V[q];
-                    if (touched[q]) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (st[q] == stamp) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }

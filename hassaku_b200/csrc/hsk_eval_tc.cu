@@ -14,244 +14,9 @@
 //               overlaps the epilogue of tile t.
 // Operands are packed row-major [rows, kpad] (K-major for both A and B) by hsk_pack_rows: bf16 (round-to-nearest-even)
 // or tf32 (fp32 container, rna-rounded), zero padded to a multiple of 128 bytes of K.
-#include <cuda.h>
-#include <stdlib.h>
-#include <cuda_bf16.h>
-
-#include "hsk_topk.cuh"
+#include "hsk_eval_tc.cuh"
 
 namespace hsk {
-
-constexpr int TC_BM = 128;        // users per CTA tile (UMMA_M)
-constexpr int TC_BN = 128;        // items per tile (UMMA_N)
-constexpr int TC_KB_BYTES = 128;  // bytes of K per k-block (one 128B swizzle atom)
-constexpr int TC_MAX_STAGES = 10;          // B-tile ring depth is chosen at launch: as many 16 KB stages as fit beside the A tile
-constexpr int TC_TILE_BYTES = TC_BN * TC_KB_BYTES;  // 16 KB per operand tile per k-block
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // TMA warp + MMA warp + 8 epilogue warps
-constexpr int TC_ACC_STAGES = 4;           // accumulator stages in TMEM: 4 x 128 fp32 columns = all 512 columns
-constexpr int TC_KPL = 16;                 // candidate keys per lane in the epilogue lists
-constexpr int TC_CAP = 32 * TC_KPL;        // 512-entry lists: a cut every ~(512 - 128 - k) appends instead of ~28
-constexpr int TC_MAX_KB = 8;      // kpad * elem_size <= 1024 bytes -> d <= 512 (bf16) / 256 (tf32)
-
-struct EvalTcArgs {
-    const float* __restrict__ Ub;   // user bias TABLE (indexed by u_idx) or null
-    const float* __restrict__ Ib;   // local item bias or null
-    const float* __restrict__ Gb;
-    const int64_t* __restrict__ u_idx;
-    const int64_t* __restrict__ u_rows;   // row of the Ub table per batch entry (null: = u_idx)
-    const int64_t* __restrict__ excl_indptr;
-    const int32_t* __restrict__ excl_indices;
-    int64_t n_users, n_local, id_offset, id_stride;
-    int Be, k, num_kb, kelems_per_kb;
-    int n_tiles, tiles_per_split, n_splits, n_stages;
-    uint64_t* cand;
-    float* out_scores;
-    int32_t* out_ids;
-    int32_t* status;
-};
-
-// ---- PTX wrappers ----
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
-                     "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-template <bool TF32>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (TF32) {
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::
-                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    } else {
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::
-                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    }
-}
-__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100):
-// start address >> 4 | SBO = 1024 B (8 rows x 128 B) | layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Epilogue of one 32-column chunk for one row: v[] already holds score' = acc + item bias (the per-row user/global bias
-// does not change the ranking inside a row and is added when the final scores are written).
-// `region` is this thread's PRIVATE half of the row's candidate list (the other column half of the row appends to the
-// other half), so an append is a register increment and a fire-and-forget store: no atomics, no dependent latency
-// (measured: with a shared counter an append cost ~280 cycles of warp time and dominated the epilogue).
-// Two steps: (1) a branch-free 32-bit survivor mask (one FSETP + one bit insert per element); (2) a short loop over the
-// set bits — survivors are rare (~5 per 1024 elements in steady state), so almost every lane runs 0 or 1 iteration.
-// The value of element e is pulled out of the register array with a 5-level select tree (no local memory).  An unrolled
-// `if (...) append` per element made the hot loop ~50 KB of divergent code that thrashed the I-cache (4.5 k cycles/scan).
-__device__ __forceinline__ float tc_pick(const float (&v)[32], int e) {
-    float a16[16], a8[8], a4[4], a2[2];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a16[i] = (e & 16) ? v[16 + i] : v[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a8[i] = (e & 8) ? a16[8 + i] : a16[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a4[i] = (e & 4) ? a8[4 + i] : a8[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) a2[i] = (e & 2) ? a4[2 + i] : a4[i];
-    return (e & 1) ? a2[1] : a2[0];
-}
-__device__ __forceinline__ void tc_scan_chunk(const float (&v)[32], float tau, uint64_t taukey, uint32_t valid, uint32_t gid0,
-                                              uint32_t id_stride, int& cnt, uint64_t* region) {
-    uint32_t mask = 0;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) mask |= (v[e] >= tau) ? (1u << e) : 0u;
-    mask &= valid;
-    while (mask) {
-        const int e = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint64_t key = make_key(tc_pick(v, e), gid0 + (uint32_t)e * id_stride);
-        if (key > taukey) region[cnt++] = key;
-    }
-}
-
-constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
-
-// Cut a row's two half-lists (cA entries at lp[0..), cB entries at lp[256..)) back to ~k WITHOUT sorting: a radix select
-// on the 16 most significant bits of the keys finds the largest prefix T with count(prefix >= T) >= k; everything
-// below T is dropped, the survivors (k plus the few ties of the T bucket) are compacted and written back split over the
-// two halves.  The new threshold is the lower edge of bucket T — conservative, so no top-k item is ever lost; the exact
-// order is established once, by the final sort.  ~1.5 k cycles instead of ~56 k for the 512-key bitonic network.
-// Entries beyond chkA / chkB are first tested against the user's exclusion row (lock-step binary searches).
-// Returns the number of survivors.
-__device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, int chkB, int k, int lane,
-                                          const int32_t* __restrict__ excl, int64_t lo, int64_t hi, bool check, int max_keep,
-                                          float* new_tau, uint64_t* new_taukey) {
-    // check == false: the exclusion test is postponed to the final cut.  At most n_excl = hi - lo excluded items can sit
-    // in the list, so selecting the (k + n_excl)-th largest RAW key is still a conservative threshold; it saves the
-    // ~11 k cycles of binary searches that made every cut stall the MMA pipeline.
-    if (!check) k += (int)(hi - lo);
-    uint64_t key[TC_KPL];
-    bool unchecked[TC_KPL];
-#pragma unroll
-    for (int r = 0; r < TC_KPL; ++r) {
-        const int e = r * 32 + lane;
-        const bool inA = e < TC_HALF_CAP;
-        const int idx = inA ? e : e - TC_HALF_CAP;
-        const bool valid = idx < (inA ? cA : cB);
-        key[r] = valid ? lp[e] : 0ull;
-        unchecked[r] = valid && idx >= (inA ? chkA : chkB);
-    }
-    if (check && hi > lo) {
-        int32_t id[TC_KPL];
-        bool found[TC_KPL];
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r) id[r] = key[r] ? key_id(key[r]) : -1;
-        if (hi - lo <= 384) csr_contains_bcast<TC_KPL>(excl, lo, hi, id, found, lane);   // short row: one coalesced pass
-        else csr_contains_many<TC_KPL>(excl, lo, hi, id, unchecked, found);             // long row: lock-step searches
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r)
-            if (found[r] && key[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
-    }
-    const int n = cA + cB;
-    uint32_t T = 0;
-    if (n > k) {
-        uint32_t pre[TC_KPL];
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r) pre[r] = (uint32_t)(key[r] >> 48);   // empty slots have prefix 0
-#pragma unroll 1
-        for (int b = 15; b >= 0; --b) {
-            const uint32_t cand = T | (1u << b);
-            int c = 0;
-#pragma unroll
-            for (int r = 0; r < TC_KPL; ++r) c += (pre[r] >= cand) ? 1 : 0;
-            c = __reduce_add_sync(kFull, c);
-            if (c >= k) T = cand;
-        }
-    }
-    // compaction: keep keys whose prefix >= T (all valid keys when n <= k)
-    int mine = 0;
-#pragma unroll
-    for (int r = 0; r < TC_KPL; ++r) mine += (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) ? 1 : 0;
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += up;
-    }
-    const int total = __shfl_sync(kFull, incl, 31);
-    if (total > max_keep) {
-        // degenerate score distribution (a huge tie bucket, e.g. all-equal scores): exact cut by the full sort; ties are
-        // then resolved by the strict key order (lower item id wins), which the scan honours through `taukey`
-        warp_sort_desc<TC_KPL>(key, lane);
-        const int nA2 = (k + 1) >> 1;
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r) {
-            const int e = r * 32 + lane;
-            if (e < k) lp[e < nA2 ? e : TC_HALF_CAP + (e - nA2)] = key[r];
-        }
-        const uint64_t thr = warp_list_at<TC_KPL>(key, k - 1);
-        *new_taukey = thr;
-        *new_tau = key_score(thr);
-        return k;
-    }
-    int pos = incl - mine;
-    const int nA = (total + 1) >> 1;
-#pragma unroll
-    for (int r = 0; r < TC_KPL; ++r) {
-        if (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) {
-            lp[pos < nA ? pos : TC_HALF_CAP + (pos - nA)] = key[r];
-            ++pos;
-        }
-    }
-    *new_tau = (n > k) ? from_orderable(T << 16) : -INFINITY;   // lower edge of bucket T (n > k implies T >= 0x007F)
-    *new_taukey = (n > k) ? ((uint64_t)(T << 16) << 32) : 0ull;
-    return total;
-}
-
-// Final, exact: the (already cut and exclusion-checked) halves nA entries at lp[0..) and nB at lp[256..), nA, nB <= 128,
-// are sorted with the 256-key network and the best k written to lp[0..k) / returned in key[] (element e = r * 32 + lane).
-__device__ __noinline__ void tc_final_sort(uint64_t* lp, int nA, int nB, int k, int lane, uint64_t (&key)[kKeysPerLane]) {
-#pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
-        const int e = r * 32 + lane;
-        const bool inA = e < 128;
-        const int idx = inA ? e : e - 128;
-        key[r] = (idx < (inA ? nA : nB)) ? lp[inA ? idx : TC_HALF_CAP + idx] : 0ull;
-    }
-    warp_sort_desc<kKeysPerLane>(key, lane);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < kKeysPerLane; ++r) {
-        const int e = r * 32 + lane;
-        if (e < k) lp[e] = key[r];
-    }
-}
 
 template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -583,9 +348,11 @@ static int make_map(CUtensorMap* map, const void* base, bool tf32, int kpad, int
     return HSK_OK;
 }
 
-static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split, int* n_splits) {
-    const int row_tiles = (Be + TC_BM - 1) / TC_BM;
-    const int nt = (int)((n_local + TC_BN - 1) / TC_BN);
+// `bn` = items per tile: TC_BN (one-CTA kernel) or 2 * TC_BN (CTA-pair kernel, whose row tiles come in pairs)
+static void tc_plan(int Be, int64_t n_local, int bn, int* n_tiles, int* tiles_per_split, int* n_splits) {
+    int row_tiles = (Be + TC_BM - 1) / TC_BM;
+    if (bn > TC_BN) row_tiles = (row_tiles + 1) / 2 * 2;
+    const int nt = (int)((n_local + bn - 1) / bn);
     const int want = sm_count();
     int splits = 1;
     if (row_tiles * 4 < want * 3) splits = (want + row_tiles - 1) / row_tiles;   // >= 75 % of the SMs busy: no split
@@ -597,6 +364,10 @@ static void tc_plan(int Be, int64_t n_local, int* n_tiles, int* tiles_per_split,
     *tiles_per_split = tps;
     *n_splits = (nt + tps - 1) / tps;
 }
+
+// hsk_eval_tc2.cu
+int launch_eval_tc2(bool tf32, int row_tiles, int n_splits, size_t smem, cudaStream_t s, const CUtensorMap& tmA,
+                    const CUtensorMap& tmB, const EvalTcArgs& a);
 
 }  // namespace hsk
 
@@ -626,9 +397,10 @@ extern "C" int hsk_pack_rows(const float* src, int ld, int d, const int64_t* row
 
 extern "C" int64_t hsk_eval_topk_tc_scratch_bytes(int Be, int64_t n_local_items, int k) {
     (void)k;
-    int nt, tps, ns;
-    tc_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, &nt, &tps, &ns);
-    return (int64_t)ns * (Be > 0 ? Be : 1) * TC_CAP * (int64_t)sizeof(uint64_t);
+    int nt, tps, ns1, ns2;     // enough for either kernel's split plan
+    tc_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, TC_BN, &nt, &tps, &ns1);
+    tc_plan(Be > 0 ? Be : 1, n_local_items > 0 ? n_local_items : 1, 2 * TC_BN, &nt, &tps, &ns2);
+    return (int64_t)(ns1 > ns2 ? ns1 : ns2) * (Be > 0 ? Be : 1) * TC_CAP * (int64_t)sizeof(uint64_t);
 }
 
 extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
@@ -636,6 +408,18 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
                                 int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
                                 int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                                 int32_t* status, hsk_stream_t stream) {
+    return hsk_eval_topk_tc_v(Uq, Vq, kpad, precision, Ub, Ib, Gb, u_idx, u_rows, Be, n_users, n_local, id_offset, id_stride,
+                              excl_indptr, excl_indices, k, top_scores, top_ids, scratch, scratch_bytes, status, HSK_EVAL_TC_AUTO,
+                              stream);
+}
+
+extern "C" int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
+                                  const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
+                                  int64_t n_local, int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr,
+                                  const int32_t* excl_indices, int k, float* top_scores, int32_t* top_ids, void* scratch,
+                                  int64_t scratch_bytes, int32_t* status, int variant, hsk_stream_t stream) {
+    HSK_REQUIRE(variant >= HSK_EVAL_TC_AUTO && variant <= HSK_EVAL_TC_PAIR, "hsk_eval_topk_tc_v: unknown kernel variant %d", variant);
+    const bool pair = variant != HSK_EVAL_TC_SINGLE;
     HSK_REQUIRE(Uq && Vq && u_idx && top_scores && top_ids, "hsk_eval_topk_tc: null pointer");
     HSK_REQUIRE(precision == HSK_PREC_TF32 || precision == HSK_PREC_BF16, "hsk_eval_topk_tc: precision must be TF32 or BF16");
     const bool tf32 = precision == HSK_PREC_TF32;
@@ -654,7 +438,7 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     a.Ub = Ub; a.Ib = Ib; a.Gb = Gb; a.u_idx = u_idx; a.u_rows = u_rows; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
     a.n_users = n_users; a.n_local = n_local; a.id_offset = id_offset; a.id_stride = id_stride;
     a.Be = Be; a.k = k; a.num_kb = num_kb; a.kelems_per_kb = per_kb;
-    tc_plan(Be, n_local, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
+    tc_plan(Be, n_local, pair ? 2 * TC_BN : TC_BN, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
     const int64_t need = (int64_t)a.n_splits * Be * TC_CAP * (int64_t)sizeof(uint64_t);
     HSK_REQUIRE(scratch && scratch_bytes >= need, "hsk_eval_topk_tc: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
     a.cand = reinterpret_cast<uint64_t*>(scratch);
@@ -672,7 +456,11 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
     cudaStream_t s = as_stream(stream);
     dim3 grid((Be + TC_BM - 1) / TC_BM, a.n_splits);
     cudaError_t e;
-    if (tf32) {
+    if (pair) {
+        rc = launch_eval_tc2(tf32, (int)grid.x, a.n_splits, smem, s, tmA, tmB, a);
+        if (rc) return rc;
+        e = cudaSuccess;
+    } else if (tf32) {
         e = cudaFuncSetAttribute(eval_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
     } else {

@@ -1,0 +1,381 @@
+// Full-rank evaluator, tensor-core mode, CTA-PAIR kernel: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs, N = 256).
+//
+// Why pairs (measured on the one-CTA kernel, hsk_eval_tc.cu, at 18 944 users x 1 M items x 256, bf16): every CTA streamed
+// the whole 512 MB item table through its own shared memory — 75.8 GB of L2 -> SM traffic per batch, 6.9 TB/s, close to
+// what the L2 can deliver — and an M128 x N128 MMA reads 8 KB of operands from shared memory per 64 tensor-pipe cycles
+// (128 B / clk, the shared-memory port's limit).  A pair shares the item tile: each CTA loads HALF of a 256-item tile
+// (128 rows) and the MMA reads both halves through the pair's datapath, so the L2 -> SM traffic and the shared-memory
+// bytes per MMA cycle halve; the epilogue's fixed per-tile work (barriers, flags, bias) is amortised over 256 columns.
+//
+// Per CTA (320 threads, one per SM, clusters of 2 along x; CTA rank 0 = leader):
+//   warp 0      TMA producer (both CTAs): its 128-user A tile once (resident), its 128-row half of every item tile through a
+//               ring of 16 KB stages (cp.async.bulk.tensor.2d.cta_group::2: the bytes complete on the LEADER's mbarrier)
+//   warp 1      leader only: tcgen05.mma.cta_group::2.kind::f16 | tf32, accumulators in BOTH CTAs' TMEM (2 stages x 256 fp32
+//               columns = all 512 columns), tcgen05.commit multicast to both CTAs' barriers
+//   warps 2-9   epilogue: thread = accumulator lane (user row) x one 128-column half, 4 chunks of 32 columns per tile:
+//               tcgen05.ld, a 3-input max tree (16 FMNMX3 per 32 scores) against the row's running k-th score — the item bias
+//               is already IN the accumulator: after a stage is read the same warps write the bias row of tile t + 2 into it
+//               (tcgen05.st), and the MMA of that tile accumulates on top, so the hot loop has no bias add (FADD per score in
+//               the one-CTA kernel) and no shared-memory bias tile; survivors go to the row's candidate list exactly as in
+//               hsk_eval_tc.cu (same scan / cut / final-sort code, hsk_eval_tc.cuh).
+#include "hsk_eval_tc.cuh"
+
+namespace hsk {
+
+constexpr int T2_BN = 256;                   // items per tile (UMMA_N); each CTA of the pair loads TC_BN = 128 rows of it
+constexpr int T2_ACC_STAGES = 2;             // 2 x 256 fp32 columns
+constexpr int T2_HALF_COLS = T2_BN / 2;      // columns per epilogue thread and tile
+constexpr int T2_PRUNE_AT = TC_HALF_CAP - T2_HALF_COLS;   // a tile appends at most 128 keys per column half
+constexpr int T2_KEEP_MID = 2 * T2_PRUNE_AT;              // survivors of an intermediate cut: <= 128 per half
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// the leader CTA's copy of a shared-memory address of this CTA (pairs: CTA rank = bit 24 of the shared::cluster address)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(smem_u32(dst)), "l"(map), "r"(leader_addr(leader_bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs when the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                     "r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(leader_addr(bar)) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::
+                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    } else {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::
+                         "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]), "f"(r[9]), "f"(r[10]),
+        "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]), "f"(r[16]), "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]),
+        "f"(r[21]), "f"(r[22]), "f"(r[23]), "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]),
+        "f"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// the item-bias row of one tile's column half -> the accumulator stage (every lane = user row gets the same 128 values)
+__device__ __forceinline__ void t2_write_bias(const float* __restrict__ Ib, bool ib_vec, int64_t n_col0, int64_t n_local, uint32_t taddr) {
+#pragma unroll 1
+    for (int c = 0; c < T2_HALF_COLS / 32; ++c) {
+        float b[32];
+        const int64_t n = n_col0 + c * 32;
+        if (Ib && ib_vec && n + 32 <= n_local) {       // warp-uniform address: one broadcast transaction per float4
+            const float4* p4 = reinterpret_cast<const float4*>(Ib + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = __ldg(p4 + q);
+                b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) b[e] = (Ib && n + e < n_local) ? __ldg(Ib + n + e) : 0.f;
+        }
+        tc_st32(taddr + (uint32_t)(c * 32), b);
+    }
+    tc_st_wait();
+}
+
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[T2_ACC_STAGES], bar_tempty[T2_ACC_STAGES];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_tau[TC_BM];
+    __shared__ uint64_t s_taukey[TC_BM];
+    __shared__ int s_cnt2[2][TC_BM], s_chk2[2][TC_BM];
+    __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
+    __shared__ float s_base[TC_BM];
+    __shared__ int s_rowok[TC_BM];
+    __shared__ int s_need[4][2][2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const bool leader = cta == 0;
+    const int m0 = blockIdx.x * TC_BM;
+    const int split = blockIdx.y;
+    const int t_begin = split * a.tiles_per_split;
+    const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
+    const int n_my_tiles = t_end - t_begin;
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smA = smem;                                        // num_kb x 16 KB, resident: this CTA's 128 users
+    unsigned char* smB = smem + (size_t)a.num_kb * TC_TILE_BYTES;     // n_stages x 16 KB: this CTA's 128 rows of the item tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < T2_ACC_STAGES; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * TC_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {   // TMEM of the pair: the same 512 columns in both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "n"(T2_ACC_STAGES * T2_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_BM) {  // per-row state
+        const int r = threadIdx.x - 64;
+        const int row = m0 + r;
+        int ok = 0;
+        int64_t lo = 0, hi = 0;
+        float base = 0.f;
+        if (row < a.Be) {
+            const int64_t u = a.u_idx[row];
+            if (bad_index(u, a.n_users)) {
+                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
+            } else {
+                ok = 1;
+                if (a.excl_indptr) { lo = a.excl_indptr[u]; hi = a.excl_indptr[u + 1]; }
+                if (a.Ub) base += a.Ub[a.u_rows ? a.u_rows[row] : u];
+            }
+        }
+        if (a.Gb) base += a.Gb[0];
+        s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
+        s_tau[r] = -INFINITY; s_taukey[r] = 0ull;
+        s_cnt2[0][r] = s_cnt2[1][r] = 0; s_chk2[0][r] = s_chk2[1][r] = 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // both CTAs' barriers are initialised and TMEM allocated before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA));
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB));
+            if (leader) mbar_expect_tx(&bar_a, 2u * (uint32_t)a.num_kb * TC_TILE_BYTES);
+            for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d_pair(smA + (size_t)kb * TC_TILE_BYTES, &tmA, kb * a.kelems_per_kb, m0, &bar_a);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < n_my_tiles; ++t) {
+                const int n0 = (t_begin + t) * T2_BN + (int)cta * TC_BN;      // this CTA's half of the tile
+                for (int kb = 0; kb < a.num_kb; ++kb) {
+                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    if (leader) mbar_expect_tx(&bar_full[s], 2u * TC_TILE_BYTES);
+                    tma_load_2d_pair(smB + (size_t)s * TC_TILE_BYTES, &tmB, kb * a.kelems_per_kb, n0, &bar_full[s]);
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16 (1) | TF32 (2), K-major both, N = 256, M = 256 (pair)
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+            mbar_wait(&bar_a, 0);
+            tc_fence_after();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < n_my_tiles; ++t) {
+                const int as = t & 1;
+                mbar_wait(&bar_tempty[as], ((uint32_t)t >> 1) & 1u);   // the epilogues of BOTH CTAs wrote the bias row into this stage
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + (uint32_t)as * T2_BN;
+                for (int kb = 0; kb < a.num_kb; ++kb) {
+                    mbar_wait(&bar_full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc(smem_u32(smA + (size_t)kb * TC_TILE_BYTES));
+                    const uint64_t db = umma_desc(smem_u32(smB + (size_t)s * TC_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TC_KB_BYTES / 32; ++k)   // accumulate = 1 always: the stage holds the bias row
+                        tc_mma_pair<TF32>(tmem_c, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+                    tc_commit_pair(&bar_empty[s]);
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+                }
+                tc_commit_pair(&bar_tfull[as]);
+            }
+        }
+    } else {
+        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const int r = quarter * 32 + lane;
+        const bool row_ok = s_rowok[r] != 0;
+        uint64_t* list = a.cand + ((int64_t)split * a.Be + min(m0 + r, a.Be - 1)) * TC_CAP;
+        uint64_t* region = list + half * TC_HALF_CAP;
+        int cnt = 0;
+        const int bar_id = 1 + quarter;
+        const bool ib_vec = (reinterpret_cast<uintptr_t>(a.Ib) & 15) == 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * T2_HALF_COLS);
+
+        // prologue: bias rows of the first two tiles, then hand both stages to the MMA warp
+        for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
+            t2_write_bias(a.Ib, ib_vec, (int64_t)(t_begin + ts) * T2_BN + half * T2_HALF_COLS, a.n_local, tlane + (uint32_t)ts * T2_BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&bar_tempty[ts]);
+        }
+
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int as = t & 1;
+            const int64_t n0 = (int64_t)(t_begin + t) * T2_BN;
+            const int ncols = (int)min((int64_t)T2_BN, a.n_local - n0);
+            const float tau = s_tau[r];
+            const uint64_t taukey = s_taukey[r];
+            mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tlane + (uint32_t)as * T2_BN;
+#pragma unroll 1
+            for (int cp = 0; cp < 2; ++cp) {       // two 32-column chunks at a time: 64 accumulator registers live
+                uint32_t raw0[32], raw1[32];
+                tc_ld32_issue(taddr + (uint32_t)(cp * 64), raw0);
+                tc_ld32_issue(taddr + (uint32_t)(cp * 64 + 32), raw1);
+                tc_ld_wait();
+                auto chunk = [&](const uint32_t (&raw)[32], int cc) {
+                    const int c = half * T2_HALF_COLS + cp * 64 + cc * 32;     // column of the tile
+                    if (c >= ncols) return;
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+                    float m0_ = fmax3(v[0], v[1], v[2]), m1_ = fmax3(v[3], v[4], v[5]);
+#pragma unroll
+                    for (int e = 6; e + 3 < 32; e += 4) { m0_ = fmax3(m0_, v[e], v[e + 1]); m1_ = fmax3(m1_, v[e + 2], v[e + 3]); }
+                    float mx = fmax3(m0_, m1_, fmaxf(v[30], v[31]));
+                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
+                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
+                    if (row_ok && mx >= tau)
+                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
+                                      cnt, region);
+                };
+                chunk(raw0, 0);
+                chunk(raw1, 1);
+            }
+            // the stage has been read: write the bias row of tile t + 2 into it and hand it back to the MMA warp
+            if (t + T2_ACC_STAGES < n_my_tiles) {
+                t2_write_bias(a.Ib, ib_vec, n0 + (int64_t)T2_ACC_STAGES * T2_BN + half * T2_HALF_COLS, a.n_local, taddr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+            }
+            const bool last = (t + 1 == n_my_tiles);
+            const bool warp_need = __any_sync(kFull, row_ok && cnt > T2_PRUNE_AT) || last;
+            if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
+            named_bar_sync(bar_id, 64);
+            const bool pair_need = (s_need[quarter][0][t & 1] | s_need[quarter][1][t & 1]) != 0;
+            if (pair_need) {
+                s_cnt2[half][r] = cnt;
+                named_bar_sync(bar_id, 64);
+                int my_a = 0, my_b = 0;
+                bool my_need = false;
+                if (lane < 16) {   // lane j looks at row j of this warp's 16 rows
+                    const int rj = quarter * 32 + half * 16 + lane;
+                    my_a = s_cnt2[0][rj];
+                    my_b = s_cnt2[1][rj];
+                    my_need = s_rowok[rj] && (my_a > T2_PRUNE_AT || my_b > T2_PRUNE_AT || last);
+                }
+                unsigned need = __ballot_sync(kFull, my_need);
+                while (need) {
+                    const int j = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int rr = quarter * 32 + half * 16 + j;
+                    const int cA = __shfl_sync(kFull, my_a, j), cB = __shfl_sync(kFull, my_b, j);
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
+                    float ntau;
+                    uint64_t ntaukey;
+                    // intermediate cuts skip the exclusion test while k + n_excl raw keys fit the 256 kept entries (<= 128 per
+                    // half, so that the next tile's <= 128 appends per half cannot overflow); the last cut always tests
+                    const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > T2_KEEP_MID - 32;
+                    const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
+                                                 s_exhi[rr], check, last ? 192 : T2_KEEP_MID, &ntau, &ntaukey);
+                    __syncwarp();
+                    const int nA = (total + 1) >> 1;
+                    if (lane == 0) {
+                        s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA;
+                        s_chk2[0][rr] = check ? nA : 0; s_chk2[1][rr] = check ? total - nA : 0;
+                        s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
+                    }
+                    if (last) {
+                        uint64_t keys[kKeysPerLane];
+                        tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
+                        if (a.n_splits == 1) {
+                            const int64_t orow = (int64_t)(m0 + rr) * a.k;
+                            const float base = s_base[rr];
+#pragma unroll
+                            for (int q = 0; q < kKeysPerLane; ++q) {
+                                const int e = q * 32 + lane;
+                                if (e < a.k) {
+                                    a.out_scores[orow + e] = keys[q] ? key_score(keys[q]) + base : -INFINITY;
+                                    a.out_ids[orow + e] = key_id(keys[q]);
+                                }
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(bar_id, 64);
+                cnt = s_cnt2[half][r];
+            }
+        }
+        // rows with a bad user index: empty lists / -1 ids
+        for (int j = 0; j < 16; ++j) {
+            const int rr = quarter * 32 + half * 16 + j;
+            if (m0 + rr < a.Be && !s_rowok[rr]) {
+                if (a.n_splits == 1) {
+                    for (int e = lane; e < a.k; e += 32) { a.out_scores[(int64_t)(m0 + rr) * a.k + e] = -INFINITY; a.out_ids[(int64_t)(m0 + rr) * a.k + e] = -1; }
+                } else {
+                    uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
+                    for (int e = lane; e < a.k; e += 32) lp[e] = 0ull;
+                }
+            }
+        }
+    }
+
+    // neither CTA may leave (or free its TMEM) while its peer can still read its shared memory or signal its barriers
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(T2_ACC_STAGES * T2_BN));
+    }
+}
+
+// launcher (called by hsk_eval_topk_tc in hsk_eval_tc.cu): grid.x = an even number of 128-user tiles
+int launch_eval_tc2(bool tf32, int row_tiles, int n_splits, size_t smem, cudaStream_t s, const CUtensorMap& tmA,
+                    const CUtensorMap& tmB, const EvalTcArgs& a) {
+    dim3 grid((unsigned)((row_tiles + 1) / 2 * 2), (unsigned)n_splits);
+    cudaError_t e;
+    if (tf32) {
+        e = cudaFuncSetAttribute(eval_topk_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) eval_topk_tc2_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+    } else {
+        e = cudaFuncSetAttribute(eval_topk_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) eval_topk_tc2_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+    }
+    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(pair): smem attribute: %s", cudaGetErrorString(e));
+    return check_launch("hsk_eval_topk_tc(pair)");
+}
+
+}  // namespace hsk

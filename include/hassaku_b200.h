@@ -46,6 +46,8 @@ enum { HSK_STATUS_BAD_INDEX = 1, HSK_STATUS_CAPACITY = 2, HSK_STATUS_SAMPLER_ROU
 enum { HSK_PREC_FP32 = 0, HSK_PREC_TF32 = 1, HSK_PREC_BF16 = 2 }; /* evaluator scoring precision */
 /* kernel selection of hsk_mf_train_fused_v: every variant computes the same step (parity tests, A/B measurements) */
 enum { HSK_TRAIN_AUTO = 0, HSK_TRAIN_REGS = 1, HSK_TRAIN_RING = 2, HSK_TRAIN_QWARP = 3 };
+/* kernel selection of hsk_eval_topk_tc_v: one CTA per 128-user tile (cta_group::1) or CTA pairs (cta_group::2, the default) */
+enum { HSK_EVAL_TC_AUTO = 0, HSK_EVAL_TC_SINGLE = 1, HSK_EVAL_TC_PAIR = 2 };
 
 /* The embedding tables of one SGDMatrixFactorization (algorithms/sgd_alg.py:127-138).  Nullable: Ub, Ib, Gb. */
 typedef struct hsk_mf_tables {
@@ -236,6 +238,16 @@ HSK_API int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int preci
                              int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr, const int32_t* excl_indices,
                              int k, float* top_scores, int32_t* top_ids, void* scratch, int64_t scratch_bytes,
                              int32_t* status, hsk_stream_t stream);
+
+/* The same with an explicit kernel choice (parity tests, A/B measurements): HSK_EVAL_TC_PAIR = thread-block clusters of two
+ * CTAs, tcgen05.mma.cta_group::2 with M = 256 / N = 256 tiles, the item tile shared by the pair, item bias pre-loaded into
+ * the TMEM accumulator (default); HSK_EVAL_TC_SINGLE = one CTA per 128-user tile, M = N = 128.  Both return the same
+ * ranking up to the rounding of (bias + dot) against (dot + bias). */
+HSK_API int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
+                               const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
+                               int64_t n_local, int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr,
+                               const int32_t* excl_indices, int k, float* top_scores, int32_t* top_ids, void* scratch,
+                               int64_t scratch_bytes, int32_t* status, int variant, hsk_stream_t stream);
 
 /* ---- fp32 re-scoring of tensor-core candidates: TF32 / BF16 ranking, fp32 scores and order ------------------------------
  * cand_ids [Be, n_cand] (n_cand <= 128; global item ids as hsk_eval_topk_tc returns them, < 0 = empty, exclusions already

@@ -12,6 +12,14 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=['pair', 'single'], autouse=True)
+def tc_kernel_variant(request, monkeypatch):
+    """Every test of this file runs on both tensor-core kernels: CTA pairs (cta_group::2, the default) and one CTA per tile."""
+    from hassaku_b200 import _C
+    monkeypatch.setattr(_C, 'EVAL_TC_VARIANT', request.param)
+    return request.param
+
 # |score_tc - score_fp32| <= TOL * sqrt(d) * rms(u) * rms(v) * ...: operand rounding 2^-9 (bf16) / 2^-11 (tf32) per factor
 TOL = {'bf16': 2 ** -7, 'tf32': 2 ** -9}
 

@@ -325,3 +325,53 @@ def test_tensor_core_evaluator_at_cfg5_shape_against_a_cpu_fp32_oracle(prec):
     clear = gap[:, :k].clone()
     clear[:, 1:] &= gap[:, :k - 1]
     assert bool((i_tc == top_i[:, :k])[clear].all())
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('U,I,d,B,n_excl', [
+    (700, 50_011, 96, 700, 40),        # 6 row tiles (3 pairs), ragged last item tile, one split
+    (300, 20_000, 256, 129, 0),        # 2 row tiles of which the second holds one user; several splits; no exclusions
+    (130, 1_000, 64, 130, 300),        # more exclusions than kept entries: every cut checks the exclusion row
+    (5, 129, 16, 5, 3),                # fewer items than one tile
+])
+def test_pair_kernel_matches_the_single_cta_kernel(prec, U, I, d, B, n_excl):
+    """cta_group::2 kernel (item bias pre-loaded into TMEM, 256-wide tiles) against the cta_group::1 kernel on the same packed
+    operands: same candidates (raw low-precision ranking, k = 128) up to the rounding of bias + dot vs dot + bias."""
+    from scipy import sparse as sp
+    from hassaku_b200 import _C
+    from hassaku_b200.eval.eval import DeviceCSR
+    k = min(128, I)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    Uw = torch.randn((U, d), device='cuda', generator=gen) / d ** 0.5
+    Vw = torch.randn((I, d), device='cuda', generator=gen) / d ** 0.5
+    Ib = torch.randn((I, 1), device='cuda', generator=gen) * 0.1
+    Ub = torch.randn((U, 1), device='cuda', generator=gen) * 0.1
+    exd = None
+    if n_excl:
+        rng = np.random.RandomState(0)
+        rows = np.repeat(np.arange(U), n_excl)
+        ex = sp.csr_matrix((np.ones(len(rows), dtype=bool), (rows, rng.randint(0, I, len(rows)))), shape=(U, I))
+        ex.sum_duplicates(); ex.sort_indices()
+        exd = DeviceCSR(ex, 'cuda')
+    users = torch.arange(B, device='cuda')
+    P = _C.PRECISIONS[prec]
+    Uq, Vq = _C.pack_rows(Uw, d, P, row_idx=users), _C.pack_rows(Vw, d, P)
+    out = {}
+    for variant in ('single', 'pair'):
+        s = torch.empty((B, k), device='cuda'); ids = torch.empty((B, k), dtype=torch.int32, device='cuda')
+        scr = torch.empty(_C.eval_topk_tc_scratch_bytes(B, I, k), dtype=torch.uint8, device='cuda')
+        st = torch.zeros(1, dtype=torch.int32, device='cuda')
+        _C.eval_topk_tc(Uq, Vq, P, users, U, k, s, ids, scr, Ub=Ub, Ib=Ib, excl_indptr=exd.indptr if exd else None,
+                        excl_indices=exd.indices if exd else None, status=st, variant=variant)
+        torch.cuda.synchronize()
+        assert int(st.item()) == 0
+        out[variant] = (s.cpu(), ids.cpu())
+    (s1, i1), (s2, i2) = out['single'], out['pair']
+    fin = torch.isfinite(s1)
+    assert torch.equal(fin, torch.isfinite(s2))
+    scale = float(s1[fin].abs().max())
+    assert float((s1[fin] - s2[fin]).abs().max()) <= 1e-6 * scale + 1e-6      # same products, one fp32 add in another order
+    same = (i1 == i2)[fin].float().mean()
+    assert float(same) >= 0.999, float(same)                                   # order flips only between near-equal scores
+    ov = np.mean([len(np.intersect1d(a[f], b[f])) / max(int(f.sum()), 1) for a, b, f in zip(i1.numpy(), i2.numpy(), fin.numpy())])
+    assert ov >= 0.9995, ov

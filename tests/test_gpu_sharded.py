@@ -20,7 +20,7 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     import faulthandler
-    faulthandler.dump_traceback_later(150, exit=True)   # a stalled collective must not hold the GPU box: dump the stack and exit
+    faulthandler.dump_traceback_later(60, exit=True)   # a stalled collective must not hold the GPU box: dump the stack and exit
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -77,6 +77,10 @@ def _worker(rank, world, port, out_dir):
             assert abs(got[k_] - v) <= 1e-9, (k_, got[k_], v)
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
@@ -92,7 +96,7 @@ def _worker_graph(rank, world, port, out_dir):
     """The CUDA-graph replays of the dense and of the sparse (device-routed, fixed-capacity all-to-all) step equal their
     eager versions (fixed local batch shape)."""
     import faulthandler
-    faulthandler.dump_traceback_later(150, exit=True)
+    faulthandler.dump_traceback_later(60, exit=True)
     models = []
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -125,11 +129,17 @@ def _worker_graph(rank, world, port, out_dir):
             for x, y in ((a.m, b.m), (a.v, b.v)):
                 assert float((x - y).abs().max() / x.abs().max()) < 1e-5, eager
             err = float((a.arena - b.arena).abs().max() / a.arena.abs().max())
-            assert err < 1e-6, (eager, err)     # atomics order differs run to run; the arithmetic is identical
+            # atomics order differs run to run; the arithmetic is identical.  Bound: the per-step tolerance of the parity
+            # tests (rtol 1e-5 + the Adam-eps conditioning term 2e-3 lr for elements whose gradient nearly cancels)
+            assert err < 1e-5 + 2e-3 * 1e-3, (eager, err)
             assert abs(a.pop_loss() - b.pop_loss()) < 1e-9
             assert float(a.g.abs().max()) == 0.0 and float(b.g.abs().max()) == 0.0
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    except BaseException:
+        import traceback
+        traceback.print_exc()       # visible even if the peer rank then stalls in a collective
+        os._exit(1)                 # do not wait in destroy_process_group() for a peer that is inside a collective
     finally:
         for mdl in models:      # captured graphs hold NCCL work: destroy_process_group() blocks until they are dropped
             mdl.close()
@@ -146,7 +156,7 @@ def _worker_tc_eval(rank, world, port, out_dir):
     """Item-sharded evaluation in BF16 / TF32 (cfg5's mode): every rank scores its item shard on the tensor cores; the
     merged result equals the single-GPU tensor-core evaluation (same operands, same K order -> same scores)."""
     import faulthandler
-    faulthandler.dump_traceback_later(150, exit=True)
+    faulthandler.dump_traceback_later(60, exit=True)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -185,6 +195,10 @@ def _worker_tc_eval(rank, world, port, out_dir):
         assert int(smf.status.item()) == 0
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
