@@ -67,6 +67,8 @@ def _declare(lib):
         'hsk_mark_batch': (i32, [vp, vp, i32, i32, i64, i64, vp, vp, i64, vp, vp]),
         'hsk_adamw_dense_rows': (i32, [vp, vp, vp, vp, i64, C.POINTER(RowSegment), i32, f64, f64, f64, f64, f64, i64, vp, vp, i32, i32, vp]),
         'hsk_rescore_topk': (i32, [T, vp, i32, i64, i64, vp, vp, i32, i32, vp, vp, vp, vp]),
+        'hsk_rescore_scores': (i32, [T, vp, i32, i64, i64, vp, i32, vp, vp, vp]),
+        'hsk_topk_combine': (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         'hsk_shard_block_rows': (i64, [i32, i32]),
         'hsk_route_scratch_bytes': (i64, [i64, i32]),
         'hsk_route_items': (i32, [vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp]),
@@ -495,6 +497,29 @@ def rescore_topk(tables: MfTables, u_rows, cand_ids, k: int, top_scores, top_ids
         _check(lib().hsk_rescore_topk(C.byref(tables), u_rows.data_ptr(), Be, id_offset, id_stride, cand_ids.data_ptr(),
                                       _ptr(cand_scores), n_cand, k, top_scores.data_ptr(), top_ids.data_ptr(), _ptr(status),
                                       st), 'hsk_rescore_topk')
+
+
+def rescore_scores(tables: MfTables, u_rows, cand_ids, out_scores, id_offset: int = 0, id_stride: int = 1, status=None):
+    """Positional fp32 scores of the candidates this shard owns (-inf for the others): item-sharded evaluation."""
+    _req(u_rows, torch.int64, 'u_rows'); _req(cand_ids, torch.int32, 'cand_ids'); _req(out_scores, torch.float32, 'out_scores')
+    Be, n_cand = cand_ids.shape
+    if tuple(out_scores.shape) != (Be, n_cand):
+        raise HskError(f'rescore_scores: out_scores must be [{Be}, {n_cand}]')
+    with _on_device_of(u_rows, cand_ids, out_scores, status) as st:
+        _check(lib().hsk_rescore_scores(C.byref(tables), u_rows.data_ptr(), Be, id_offset, id_stride, cand_ids.data_ptr(), n_cand,
+                                        out_scores.data_ptr(), _ptr(status), st), 'hsk_rescore_scores')
+
+
+def topk_combine(scores, ids, k: int, out_scores, out_ids):
+    """scores [G, rows, n_cand] (finite where shard g owns the item), ids [rows, n_cand] -> the k best per row."""
+    _req(scores, torch.float32, 'scores'); _req(ids, torch.int32, 'ids')
+    _req(out_scores, torch.float32, 'out_scores'); _req(out_ids, torch.int32, 'out_ids')
+    G, rows, n_cand = scores.shape
+    if tuple(ids.shape) != (rows, n_cand) or tuple(out_scores.shape) != (rows, k) or tuple(out_ids.shape) != (rows, k):
+        raise HskError('topk_combine: ids must be [rows, n_cand], outputs [rows, k]')
+    with _on_device_of(scores, ids, out_scores, out_ids) as st:
+        _check(lib().hsk_topk_combine(scores.data_ptr(), ids.data_ptr(), G, rows, n_cand, k, out_scores.data_ptr(),
+                                      out_ids.data_ptr(), st), 'hsk_topk_combine')
 
 
 def topk_merge(scores, ids, out_scores, out_ids):

@@ -199,100 +199,58 @@ extern "C" int hsk_adamw_dense(float* p, float* m, float* v, float* g, int64_t n
 namespace hsk {
 
 struct AdamSeg {
-    int64_t offset;                  // first element of the segment
-    int64_t row_begin;               // rows of the earlier segments (the kernel walks one global row index)
-    int64_t n_rows;
+    int64_t begin4, end4;            // float4 range [begin4, end4) of the arena
     const uint8_t* stamps;           // one byte per row of the segment
-    int nvec;                        // float4 per row
+    uint64_t magic;                  // ceil(2^64 / nvec): row = umul64hi(float4 index inside the segment, magic); 0: nvec = 1
 };
 struct AdamSegs {
     AdamSeg s[4];
     int n;
-    int64_t total_rows;
+    int64_t lo4, hi4;                // float4 range covered by the kernel: [lo4, hi4) = first segment's begin .. last one's end
 };
 
 __host__ __device__ __forceinline__ int stamp_of_step(int64_t step) { return 1 + (int)(step % 255); }
 
-// One warp owns kRowsPerWarp consecutive rows per iteration: the p, m, v loads of ALL its rows are issued before any
-// arithmetic (12 independent 16-byte loads per lane in flight), the g loads only for stamped rows; the stamp bytes are
-// fetched one iteration ahead.  Measured at cfg4 (385 M parameters, 0.35 M of 3 M rows stamped): a per-float4 variant
-// with a row lookup (integer division) per element 1.88 ms; this layout with the stamp load in front of the data loads
-// 2.34 ms (the latencies add up); see DESIGN.md for the current figure.  Rows longer than 32 float4 are walked in
-// chunks of 32.
-constexpr int kRowsPerWarp = 4;
-
-// row r of the concatenated segments -> (float4 index of its first vector, float4 per row, stamp byte); base -1 = no row
-__device__ __forceinline__ void adam_row_lookup(const AdamSegs& segs, int64_t r, int64_t& base, int& nvec, uint8_t& st) {
-    base = -1; nvec = 0; st = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < segs.n && r >= segs.s[k].row_begin && r < segs.s[k].row_begin + segs.s[k].n_rows) {
-            const int64_t rl = r - segs.s[k].row_begin;
-            nvec = segs.s[k].nvec;
-            base = (segs.s[k].offset >> 2) + rl * nvec;
-            st = __ldg(segs.s[k].stamps + rl);
-        }
-    }
-}
-
+// Flat streaming pass (one float4 per thread and iteration, grid-stride — the access pattern and occupancy of
+// adamw_dense_kernel, which reaches 94 % of the copy bandwidth) over the float4 range spanned by the row segments.  The
+// p / m / v loads are issued first; the row of the float4 comes from a multiply-high (no integer division), its stamp byte
+// is one more independent load; only then the gradient is loaded — for stamped rows only.  float4s between two segments
+// (alignment padding) take the dense path.  Measured alternatives at cfg4 (385 M parameters, 0.35 M of 3 M rows stamped):
+// row lookup by integer division with the stamp load in front of the data loads 1.88 ms; warp-per-row layouts with 4 / 2 /
+// 1 rows per warp 2.34-2.47 / 2.08 / 1.93 ms (fewer resident warps hide the ~60 instructions per element of IEEE
+// division / square root worse); the plain 32 B / parameter kernel 2.01 ms.
 template <int ARITH, bool L2, bool DECAY>
-__global__ void __launch_bounds__(256, 2) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                            float* __restrict__ g, AdamConsts c_host,
-                                                            const AdamConsts* __restrict__ c_dev, AdamSegs segs, int stamp_host,
-                                                            const int64_t* __restrict__ step_dev) {
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                         float* __restrict__ g, AdamConsts c_host,
+                                                         const AdamConsts* __restrict__ c_dev, AdamSegs segs, int stamp_host,
+                                                         const int64_t* __restrict__ step_dev) {
     const AdamConsts c = c_dev ? *c_dev : c_host;
     const uint8_t stamp = (uint8_t)(step_dev ? stamp_of_step(*step_dev) : stamp_host);
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRowsPerWarp;
-    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * kRowsPerWarp;
-    // the row descriptors (incl. the stamp bytes) of the NEXT iteration are fetched while this one's rows stream, so the
-    // stamp load is never in front of the p / m / v loads
-    int64_t base[kRowsPerWarp], nbase[kRowsPerWarp];
-    int nvec[kRowsPerWarp], nnvec[kRowsPerWarp];
-    uint8_t st[kRowsPerWarp], nst[kRowsPerWarp];
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = segs.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < segs.hi4; i += stride) {
+        float4 P = p4[i], M = m4[i], V = v4[i];
+        uint8_t st = stamp;          // outside every segment: dense path
 #pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) adam_row_lookup(segs, warp0 + q, nbase[q], nnvec[q], nst[q]);
-    for (int64_t r0 = warp0; r0 < segs.total_rows; r0 += stride) {
-        int max_nvec = 0;
-#pragma unroll
-        for (int q = 0; q < kRowsPerWarp; ++q) {
-            base[q] = nbase[q]; nvec[q] = nnvec[q]; st[q] = nst[q];
-            max_nvec = max(max_nvec, nvec[q]);
+        for (int k = 0; k < 4; ++k) {
+            if (k < segs.n && i >= segs.s[k].begin4 && i < segs.s[k].end4)
+                st = __ldg(segs.s[k].stamps + (segs.s[k].magic ? __umul64hi((uint64_t)(i - segs.s[k].begin4), segs.s[k].magic)
+                                                             : (uint64_t)(i - segs.s[k].begin4)));
         }
-#pragma unroll
-        for (int q = 0; q < kRowsPerWarp; ++q) adam_row_lookup(segs, r0 + stride + q, nbase[q], nnvec[q], nst[q]);
-        for (int k0 = 0; k0 < max_nvec; k0 += 32) {
-            const int kk = k0 + lane;
-            float4 P[kRowsPerWarp], M[kRowsPerWarp], V[kRowsPerWarp], G[kRowsPerWarp];
-#pragma unroll
-            for (int q = 0; q < kRowsPerWarp; ++q) {      // unconditional loads first: 12 x 16 B in flight per lane
-                if (kk < nvec[q]) {
-                    const int64_t i = base[q] + kk;
-                    P[q] = reinterpret_cast<const float4*>(p)[i];
-                    M[q] = reinterpret_cast<const float4*>(m)[i];
-                    V[q] = reinterpret_cast<const float4*>(v)[i];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < kRowsPerWarp; ++q) {      // then the gradient of the (few) stamped rows
-                G[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kk < nvec[q] && st[q] == stamp) G[q] = __ldcs(reinterpret_cast<const float4*>(g) + base[q] + kk);
-            }
-#pragma unroll
-            for (int q = 0; q < kRowsPerWarp; ++q) {
-                if (kk < nvec[q]) {
-                    const int64_t i = base[q] + kk;
-                    adam_elem<ARITH, L2, DECAY>(P[q].x, M[q].x, V[q].x, G[q].x, c);
-                    adam_elem<ARITH, L2, DECAY>(P[q].y, M[q].y, V[q].y, G[q].y, c);
-                    adam_elem<ARITH, L2, DECAY>(P[q].z, M[q].z, V[q].z, G[q].z, c);
-                    adam_elem<ARITH, L2, DECAY>(P[q].w, M[q].w, V[q].w, G[q].w, c);
-                    reinterpret_cast<float4*>(p)[i] = P[q];
-                    reinterpret_cast<float4*>(m)[i] = M[q];
-                    reinterpret_cast<float4*>(v)[i] = V[q];
-                    if (st[q] == stamp) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        }
+        const bool touched = st == stamp;
+        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (touched) G = __ldcs(g4 + i);
+        adam_elem<ARITH, L2, DECAY>(P.x, M.x, V.x, G.x, c);
+        adam_elem<ARITH, L2, DECAY>(P.y, M.y, V.y, G.y, c);
+        adam_elem<ARITH, L2, DECAY>(P.z, M.z, V.z, G.z, c);
+        adam_elem<ARITH, L2, DECAY>(P.w, M.w, V.w, G.w, c);
+        p4[i] = P;
+        m4[i] = M;
+        v4[i] = V;
+        if (touched) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -368,26 +326,35 @@ extern "C" int hsk_adamw_dense_rows(float* p, float* m, float* v, float* g, int6
     if (n == 0) return HSK_OK;
     AdamSegs segs;
     memset(&segs, 0, sizeof(segs));
-    int64_t cursor = 0;   // segments must be ascending and disjoint: what lies between them takes the plain dense kernel
-    struct Gap { int64_t off, len; } gaps[5];
-    int n_gaps = 0;
+    int64_t cursor = 0;   // segments must be ascending and disjoint
     for (int k = 0; k < n_segments; ++k) {
         const hsk_row_segment& sg = segments[k];
         HSK_REQUIRE(sg.n_rows >= 0 && sg.ld >= 4 && sg.ld % 4 == 0 && sg.offset % 4 == 0 && sg.offset >= cursor &&
                         sg.offset + sg.n_rows * sg.ld <= n && sg.stamps,
                     "hsk_adamw_dense_rows: segment %d must be a 16-byte aligned range of rows (ld %% 4 == 0) inside [0, n), "
                     "segments ascending and disjoint", k);
-        if (sg.offset > cursor) gaps[n_gaps++] = {cursor, sg.offset - cursor};
-        segs.s[segs.n].offset = sg.offset;
-        segs.s[segs.n].row_begin = segs.total_rows;
-        segs.s[segs.n].n_rows = sg.n_rows;
-        segs.s[segs.n].stamps = sg.stamps;
-        segs.s[segs.n].nvec = sg.ld / 4;
-        segs.total_rows += sg.n_rows;
-        ++segs.n;
+        HSK_REQUIRE(sg.n_rows * (int64_t)(sg.ld / 4) < ((int64_t)1 << 32), "hsk_adamw_dense_rows: segment %d too long", k);
         cursor = sg.offset + sg.n_rows * sg.ld;
+        if (sg.n_rows == 0) continue;
+        const uint64_t nvec = (uint64_t)(sg.ld / 4);
+        AdamSeg& d = segs.s[segs.n++];
+        d.begin4 = sg.offset / 4;
+        d.end4 = (sg.offset + sg.n_rows * sg.ld) / 4;
+        d.stamps = sg.stamps;
+        d.magic = nvec == 1 ? 0 : (~0ull) / nvec + 1;     // ceil(2^64 / nvec); 0 = one float4 per row (row = index)
     }
-    if (cursor < n) gaps[n_gaps++] = {cursor, n - cursor};
+    // what lies before the first / after the last segment (bias vectors, the global bias) takes the plain dense kernel; the
+    // alignment padding BETWEEN segments is walked by the rows kernel on its dense path
+    struct Gap { int64_t off, len; } gaps[2];
+    int n_gaps = 0;
+    if (segs.n > 0) {
+        segs.lo4 = segs.s[0].begin4;
+        segs.hi4 = segs.s[segs.n - 1].end4;
+        if (segs.lo4 > 0) gaps[n_gaps++] = {0, segs.lo4 * 4};
+        if (segs.hi4 * 4 < n) gaps[n_gaps++] = {segs.hi4 * 4, n - segs.hi4 * 4};
+    } else {
+        gaps[n_gaps++] = {0, n};
+    }
     AdamConsts c;
     memset(&c, 0, sizeof(c));
     if (!consts_dev) fill_consts(c, lr, beta1, beta2, eps, weight_decay, step);
@@ -397,8 +364,8 @@ extern "C" int hsk_adamw_dense_rows(float* p, float* m, float* v, float* g, int6
     cudaStream_t s = as_stream(stream);
     const AdamConsts* cp = reinterpret_cast<const AdamConsts*>(consts_dev);
     const int stamp = stamp_of_step(step);
-    if (segs.total_rows > 0) {
-        const int64_t want = (segs.total_rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp);
+    if (segs.n > 0) {
+        const int64_t want = (segs.hi4 - segs.lo4 + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 16;
         const int blocks = (int)(want < cap ? want : cap);
 #define HSK_LAUNCH_ADAMR(A, L, D) adamw_rows_kernel<A, L, D><<<blocks, 256, 0, s>>>(p, m, v, g, c, cp, segs, stamp, step_dev)

@@ -27,12 +27,13 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // per-row top-k state shared by the two epilogue warps of a row (column halves)
     __shared__ float s_tau[TC_BM];
     __shared__ uint64_t s_taukey[TC_BM];
-    __shared__ int s_cnt2[2][TC_BM], s_chk2[2][TC_BM];   // per column half: entries / exclusion-checked entries
+    __shared__ int s_cnt2[2][TC_BM];   // per column half: entries of the row's candidate list
     __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
     __shared__ float s_base[TC_BM];
     __shared__ int s_rowok[TC_BM];
     __shared__ int s_need[4][2][2];   // per pair / column half / tile parity: a list of this warp may overflow
-    __shared__ __align__(16) float s_ib[4][2][TC_BN];   // per pair: item-bias tile, double buffered with the accumulator stages
+    // per pair: item-bias tiles of the next tiles (ring of 2 x TC_ACC_STAGES... see the epilogue), written one tile ahead
+    __shared__ __align__(16) float s_ib[4][2][TC_BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
@@ -75,7 +76,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (a.Gb) base += a.Gb[0];
         s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
         s_tau[r] = -INFINITY; s_taukey[r] = 0ull;
-        s_cnt2[0][r] = s_cnt2[1][r] = 0; s_chk2[0][r] = s_chk2[1][r] = 0;
+        s_cnt2[0][r] = s_cnt2[1][r] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -113,7 +114,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t ph = 0;
             for (int t = 0; t < n_my_tiles; ++t) {
                 const int as = t % TC_ACC_STAGES;
-                mbar_wait(&bar_tempty[as], (((uint32_t)t / TC_ACC_STAGES) & 1u) ^ 1u);
+                mbar_wait(&bar_tempty[as], ((uint32_t)t / TC_ACC_STAGES) & 1u);   // the epilogue wrote this tile's bias row into the stage
                 tc_fence_after();
                 const uint32_t tmem_c = tmem_base + (uint32_t)as * TC_BN;
                 for (int kb = 0; kb < a.num_kb; ++kb) {
@@ -123,7 +124,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t db = umma_desc(smem_u32(smB + (size_t)s * TC_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < TC_KB_BYTES / 32; ++k)  // 32 bytes of K per MMA: advance the start address by 2 (x16 B)
-                        tc_mma<TF32>(tmem_c, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma<TF32>(tmem_c, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);   // on top of the bias row
                     tc_commit(&bar_empty[s]);
                     if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
@@ -142,75 +143,77 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int prune_at = TC_HALF_CAP - TC_BN / 2;   // a tile appends at most 64 keys per column half
         uint64_t* region = list + half * TC_HALF_CAP;
         int cnt = 0;
+        const int bar_id = 1 + quarter;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         float* ib_pair = &s_ib[quarter][0][0];
         const int pt = half * 32 + lane;     // thread index within the pair (0..63)
-        const int bar_id = 1 + quarter;
+        ExCursor ex;
+        ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
+        // bias value of column `col` of tile `tt` (0 beyond the table / without item bias)
+        auto ib_at = [&](int tt, int col) -> float {
+            const int64_t n = (int64_t)(t_begin + tt) * TC_BN + col;
+            return (a.Ib && tt < n_my_tiles && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
+        };
 
-        // item-bias tile of the first tile -> shared memory (each pair keeps its own copy: no CTA-wide sync needed)
-        {
-            const int64_t n0 = (int64_t)t_begin * TC_BN;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t n = n0 + pt + 64 * h;
-                ib_pair[pt + 64 * h] = (a.Ib && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
-            }
+        // prologue: the bias rows of the first TC_ACC_STAGES tiles go into the stages (through the pair's staging tile), the
+        // stages to the MMA warp; then the staging slot of tile TC_ACC_STAGES is filled for the first loop iteration
+        for (int ts = 0; ts < TC_ACC_STAGES && ts < n_my_tiles; ++ts) {
+            ib_pair[pt] = ib_at(ts, pt);
+            ib_pair[pt + 64] = ib_at(ts, pt + 64);
+            named_bar_sync(bar_id, 64);
+            tc_write_bias<2>(ib_pair + half * 64, tlane + (uint32_t)ts * TC_BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[ts]);
+            named_bar_sync(bar_id, 64);
         }
+        ib_pair[pt] = ib_at(TC_ACC_STAGES, pt);                 // slot 0 <- tile 4 (consumed at t = 0)
+        ib_pair[pt + 64] = ib_at(TC_ACC_STAGES, pt + 64);
         named_bar_sync(bar_id, 64);
 
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t % TC_ACC_STAGES;
-            const int ibs = t & 1;
             const int64_t n0 = (int64_t)(t_begin + t) * TC_BN;
             const int ncols = (int)min((int64_t)TC_BN, a.n_local - n0);
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
-            const float* ibt = ib_pair + ibs * TC_BN;
-            // prefetch the next tile's bias values into registers (stored to the other smem stage after the scan)
-            float ibn0 = 0.f, ibn1 = 0.f;
-            if (t + 1 < n_my_tiles && a.Ib) {
-                const int64_t nn = n0 + TC_BN + pt;
-                if (nn < a.n_local) ibn0 = __ldg(a.Ib + nn);
-                if (nn + 64 < a.n_local) ibn1 = __ldg(a.Ib + nn + 64);
-            }
+            // the bias values the NEXT iteration writes (tile t + 5): in flight during this tile, stored before the pair barrier
+            const float ibn0 = ib_at(t + 1 + TC_ACC_STAGES, pt), ibn1 = ib_at(t + 1 + TC_ACC_STAGES, pt + 64);
             mbar_wait(&bar_tfull[as], ((uint32_t)t / TC_ACC_STAGES) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * TC_BN + (uint32_t)(half * 64);
+            const uint32_t taddr = tlane + (uint32_t)as * TC_BN;
             uint32_t raw0[32], raw1[32];
             tc_ld32_issue(taddr, raw0);
             tc_ld32_issue(taddr + 32u, raw1);
             tc_ld_wait();
-            // both chunks are in registers: release the accumulator stage right away (MMA of tile t+2 may start)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            // both chunks are in registers: refill the stage with the bias row of tile t + 4 and release it right away
+            if (t + TC_ACC_STAGES < n_my_tiles) {
+                tc_write_bias<2>(ib_pair + (t & 1) * TC_BN + half * 64, taddr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            }
             {   // two inlined copies of the chunk body: chunk 0 reads raw0, chunk 1 reads raw1 in place
                 auto chunk = [&](const uint32_t (&raw)[32], int cc) {
                     const int c = half * 64 + cc * 32;
                     if (c >= ncols) return;
-                    float v[32];
-                    const float4* ib4 = reinterpret_cast<const float4*>(ibt + c);
-                    float mx = -INFINITY;
+                    float v[32], g[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b4 = ib4[q];
-                        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b4.x;
-                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
-                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z;
-                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
-                        mx = fmaxf(mx, fmaxf(fmaxf(v[4 * q + 0], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+                    if (ncols - c < 32) {            // ragged last tile: columns beyond the table become NaN (never a candidate)
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = (e < ncols - c) ? v[e] : __int_as_float(0x7fc00000);
                     }
-                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
-                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
+                    const float mx = tc_chunk_max(v, g);
                     if (row_ok && mx >= tau)
-                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
-                                      cnt, region);
+                        tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
+                                       region, ex);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);
             }
-            ib_pair[(ibs ^ 1) * TC_BN + pt] = ibn0;
-            ib_pair[(ibs ^ 1) * TC_BN + pt + 64] = ibn1;
+            ib_pair[((t + 1) & 1) * TC_BN + pt] = ibn0;          // staging slot of tile t + 5, read after the pair barrier below
+            ib_pair[((t + 1) & 1) * TC_BN + pt + 64] = ibn1;
             // Does any row of this pair need its list cut before the next tile?  Common case: no -> one flag store, one
             // pair barrier, one flag load per tile.  Only when a list may overflow (or at the last tile) do the two warps
             // exchange their counts and run the cut protocol (two more pair barriers).
@@ -239,17 +242,13 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
                     float ntau;
                     uint64_t ntaukey;
-                    // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors)
-                    // no exclusion test in the intermediate cuts when k + n_excl raw keys still fit comfortably (each half
-                    // keeps total / 2 <= 160 of its 256 slots); the last cut always tests and keeps <= 192 for the final sort
-                    const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > 288;
-                    const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
-                                                 s_exhi[rr], check, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey);
+                    // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors);
+                    // intermediate cuts keep <= 160 of a half's 256 slots, the last one <= 192 in all for the final sort
+                    const int total = tc_cut_row(lp, cA, cB, a.k, lane, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey);
                     __syncwarp();
                     const int nA = (total + 1) >> 1;
                     if (lane == 0) {
                         s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA;
-                        s_chk2[0][rr] = check ? nA : 0; s_chk2[1][rr] = check ? total - nA : 0;
                         s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
                     }
                     if (last) {

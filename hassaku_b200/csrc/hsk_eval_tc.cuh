@@ -93,38 +93,110 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Epilogue of one 32-column chunk for one row: v[] already holds score' = acc + item bias (the per-row user/global bias
-// does not change the ranking inside a row and is added when the final scores are written).
-// `region` is this thread's PRIVATE half of the row's candidate list (the other column half of the row appends to the
-// other half), so an append is a register increment and a fire-and-forget store: no atomics, no dependent latency
-// (measured: with a shared counter an append cost ~280 cycles of warp time and dominated the epilogue).
-// Two steps: (1) a branch-free 32-bit survivor mask (one FSETP + one bit insert per element); (2) a short loop over the
-// set bits — survivors are rare (~5 per 1024 elements in steady state), so almost every lane runs 0 or 1 iteration.
-// The value of element e is pulled out of the register array with a 5-level select tree (no local memory).  An unrolled
-// `if (...) append` per element made the hot loop ~50 KB of divergent code that thrashed the I-cache (4.5 k cycles/scan).
-__device__ __forceinline__ float tc_pick(const float (&v)[32], int e) {
-    float a16[16], a8[8], a4[4], a2[2];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a16[i] = (e & 16) ? v[16 + i] : v[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a8[i] = (e & 8) ? a16[8 + i] : a16[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a4[i] = (e & 4) ? a8[4 + i] : a8[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) a2[i] = (e & 2) ? a4[2 + i] : a4[i];
-    return (e & 1) ? a2[1] : a2[0];
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]), "f"(r[9]), "f"(r[10]),
+        "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]), "f"(r[16]), "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]),
+        "f"(r[21]), "f"(r[22]), "f"(r[23]), "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]),
+        "f"(r[31])
+        : "memory");
 }
-__device__ __forceinline__ void tc_scan_chunk(const float (&v)[32], float tau, uint64_t taukey, uint32_t valid, uint32_t gid0,
-                                              uint32_t id_stride, int& cnt, uint64_t* region) {
-    uint32_t mask = 0;
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3 (sm_100)
+    float d;
+    asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// The item-bias row of NCHUNK x 32 consecutive items -> TMEM columns [taddr, +NCHUNK * 32) of this thread's lane (every lane =
+// user row gets the same values).  The MMA of that tile then accumulates on top (enable_input_d = 1), so the epilogue reads
+// score' = bias + <u, v> straight from the accumulator: no bias add in the hot loop.  `sb` = the bias values in SHARED memory
+// (staged one tile ahead by the pair, so no global-memory latency sits between reading a stage and releasing it); the
+// loads are warp-uniform 128-bit broadcasts.
+template <int NCHUNK>
+__device__ __forceinline__ void tc_write_bias(const float* sb, uint32_t taddr) {
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+        float b[32];
+        const float4* p4 = reinterpret_cast<const float4*>(sb + c * 32);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) mask |= (v[e] >= tau) ? (1u << e) : 0u;
-    mask &= valid;
-    while (mask) {
-        const int e = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint64_t key = make_key(tc_pick(v, e), gid0 + (uint32_t)e * id_stride);
-        if (key > taukey) region[cnt++] = key;
+        for (int q = 0; q < 8; ++q) {
+            const float4 x = p4[q];
+            b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+        }
+        tc_st32(taddr + (uint32_t)(c * 32), b);
+    }
+    tc_st_wait();
+}
+
+// ---- the user's exclusion row as a CURSOR: a thread meets its candidates in ascending item-id order (tiles, chunks and
+// elements are all walked upwards), and the CSR row is sorted, so "is this id excluded?" is a comparison with the next
+// unconsumed exclusion — the mask of eval/eval.py:250-251 is applied at the append, exactly, with <= n_excl dependent loads
+// per thread over the whole sweep.  (Round 1 kept raw candidates and tested them at the list cuts with lock-step binary
+// searches, which forced the lists to hold k + n_excl entries and made every cut ~5x more expensive.)
+struct ExCursor {
+    const int32_t* __restrict__ idx;
+    int64_t pos, hi;
+    uint32_t next;          // indices[pos], or 0xFFFFFFFF when the row is used up
+};
+__device__ __forceinline__ void ex_init(ExCursor& c, const int32_t* __restrict__ idx, int64_t lo, int64_t hi) {
+    c.idx = idx; c.pos = lo; c.hi = hi;
+    c.next = lo < hi ? (uint32_t)__ldg(idx + lo) : 0xFFFFFFFFu;
+}
+__device__ __forceinline__ bool ex_excluded(ExCursor& c, uint32_t gid) {
+    while (c.next < gid) {
+        ++c.pos;
+        c.next = c.pos < c.hi ? (uint32_t)__ldg(c.idx + c.pos) : 0xFFFFFFFFu;
+    }
+    return c.next == gid;
+}
+
+// Epilogue of one 32-column chunk for one row: v[] holds score' = item bias + dot (the per-row user / global bias does not
+// change the ranking inside a row and is added when the final scores are written).  `region` is this thread's PRIVATE
+// half of the row's candidate list, so an append is a register increment and a fire-and-forget store.
+// tc_chunk_max: 8 group maxima of 4 (FMNMX3 + FMNMX each) and their maximum (NaN = a column beyond the table: ignored by
+// max).  tc_scan_groups: only the groups whose maximum reaches the row's threshold are looked at — per row-chunk a
+// survivor is rare (~6 %), but per WARP (32 rows with their own thresholds) some lane almost always has one, so this
+// divergent path is the common path and its length, not the all-clear path, sets the epilogue's cost.
+__device__ __forceinline__ float tc_chunk_max(const float (&v)[32], float (&g)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmax3(v[4 * j], v[4 * j + 1], v[4 * j + 2]), v[4 * j + 3]);
+    return fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+}
+// Kept compact and branch-poor on purpose.  Measured alternatives (18 944 users x 1 M items x 256, bf16, one-CTA kernel):
+//   one guarded append block per element, fully unrolled (105 KB of kernel body)                 34.3 ms
+//   warp-uniform vote per group (8 x __any_sync + branch per chunk, group values as named registers)  14.6 ms
+//   this version: an 8-bit mask of the groups whose maximum reaches the threshold (8 compares), then per set bit the group's
+//   4 values pulled out of the register array by a 3-level select tree (28 selects, no local memory)   10.7 ms
+// — every taken branch in this divergent path costs an instruction-fetch bubble, selects do not.
+__device__ __forceinline__ void tc_scan_groups(const float (&v)[32], const float (&g)[8], float tau, uint64_t taukey, uint32_t gid0,
+                                               uint32_t id_stride, int& cnt, uint64_t* region, ExCursor& ex) {
+    uint32_t gm = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gm |= (g[j] >= tau) ? (1u << j) : 0u;
+    while (gm) {
+        const int j = __ffs(gm) - 1;
+        gm &= gm - 1;
+        float a16[16], a8[8], a4[4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a16[i] = (j & 4) ? v[16 + i] : v[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a8[i] = (j & 2) ? a16[8 + i] : a16[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a4[i] = (j & 1) ? a8[4 + i] : a8[i];
+        uint32_t em = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) em |= (a4[q] >= tau) ? (1u << q) : 0u;     // NaN (a column beyond the table) never passes
+        while (em) {
+            const int q = __ffs(em) - 1;
+            em &= em - 1;
+            const float x = (q & 2) ? ((q & 1) ? a4[3] : a4[2]) : ((q & 1) ? a4[1] : a4[0]);
+            const uint32_t gid = gid0 + (uint32_t)(4 * j + q) * id_stride;
+            const uint64_t key = make_key(x, gid);
+            if (key > taukey && !ex_excluded(ex, gid)) region[cnt++] = key;
+        }
     }
 }
 
@@ -135,36 +207,16 @@ constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
 // below T is dropped, the survivors (k plus the few ties of the T bucket) are compacted and written back split over the
 // two halves.  The new threshold is the lower edge of bucket T — conservative, so no top-k item is ever lost; the exact
 // order is established once, by the final sort.  ~1.5 k cycles instead of ~56 k for the 512-key bitonic network.
-// Entries beyond chkA / chkB are first tested against the user's exclusion row (lock-step binary searches).
-// Returns the number of survivors.
-static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int chkA, int chkB, int k, int lane,
-                                          const int32_t* __restrict__ excl, int64_t lo, int64_t hi, bool check, int max_keep,
-                                          float* new_tau, uint64_t* new_taukey) {
-    // check == false: the exclusion test is postponed to the final cut.  At most n_excl = hi - lo excluded items can sit
-    // in the list, so selecting the (k + n_excl)-th largest RAW key is still a conservative threshold; it saves the
-    // ~11 k cycles of binary searches that made every cut stall the MMA pipeline.
-    if (!check) k += (int)(hi - lo);
+// Every entry is an admissible item (exclusions are dropped at the append).  Returns the number of survivors.
+static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int k, int lane, int max_keep, float* new_tau,
+                                              uint64_t* new_taukey) {
     uint64_t key[TC_KPL];
-    bool unchecked[TC_KPL];
 #pragma unroll
     for (int r = 0; r < TC_KPL; ++r) {
         const int e = r * 32 + lane;
         const bool inA = e < TC_HALF_CAP;
         const int idx = inA ? e : e - TC_HALF_CAP;
-        const bool valid = idx < (inA ? cA : cB);
-        key[r] = valid ? lp[e] : 0ull;
-        unchecked[r] = valid && idx >= (inA ? chkA : chkB);
-    }
-    if (check && hi > lo) {
-        int32_t id[TC_KPL];
-        bool found[TC_KPL];
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r) id[r] = key[r] ? key_id(key[r]) : -1;
-        if (hi - lo <= 384) csr_contains_bcast<TC_KPL>(excl, lo, hi, id, found, lane);   // short row: one coalesced pass
-        else csr_contains_many<TC_KPL>(excl, lo, hi, id, unchecked, found);             // long row: lock-step searches
-#pragma unroll
-        for (int r = 0; r < TC_KPL; ++r)
-            if (found[r] && key[r]) key[r] = make_key(-INFINITY, (uint32_t)id[r]);
+        key[r] = (idx < (inA ? cA : cB)) ? lp[e] : 0ull;
     }
     const int n = cA + cB;
     uint32_t T = 0;

@@ -51,8 +51,11 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on 
                      "r"(smem_u32(bar)), "h"((uint16_t)3)
                  : "memory");
 }
+// Arrive on the LEADER CTA's barrier.  No .release.cluster here: that form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per
+// tile and warp (17 % of the kernel's stall samples, ncu r02); nothing in generic memory is handed over through this
+// barrier — the TMEM writes it guards are ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(leader_addr(bar)) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(leader_addr(bar)) : "memory");
 }
 template <bool TF32>
 __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -66,45 +69,6 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t adesc, uin
                      : "memory");
     }
 }
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
-        "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]), "f"(r[9]), "f"(r[10]),
-        "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]), "f"(r[16]), "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]),
-        "f"(r[21]), "f"(r[22]), "f"(r[23]), "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]),
-        "f"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
-
-// the item-bias row of one tile's column half -> the accumulator stage (every lane = user row gets the same 128 values)
-__device__ __forceinline__ void t2_write_bias(const float* __restrict__ Ib, bool ib_vec, int64_t n_col0, int64_t n_local, uint32_t taddr) {
-#pragma unroll 1
-    for (int c = 0; c < T2_HALF_COLS / 32; ++c) {
-        float b[32];
-        const int64_t n = n_col0 + c * 32;
-        if (Ib && ib_vec && n + 32 <= n_local) {       // warp-uniform address: one broadcast transaction per float4
-            const float4* p4 = reinterpret_cast<const float4*>(Ib + n);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 x = __ldg(p4 + q);
-                b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) b[e] = (Ib && n + e < n_local) ? __ldg(Ib + n + e) : 0.f;
-        }
-        tc_st32(taddr + (uint32_t)(c * 32), b);
-    }
-    tc_st_wait();
-}
-
 template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
@@ -113,11 +77,12 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_tau[TC_BM];
     __shared__ uint64_t s_taukey[TC_BM];
-    __shared__ int s_cnt2[2][TC_BM], s_chk2[2][TC_BM];
+    __shared__ int s_cnt2[2][TC_BM];
     __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
     __shared__ float s_base[TC_BM];
     __shared__ int s_rowok[TC_BM];
     __shared__ int s_need[4][2][2];
+    __shared__ __align__(16) float s_ib[4][2][T2_BN];   // per pair: item-bias tiles staged one tile ahead of their TMEM write
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -161,7 +126,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (a.Gb) base += a.Gb[0];
         s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
         s_tau[r] = -INFINITY; s_taukey[r] = 0ull;
-        s_cnt2[0][r] = s_cnt2[1][r] = 0; s_chk2[0][r] = s_chk2[1][r] = 0;
+        s_cnt2[0][r] = s_cnt2[1][r] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -228,16 +193,31 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint64_t* region = list + half * TC_HALF_CAP;
         int cnt = 0;
         const int bar_id = 1 + quarter;
-        const bool ib_vec = (reinterpret_cast<uintptr_t>(a.Ib) & 15) == 0;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * T2_HALF_COLS);
+        float* ib_pair = &s_ib[quarter][0][0];
+        const int pt = half * 32 + lane;     // thread index within the pair (0..63)
+        ExCursor ex;
+        ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
+        // bias value of column `col` of tile `tt` (0 beyond the table / without item bias)
+        auto ib_at = [&](int tt, int col) -> float {
+            const int64_t n = (int64_t)(t_begin + tt) * T2_BN + col;
+            return (a.Ib && tt < n_my_tiles && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
+        };
 
-        // prologue: bias rows of the first two tiles, then hand both stages to the MMA warp
+        // prologue: bias rows of the first two tiles into the stages (through the pair's staging tile), stages to the MMA warp
         for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
-            t2_write_bias(a.Ib, ib_vec, (int64_t)(t_begin + ts) * T2_BN + half * T2_HALF_COLS, a.n_local, tlane + (uint32_t)ts * T2_BN);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) ib_pair[pt + 64 * h] = ib_at(ts, pt + 64 * h);
+            named_bar_sync(bar_id, 64);
+            tc_write_bias<T2_HALF_COLS / 32>(ib_pair + half * T2_HALF_COLS, tlane + (uint32_t)ts * T2_BN);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&bar_tempty[ts]);
+            named_bar_sync(bar_id, 64);
         }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) ib_pair[pt + 64 * h] = ib_at(T2_ACC_STAGES, pt + 64 * h);   // slot 0 <- tile 2 (consumed at t = 0)
+        named_bar_sync(bar_id, 64);
 
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
@@ -245,6 +225,10 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int ncols = (int)min((int64_t)T2_BN, a.n_local - n0);
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
+            // the bias values the NEXT iteration writes (tile t + 3): in flight during this tile
+            float ibn[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, pt + 64 * h);
             mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)as * T2_BN;
@@ -257,30 +241,30 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 auto chunk = [&](const uint32_t (&raw)[32], int cc) {
                     const int c = half * T2_HALF_COLS + cp * 64 + cc * 32;     // column of the tile
                     if (c >= ncols) return;
-                    float v[32];
+                    float v[32], g[8];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                    float m0_ = fmax3(v[0], v[1], v[2]), m1_ = fmax3(v[3], v[4], v[5]);
+                    if (ncols - c < 32) {            // ragged last tile: columns beyond the table become NaN (never a candidate)
 #pragma unroll
-                    for (int e = 6; e + 3 < 32; e += 4) { m0_ = fmax3(m0_, v[e], v[e + 1]); m1_ = fmax3(m1_, v[e + 2], v[e + 3]); }
-                    float mx = fmax3(m0_, m1_, fmaxf(v[30], v[31]));
-                    const int nvalid = ncols - c;   // >= 32 except in the ragged last tile
-                    const uint32_t valid = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-                    if (nvalid < 32) mx = INFINITY;   // ragged: always take the (masked) scan
+                        for (int e = 0; e < 32; ++e) v[e] = (e < ncols - c) ? v[e] : __int_as_float(0x7fc00000);
+                    }
+                    const float mx = tc_chunk_max(v, g);
                     if (row_ok && mx >= tau)
-                        tc_scan_chunk(v, tau, taukey, valid, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride,
-                                      cnt, region);
+                        tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
+                                       region, ex);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);
             }
             // the stage has been read: write the bias row of tile t + 2 into it and hand it back to the MMA warp
             if (t + T2_ACC_STAGES < n_my_tiles) {
-                t2_write_bias(a.Ib, ib_vec, n0 + (int64_t)T2_ACC_STAGES * T2_BN + half * T2_HALF_COLS, a.n_local, taddr);
+                tc_write_bias<T2_HALF_COLS / 32>(ib_pair + (t & 1) * T2_BN + half * T2_HALF_COLS, taddr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
             }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) ib_pair[((t + 1) & 1) * T2_BN + pt + 64 * h] = ibn[h];   // staging slot of tile t + 3
             const bool last = (t + 1 == n_my_tiles);
             const bool warp_need = __any_sync(kFull, row_ok && cnt > T2_PRUNE_AT) || last;
             if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
@@ -306,16 +290,13 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
                     float ntau;
                     uint64_t ntaukey;
-                    // intermediate cuts skip the exclusion test while k + n_excl raw keys fit the 256 kept entries (<= 128 per
-                    // half, so that the next tile's <= 128 appends per half cannot overflow); the last cut always tests
-                    const bool check = last || (a.k + (s_exhi[rr] - s_exlo[rr])) > T2_KEEP_MID - 32;
-                    const int total = tc_cut_row(lp, cA, cB, s_chk2[0][rr], s_chk2[1][rr], a.k, lane, a.excl_indices, s_exlo[rr],
-                                                 s_exhi[rr], check, last ? 192 : T2_KEEP_MID, &ntau, &ntaukey);
+                    // intermediate cuts keep <= 128 entries per half, so that the next tile's <= 128 appends per half cannot
+                    // overflow its 256 slots; the last cut keeps <= 192 in all for the final sort
+                    const int total = tc_cut_row(lp, cA, cB, a.k, lane, last ? 192 : T2_KEEP_MID, &ntau, &ntaukey);
                     __syncwarp();
                     const int nA = (total + 1) >> 1;
                     if (lane == 0) {
                         s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA;
-                        s_chk2[0][rr] = check ? nA : 0; s_chk2[1][rr] = check ? total - nA : 0;
                         s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
                     }
                     if (last) {

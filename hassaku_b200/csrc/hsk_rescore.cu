@@ -32,17 +32,19 @@ struct RescoreArgs {
     int32_t* status;
 };
 
-template <int NV>
+// POSITIONAL (item-sharded evaluation): no selection — out_scores[row, c] = the fp32 score of candidate c if THIS shard owns
+// it ((id - id_offset) % id_stride == 0), else -inf; ids of other shards are expected and not reported.
+template <int NV, bool POSITIONAL>
 __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= a.Be) return;
     const int64_t u = a.u_idx[row];
-    float* os = a.out_scores + (int64_t)row * a.k;
-    int32_t* oi = a.out_ids + (int64_t)row * a.k;
+    float* os = a.out_scores + (int64_t)row * (POSITIONAL ? a.n_cand : a.k);
+    int32_t* oi = POSITIONAL ? nullptr : a.out_ids + (int64_t)row * a.k;
     if (bad_index(u, a.n_users)) {
         if (lane == 0 && a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
-        for (int e = lane; e < a.k; e += 32) { os[e] = -INFINITY; oi[e] = -1; }
+        for (int e = lane; e < (POSITIONAL ? a.n_cand : a.k); e += 32) { os[e] = -INFINITY; if (!POSITIONAL) oi[e] = -1; }
         return;
     }
     Row<NV> ur;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
             const int64_t rel = (int64_t)gid[r] - a.id_offset;
             const int64_t l = rel / a.id_stride;
             if (rel < 0 || l * a.id_stride != rel || l >= a.n_local) {
-                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
+                if (!POSITIONAL && a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
                 gid[r] = -1;
             } else {
                 loc[r] = l;
@@ -98,7 +100,12 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
             if (a.Ib) sc += __ldg(a.Ib + loc[r]);
             key[r] = make_key(masked[r] ? -INFINITY : sc, (uint32_t)gid[r]);
         }
+        if (POSITIONAL) {
+            const int c = r * 32 + lane;
+            if (c < a.n_cand) os[c] = (loc[r] >= 0 && !masked[r]) ? sc + base : -INFINITY;
+        }
     }
+    if (POSITIONAL) return;
     warp_sort_desc<kRescoreKPL>(key, lane);
 #pragma unroll
     for (int r = 0; r < kRescoreKPL; ++r) {
@@ -134,6 +141,73 @@ extern "C" int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, i
     const int nv = (a.nvec + 31) / 32;
     const int blocks = (Be + 7) / 8;
     cudaStream_t s = as_stream(stream);
-    HSK_DISPATCH_NV(nv, (rescore_topk_kernel<NV><<<blocks, 256, 0, s>>>(a)));
+    HSK_DISPATCH_NV(nv, (rescore_topk_kernel<NV, false><<<blocks, 256, 0, s>>>(a)));
     return check_launch("hsk_rescore_topk");
+}
+
+extern "C" int hsk_rescore_scores(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,
+                                  const int32_t* cand_ids, int n_cand, float* out_scores, int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(t && t->Uw && t->Vw && u_rows && cand_ids && out_scores, "hsk_rescore_scores: null pointer");
+    HSK_REQUIRE(t->d >= 1 && t->ld >= t->d && t->ld % 4 == 0 && t->ld <= 1024, "hsk_rescore_scores: bad table shape");
+    HSK_REQUIRE(aligned16(t->Uw) && aligned16(t->Vw), "hsk_rescore_scores: tables must be 16-byte aligned");
+    HSK_REQUIRE(n_cand >= 1 && n_cand <= kRescoreMax, "hsk_rescore_scores: need 1 <= n_cand <= %d", kRescoreMax);
+    HSK_REQUIRE(id_stride >= 1 && id_offset >= 0 && Be >= 0, "hsk_rescore_scores: bad id mapping / batch");
+    if (Be == 0) return HSK_OK;
+    RescoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Uw = t->Uw; a.Vw = t->Vw; a.Ub = t->Ub; a.Ib = t->Ib; a.Gb = t->Gb;
+    a.u_idx = u_rows; a.cand = cand_ids;
+    a.n_users = t->n_users; a.n_local = t->n_items; a.id_offset = id_offset; a.id_stride = id_stride;
+    a.Be = Be; a.n_cand = n_cand; a.k = n_cand; a.ld = t->ld; a.nvec = t->ld / 4;
+    a.out_scores = out_scores; a.status = status;
+    const int nv = (a.nvec + 31) / 32;
+    const int blocks = (Be + 7) / 8;
+    cudaStream_t s = as_stream(stream);
+    HSK_DISPATCH_NV(nv, (rescore_topk_kernel<NV, true><<<blocks, 256, 0, s>>>(a)));
+    return check_launch("hsk_rescore_scores");
+}
+
+// ---- item-sharded evaluation, last step: the owner of a user row holds the merged candidate ids [rows, n_cand] and, from
+// every shard, the positional fp32 scores [G, rows, n_cand] (finite only where that shard owns the item): the score of a
+// candidate is the maximum over the shards; the k best by (score desc, id asc) are the row's result.
+namespace hsk {
+__global__ void __launch_bounds__(256) topk_combine_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids, int G,
+                                                           int rows, int n_cand, int k, float* __restrict__ out_s,
+                                                           int32_t* __restrict__ out_i) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    uint64_t key[kRescoreKPL];
+#pragma unroll
+    for (int r = 0; r < kRescoreKPL; ++r) {
+        const int c = r * 32 + lane;
+        key[r] = 0ull;
+        if (c < n_cand) {
+            const int32_t id = ids[(int64_t)row * n_cand + c];
+            if (id >= 0) {
+                float sc = -INFINITY;
+                for (int q = 0; q < G; ++q) sc = fmaxf(sc, scores[((int64_t)q * rows + row) * n_cand + c]);
+                key[r] = make_key(sc, (uint32_t)id);
+            }
+        }
+    }
+    warp_sort_desc<kRescoreKPL>(key, lane);
+#pragma unroll
+    for (int r = 0; r < kRescoreKPL; ++r) {
+        const int e = r * 32 + lane;
+        if (e < k) {
+            out_s[(int64_t)row * k + e] = key[r] ? key_score(key[r]) : -INFINITY;
+            out_i[(int64_t)row * k + e] = key_id(key[r]);
+        }
+    }
+}
+}  // namespace hsk
+
+extern "C" int hsk_topk_combine(const float* scores, const int32_t* ids, int G, int rows, int n_cand, int k, float* out_scores,
+                                int32_t* out_ids, hsk_stream_t stream) {
+    HSK_REQUIRE(scores && ids && out_scores && out_ids, "hsk_topk_combine: null pointer");
+    HSK_REQUIRE(G >= 1 && rows >= 0 && n_cand >= 1 && n_cand <= kRescoreMax && k >= 1 && k <= n_cand, "hsk_topk_combine: bad sizes");
+    if (rows == 0) return HSK_OK;
+    topk_combine_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(scores, ids, G, rows, n_cand, k, out_scores, out_ids);
+    return check_launch("hsk_topk_combine");
 }

@@ -473,6 +473,10 @@ class ShardedMF:
         Be = G * bs
         kc = min(128, k + self.RESCORE_MARGIN, lay.n_items) if (prec != 0 and rescore) else k
         do_rescore = kc > k
+        # G > 1: re-score AFTER the merge — the shards exchange their low-precision top-kc lists, the owner merges them to the
+        # global top-kc, every shard scores in fp32 only the merged candidates it owns (kc / G per user on average instead of
+        # kc per user and shard), the owner combines: the fp32 work shards with the items like the scoring itself
+        late = do_rescore and G > 1
         if prec == 0:
             scratch = torch.empty(_C.eval_topk_scratch_bytes(Be, lay.n_items, k), dtype=torch.uint8, device=dev)
         else:
@@ -485,7 +489,10 @@ class ShardedMF:
         bufs = [{'rows': f32(bs, ld), 'ubias': f32(bs), 'gids': i64(bs), 'all_rows': f32(Be, ld), 'all_ub': f32(Be),
                  'all_gids': i64(Be), 'safe': i64(Be), 'top_s': f32(Be, k), 'top_i': i32(Be, k),
                  'cand_s': f32(Be, kc) if do_rescore else None, 'cand_i': i32(Be, kc) if do_rescore else None,
-                 'recv_s': f32(G, bs, k), 'recv_i': i32(G, bs, k), 'ms': f32(bs, k), 'mi': i32(bs, k),
+                 'recv_s': f32(G, bs, kc if late else k), 'recv_i': i32(G, bs, kc if late else k), 'ms': f32(bs, k), 'mi': i32(bs, k),
+                 'mcs': f32(bs, kc) if late else None, 'mci': i32(bs, kc) if late else None,
+                 'all_mci': i32(Be, kc) if late else None, 'sc': f32(Be, kc) if late else None,
+                 'recv_sc': f32(G, bs, kc) if late else None,
                  'ready': None, 'scored': None, 'merged': None} for _ in range(2)]
         u_rows = torch.arange(Be, dtype=torch.int64, device=dev)
         starts = list(range(0, cap, bs))
@@ -538,7 +545,7 @@ class ShardedMF:
                 _C.eval_topk_tc(Uq, Vq, prec, b['safe'], self.spec.n_users, kc, cs, ci, scratch, Ub=ub, Ib=Ib, Gb=Gb,
                                 excl_indptr=exclude.indptr, excl_indices=exclude.indices, id_offset=r, id_stride=G,
                                 status=self.status, u_rows=u_rows)
-                if do_rescore:
+                if do_rescore and not late:
                     _C.rescore_topk(t, u_rows, ci, k, b['top_s'], b['top_i'], id_offset=r, id_stride=G, status=self.status,
                                     cand_scores=cs)
             if use_streams:
@@ -550,10 +557,21 @@ class ShardedMF:
             with on_comm():
                 if use_streams:
                     comm.wait_event(b['scored'])
-                self._a2a(b['recv_s'], b['top_s'].view(G, bs, k))
-                self._a2a(b['recv_i'], b['top_i'].view(G, bs, k))
-                if b['n_mine'] > 0:
+                if late:
+                    self._a2a(b['recv_s'], b['cand_s'].view(G, bs, kc))
+                    self._a2a(b['recv_i'], b['cand_i'].view(G, bs, kc))
+                    _C.topk_merge(b['recv_s'], b['recv_i'], b['mcs'], b['mci'])          # global top-kc by low-precision score
+                    self._all_gather(b['all_mci'], b['mci'])
+                    ub = b['all_ub'] if Ub is not None else None
+                    t = _C.make_tables(b['all_rows'][:, :lay.d], Vw, ub, Ib, Gb, lay.d)
+                    _C.rescore_scores(t, u_rows, b['all_mci'], b['sc'], id_offset=r, id_stride=G, status=self.status)
+                    self._a2a(b['recv_sc'], b['sc'].view(G, bs, kc))
+                    _C.topk_combine(b['recv_sc'], b['mci'], k, b['ms'], b['mi'])
+                else:
+                    self._a2a(b['recv_s'], b['top_s'].view(G, bs, k))
+                    self._a2a(b['recv_i'], b['top_i'].view(G, bs, k))
                     _C.topk_merge(b['recv_s'], b['recv_i'], b['ms'], b['mi'])
+                if b['n_mine'] > 0:
                     n = b['n_mine']
                     evaluator.eval_batch_topk(b['gids'][:n].contiguous(), b['mi'][:n].contiguous(), labels)
                 if use_streams:

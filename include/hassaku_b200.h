@@ -262,6 +262,18 @@ HSK_API int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, int 
                              const int32_t* cand_ids, const float* cand_scores /* nullable */, int n_cand, int k,
                              float* top_scores, int32_t* top_ids, int32_t* status, hsk_stream_t stream);
 
+/* Item-sharded evaluation re-scores AFTER the merge, so that the fp32 work shards with the items (each shard scores only
+ * the merged candidates it owns, ~n_cand / G per user) instead of every shard re-scoring its own n_cand:
+ *   hsk_rescore_scores  positional: out_scores[r, c] = the fp32 score of cand_ids[r, c] if this shard owns it
+ *                       ((id - id_offset) % id_stride == 0), else -inf (ids of other shards are expected here);
+ *   hsk_topk_combine    on the row's owner: scores [G, rows, n_cand] from all shards + the merged ids [rows, n_cand] ->
+ *                       candidate score = max over shards, then the k best ordered like hsk_eval_topk. */
+HSK_API int hsk_rescore_scores(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,
+                               const int32_t* cand_ids, int n_cand, float* out_scores /* [Be, n_cand] */, int32_t* status,
+                               hsk_stream_t stream);
+HSK_API int hsk_topk_combine(const float* scores, const int32_t* ids, int G, int rows, int n_cand, int k, float* out_scores,
+                             int32_t* out_ids, hsk_stream_t stream);
+
 /* ---- merge of G per-shard top-k lists (item-sharded evaluation: all-gather, then this) --------------------------
  * scores/ids: [G, rows, k] (id < 0 = empty slot) -> out [rows, k], same ordering rule as hsk_eval_topk. */
 HSK_API int hsk_topk_merge(const float* scores, const int32_t* ids, int G, int rows, int k, float* out_scores,
