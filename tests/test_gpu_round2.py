@@ -283,9 +283,12 @@ def test_sharded_evaluate_at_world_1_equals_the_single_gpu_sweep():
         single.eval_precision = prec
         ref = evaluate_recommender_algorithm(single, L, FullEvaluator(True, 2, ds.user_to_user_group), 'cuda')
         got = smf.evaluate(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=200, precision=prec)
-        assert sorted(got) == sorted(ref)
+        rep = smf.evaluate_replicated(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=300,
+                                      precision=prec)
+        assert sorted(got) == sorted(ref) == sorted(rep)
         for k_, v in ref.items():
             assert abs(got[k_] - v) <= 1e-9, (prec, k_, got[k_], v)
+            assert abs(rep[k_] - v) <= 1e-9, (prec, 'replicated', k_, rep[k_], v)
     smf.check_status()
 
 

@@ -189,9 +189,12 @@ def _worker_tc_eval(rank, world, port, out_dir):
             ref = evaluate_recommender_algorithm(single, L, FullEvaluator(True, 2, ds.user_to_user_group), dev)
             got = smf.evaluate(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=200,
                                precision=prec)
-            assert sorted(got) == sorted(ref)
+            rep = smf.evaluate_replicated(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=256,
+                                          precision=prec)
+            assert sorted(got) == sorted(ref) == sorted(rep)
             for k_, v in ref.items():
                 assert abs(got[k_] - v) <= 1e-6, (prec, k_, got[k_], v)
+                assert abs(rep[k_] - v) <= 1e-6, (prec, 'replicated', k_, rep[k_], v)
         assert int(smf.status.item()) == 0
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
