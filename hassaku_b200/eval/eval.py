@@ -15,7 +15,7 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
-from hassaku_b200 import _C
+from hassaku_b200 import _C, nvtx
 from hassaku_b200.algorithms.base_classes import RecommenderAlgorithm
 from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
 from hassaku_b200.eval.metrics import (dense_topk, discount_table, hellinger_distance, hit_from_precision,
@@ -471,11 +471,12 @@ def evaluate_mf_sweep(alg: SGDMatrixFactorization, labels: DeviceCSR, exclude: O
         starts = range(0, n_users, batch_size)
         user_batches = (torch.arange(s, min(s + batch_size, n_users), dtype=torch.int64, device=dev)
                         for s in (tqdm(starts) if verbose else starts))
-    with torch.no_grad():
+    with torch.no_grad(), nvtx.range('hsk.eval_sweep'):
         for u_idxs in user_batches:
-            u_idxs = u_idxs.to(dev, torch.int64, non_blocking=True)
-            _, ids = scorer(u_idxs, exclude)
-            evaluator.eval_batch_topk(u_idxs, ids, labels)
+            with nvtx.range('hsk.eval_batch'):
+                u_idxs = u_idxs.to(dev, torch.int64, non_blocking=True)
+                _, ids = scorer(u_idxs, exclude)
+                evaluator.eval_batch_topk(u_idxs, ids, labels)
     alg.check_status()
 
 

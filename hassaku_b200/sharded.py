@@ -37,7 +37,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from hassaku_b200 import _C
+from hassaku_b200 import _C, nvtx
 from hassaku_b200.algorithms.sgd_alg import ArenaLayout
 
 
@@ -416,7 +416,8 @@ class ShardedMF:
             exchange = ('dense' if dense else 'sparse') + ('_graph' if exchange == 'auto_graph' else '')
         fn = {'dense': self.train_step_dense, 'dense_graph': self.train_step_dense_graphed, 'sparse': self.train_step,
               'sparse_graph': self.train_step_graphed}[exchange]
-        return fn(u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled, capq=capq)
+        with nvtx.range('hsk.sharded_step'):
+            return fn(u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled, capq=capq)
 
     def pop_loss(self) -> float:
         """Sum over ranks of the batch-mean loss contributions since the last call (one all-reduce + host sync)."""
@@ -580,10 +581,11 @@ class ShardedMF:
         if starts:
             gather(0)
         for j in range(len(starts)):
-            if j + 1 < len(starts):
-                gather(j + 1)        # comm stream: runs under score(j)
-            score(j)
-            merge(j)                 # comm stream: runs under score(j + 1)
+            with nvtx.range('hsk.sharded_eval_round'):
+                if j + 1 < len(starts):
+                    gather(j + 1)        # comm stream: runs under score(j)
+                score(j)
+                merge(j)                 # comm stream: runs under score(j + 1)
         if use_streams:
             main.wait_stream(comm)
         # one all-reduce of the accumulators per sweep

@@ -1,7 +1,7 @@
 """One fused training step of SGDMatrixFactorization (train/trainer.py:133-148 of the reference)."""
 import torch
 
-from hassaku_b200 import _C
+from hassaku_b200 import _C, nvtx
 from hassaku_b200.train.optim import DenseAdam
 from hassaku_b200.train.rec_losses import RecommenderSystemLoss
 
@@ -45,6 +45,10 @@ class FusedMFTrainStep:
     def __call__(self, u_idxs: torch.Tensor, i_idxs: torch.Tensor, loss_out: torch.Tensor = None):
         """Enqueue one step.  `loss_out` (fp64 [1], device) receives this batch's mean loss added to it; by default
         the epoch accumulator is used."""
+        with nvtx.range('hsk.train_step'):
+            self._step(u_idxs, i_idxs, loss_out)
+
+    def _step(self, u_idxs, i_idxs, loss_out):
         slot = None
         if u_idxs.is_cuda and i_idxs.is_cuda:
             u = u_idxs.to(self.device, torch.int64).contiguous()

@@ -17,8 +17,8 @@ Files:
   mf_oracle.py   torch-CPU restatement (same ATen op sequence as the reference's Python)
   philox.py      numpy restatement of Philox4x32-10 and of the device negative sampler's index
                  spec (integer arithmetic, bit-exact contract), pinned by Random123 known answers
-  adamw_ref.c    plain-C restatement of torch.optim.AdamW's per-element arithmetic (CPU
-                 single-tensor order and CUDA foreach order), built by oracle/Makefile
+                 (the AdamW arithmetic has no C restatement here: its checker is torch.optim.AdamW /
+                 Adam / Adagrad themselves, bitwise, in tests/test_gpu_adamw.py)
   ref_shim.py    import shims for the real reference (build container only)
   make_golden.py generates tests/golden/ from the real reference (build container only)
 """
