@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libhassaku_b200.so')
+LIB_PATH = os.environ.get('HSK_LIB_PATH') or os.path.join(_HERE, 'lib', 'libhassaku_b200.so')   # override: experimental builds
 
 LOSS_KINDS = {'bpr': 0, 'sampled_softmax': 1, 'bce': 2}
 STATUS_BAD_INDEX = 1

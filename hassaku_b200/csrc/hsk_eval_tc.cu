@@ -244,7 +244,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint64_t ntaukey;
                     // (a degenerate tie bucket makes tc_cut_row fall back to its exact sort and return exactly k survivors);
                     // intermediate cuts keep <= 160 of a half's 256 slots, the last one <= 192 in all for the final sort
-                    const int total = tc_cut_row(lp, cA, cB, a.k, lane, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey);
+                    const int cc[2] = {cA, cB};
+                    const int total = tc_cut_row<2>(lp, cc, a.k, lane, last ? TC_HALF_CAP - TC_BN / 2 : 320, &ntau, &ntaukey);
                     __syncwarp();
                     const int nA = (total + 1) >> 1;
                     if (lane == 0) {
@@ -253,7 +254,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (last) {
                         uint64_t keys[kKeysPerLane];
-                        tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
+                        tc_final_sort<2>(lp, total, a.k, lane, keys);
                         if (a.n_splits == 1) {
                             const int64_t orow = (int64_t)(m0 + rr) * a.k;
                             const float base = s_base[rr];

@@ -200,25 +200,32 @@ __device__ __forceinline__ void tc_scan_groups(const float (&v)[32], const float
     }
 }
 
-constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half
+constexpr int TC_HALF_CAP = TC_CAP / 2;   // 256 entries per column half (two-region layout)
 
-// Cut a row's two half-lists (cA entries at lp[0..), cB entries at lp[256..)) back to ~k WITHOUT sorting: a radix select
-// on the 16 most significant bits of the keys finds the largest prefix T with count(prefix >= T) >= k; everything
-// below T is dropped, the survivors (k plus the few ties of the T bucket) are compacted and written back split over the
-// two halves.  The new threshold is the lower edge of bucket T — conservative, so no top-k item is ever lost; the exact
-// order is established once, by the final sort.  ~1.5 k cycles instead of ~56 k for the 512-key bitonic network.
-// Every entry is an admissible item (exclusions are dropped at the append).  Returns the number of survivors.
-static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int k, int lane, int max_keep, float* new_tau,
+// A row's candidate list of TC_CAP = 512 keys is split into NR regions (one per epilogue warp that shares the row: NR = 2
+// column halves, or 4 column quarters), region q at lp[q * (TC_CAP / NR) ..) with c[q] entries.
+//
+// tc_cut_row: cut the list back to ~k WITHOUT sorting: a radix select on the 16 most significant bits of the keys finds
+// the largest prefix T with count(prefix >= T) >= k; everything below T is dropped, the survivors (k plus the few ties of the
+// T bucket) are compacted and dealt round-robin to the regions (survivor #pos -> region pos % NR, slot pos / NR).  The new
+// threshold is the lower edge of bucket T — conservative, so no top-k item is ever lost; the exact order is established
+// once, by the final sort.  ~1.5 k cycles instead of ~56 k for the 512-key bitonic network.  Every entry is an admissible
+// item (exclusions are dropped at the append).  Returns the number of survivors; region q then holds
+// (total - q + NR - 1) / NR of them.
+template <int NR>
+static __device__ __noinline__ int tc_cut_row(uint64_t* lp, const int* c, int k, int lane, int max_keep, float* new_tau,
                                               uint64_t* new_taukey) {
+    constexpr int RC = TC_CAP / NR;
     uint64_t key[TC_KPL];
+    int n = 0;
+#pragma unroll
+    for (int q = 0; q < NR; ++q) n += c[q];
 #pragma unroll
     for (int r = 0; r < TC_KPL; ++r) {
         const int e = r * 32 + lane;
-        const bool inA = e < TC_HALF_CAP;
-        const int idx = inA ? e : e - TC_HALF_CAP;
-        key[r] = (idx < (inA ? cA : cB)) ? lp[e] : 0ull;
+        const int q = e / RC, idx = e % RC;
+        key[r] = (idx < c[q]) ? lp[e] : 0ull;
     }
-    const int n = cA + cB;
     uint32_t T = 0;
     if (n > k) {
         uint32_t pre[TC_KPL];
@@ -227,11 +234,11 @@ static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int 
 #pragma unroll 1
         for (int b = 15; b >= 0; --b) {
             const uint32_t cand = T | (1u << b);
-            int c = 0;
+            int cc = 0;
 #pragma unroll
-            for (int r = 0; r < TC_KPL; ++r) c += (pre[r] >= cand) ? 1 : 0;
-            c = __reduce_add_sync(kFull, c);
-            if (c >= k) T = cand;
+            for (int r = 0; r < TC_KPL; ++r) cc += (pre[r] >= cand) ? 1 : 0;
+            cc = __reduce_add_sync(kFull, cc);
+            if (cc >= k) T = cand;
         }
     }
     // compaction: keep keys whose prefix >= T (all valid keys when n <= k)
@@ -249,11 +256,10 @@ static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int 
         // degenerate score distribution (a huge tie bucket, e.g. all-equal scores): exact cut by the full sort; ties are
         // then resolved by the strict key order (lower item id wins), which the scan honours through `taukey`
         warp_sort_desc<TC_KPL>(key, lane);
-        const int nA2 = (k + 1) >> 1;
 #pragma unroll
         for (int r = 0; r < TC_KPL; ++r) {
             const int e = r * 32 + lane;
-            if (e < k) lp[e < nA2 ? e : TC_HALF_CAP + (e - nA2)] = key[r];
+            if (e < k) lp[(e % NR) * RC + e / NR] = key[r];
         }
         const uint64_t thr = warp_list_at<TC_KPL>(key, k - 1);
         *new_taukey = thr;
@@ -261,11 +267,10 @@ static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int 
         return k;
     }
     int pos = incl - mine;
-    const int nA = (total + 1) >> 1;
 #pragma unroll
     for (int r = 0; r < TC_KPL; ++r) {
         if (key[r] != 0ull && (uint32_t)(key[r] >> 48) >= T) {
-            lp[pos < nA ? pos : TC_HALF_CAP + (pos - nA)] = key[r];
+            lp[(pos % NR) * RC + pos / NR] = key[r];
             ++pos;
         }
     }
@@ -274,15 +279,15 @@ static __device__ __noinline__ int tc_cut_row(uint64_t* lp, int cA, int cB, int 
     return total;
 }
 
-// Final, exact: the (already cut and exclusion-checked) halves nA entries at lp[0..) and nB at lp[256..), nA, nB <= 128,
-// are sorted with the 256-key network and the best k written to lp[0..k) / returned in key[] (element e = r * 32 + lane).
-static __device__ __noinline__ void tc_final_sort(uint64_t* lp, int nA, int nB, int k, int lane, uint64_t (&key)[kKeysPerLane]) {
+// Final, exact: `total` <= 192 survivors dealt round-robin over the NR regions (as tc_cut_row leaves them) are sorted with
+// the 256-key network and the best k written to lp[0..k) / returned in key[] (element e = r * 32 + lane).
+template <int NR>
+static __device__ __noinline__ void tc_final_sort(uint64_t* lp, int total, int k, int lane, uint64_t (&key)[kKeysPerLane]) {
+    constexpr int RC = TC_CAP / NR;
 #pragma unroll
     for (int r = 0; r < kKeysPerLane; ++r) {
         const int e = r * 32 + lane;
-        const bool inA = e < 128;
-        const int idx = inA ? e : e - 128;
-        key[r] = (idx < (inA ? nA : nB)) ? lp[inA ? idx : TC_HALF_CAP + idx] : 0ull;
+        key[r] = (e < total) ? lp[(e % NR) * RC + e / NR] : 0ull;
     }
     warp_sort_desc<kKeysPerLane>(key, lane);
     __syncwarp();

@@ -24,9 +24,20 @@ namespace hsk {
 
 constexpr int T2_BN = 256;                   // items per tile (UMMA_N); each CTA of the pair loads TC_BN = 128 rows of it
 constexpr int T2_ACC_STAGES = 2;             // 2 x 256 fp32 columns
-constexpr int T2_HALF_COLS = T2_BN / 2;      // columns per epilogue thread and tile
-constexpr int T2_PRUNE_AT = TC_HALF_CAP - T2_HALF_COLS;   // a tile appends at most 128 keys per column half
-constexpr int T2_KEEP_MID = 2 * T2_PRUNE_AT;              // survivors of an intermediate cut: <= 128 per half
+// NCG = column groups per tile = epilogue warps / 4 (a warp reads the TMEM lane quarter warp % 4, so the warps that share a
+// lane quarter split the tile's columns): NCG = 2 -> 8 epilogue warps x 128 columns, NCG = 4 -> 16 warps x 64 columns.
+// A row's 512-entry candidate list has one region per column group; a tile appends at most COLS keys to a region, so a
+// region is cut when it holds more than RCAP - COLS, and an intermediate cut keeps <= NCG * (RCAP - COLS) = 256 entries.
+template <int NCG> struct T2Cfg {
+    static constexpr int WARPS = 4 * NCG;
+    static constexpr int THREADS = 64 + WARPS * 32;
+    static constexpr int COLS = T2_BN / NCG;
+    static constexpr int RCAP = TC_CAP / NCG;
+    static constexpr int PRUNE_AT = RCAP - COLS;
+    static constexpr int KEEP_MID = NCG * PRUNE_AT;
+    static constexpr int GROUP = NCG * 32;           // threads that share a lane quarter
+    static constexpr int ROWS_PER_WARP = 32 / NCG;   // rows a warp cuts / finalises
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -69,20 +80,21 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t adesc, uin
                      : "memory");
     }
 }
-template <bool TF32>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <bool TF32, int NCG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2Cfg<NCG>::THREADS, 1)
 eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+    using Cfg = T2Cfg<NCG>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[T2_ACC_STAGES], bar_tempty[T2_ACC_STAGES];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_tau[TC_BM];
     __shared__ uint64_t s_taukey[TC_BM];
-    __shared__ int s_cnt2[2][TC_BM];
+    __shared__ int s_cnt[NCG][TC_BM];
     __shared__ int64_t s_exlo[TC_BM], s_exhi[TC_BM];
     __shared__ float s_base[TC_BM];
     __shared__ int s_rowok[TC_BM];
-    __shared__ int s_need[4][2][2];
-    __shared__ __align__(16) float s_ib[4][2][T2_BN];   // per pair: item-bias tiles staged one tile ahead of their TMEM write
+    __shared__ int s_need[4][NCG][2];
+    __shared__ __align__(16) float s_ib[4][2][T2_BN];   // per lane quarter: item-bias tiles staged one tile ahead of their TMEM write
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -100,7 +112,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_a, 1);
-        for (int s = 0; s < T2_ACC_STAGES; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * TC_EPI_WARPS); }
+        for (int s = 0; s < T2_ACC_STAGES; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * Cfg::WARPS); }
         mbar_fence_init();
     }
     if (warp == 1) {   // TMEM of the pair: the same 512 columns in both CTAs
@@ -126,7 +138,8 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (a.Gb) base += a.Gb[0];
         s_rowok[r] = ok; s_exlo[r] = lo; s_exhi[r] = hi; s_base[r] = base;
         s_tau[r] = -INFINITY; s_taukey[r] = 0ull;
-        s_cnt2[0][r] = s_cnt2[1][r] = 0;
+#pragma unroll
+        for (int q = 0; q < NCG; ++q) s_cnt[q][r] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -183,19 +196,20 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else {
-        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 =====
         const int ew = warp - 2;
         const int quarter = warp & 3;
-        const int half = ew >> 2;
+        const int cg = ew >> 2;
         const int r = quarter * 32 + lane;
         const bool row_ok = s_rowok[r] != 0;
         uint64_t* list = a.cand + ((int64_t)split * a.Be + min(m0 + r, a.Be - 1)) * TC_CAP;
-        uint64_t* region = list + half * TC_HALF_CAP;
+        uint64_t* region = list + cg * Cfg::RCAP;
         int cnt = 0;
         const int bar_id = 1 + quarter;
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * T2_HALF_COLS);
-        float* ib_pair = &s_ib[quarter][0][0];
-        const int pt = half * 32 + lane;     // thread index within the pair (0..63)
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * Cfg::COLS);
+        float* ib_grp = &s_ib[quarter][0][0];
+        const int pt = cg * 32 + lane;       // thread index within the lane-quarter group
+        constexpr int STG = T2_BN / Cfg::GROUP;   // bias values a thread stages per tile
         ExCursor ex;
         ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
         // bias value of column `col` of tile `tt` (0 beyond the table / without item bias)
@@ -204,20 +218,20 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             return (a.Ib && tt < n_my_tiles && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
         };
 
-        // prologue: bias rows of the first two tiles into the stages (through the pair's staging tile), stages to the MMA warp
+        // prologue: bias rows of the first two tiles into the stages (through the group's staging tile), stages to the MMA warp
         for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
 #pragma unroll
-            for (int h = 0; h < 4; ++h) ib_pair[pt + 64 * h] = ib_at(ts, pt + 64 * h);
-            named_bar_sync(bar_id, 64);
-            tc_write_bias<T2_HALF_COLS / 32>(ib_pair + half * T2_HALF_COLS, tlane + (uint32_t)ts * T2_BN);
+            for (int h = 0; h < STG; ++h) ib_grp[pt + Cfg::GROUP * h] = ib_at(ts, pt + Cfg::GROUP * h);
+            named_bar_sync(bar_id, Cfg::GROUP);
+            tc_write_bias<Cfg::COLS / 32>(ib_grp + cg * Cfg::COLS, tlane + (uint32_t)ts * T2_BN);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&bar_tempty[ts]);
-            named_bar_sync(bar_id, 64);
+            named_bar_sync(bar_id, Cfg::GROUP);
         }
 #pragma unroll
-        for (int h = 0; h < 4; ++h) ib_pair[pt + 64 * h] = ib_at(T2_ACC_STAGES, pt + 64 * h);   // slot 0 <- tile 2 (consumed at t = 0)
-        named_bar_sync(bar_id, 64);
+        for (int h = 0; h < STG; ++h) ib_grp[pt + Cfg::GROUP * h] = ib_at(T2_ACC_STAGES, pt + Cfg::GROUP * h);   // slot 0 <- tile 2
+        named_bar_sync(bar_id, Cfg::GROUP);
 
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
@@ -226,20 +240,20 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
             // the bias values the NEXT iteration writes (tile t + 3): in flight during this tile
-            float ibn[4];
+            float ibn[STG];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, pt + 64 * h);
+            for (int h = 0; h < STG; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, pt + Cfg::GROUP * h);
             mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)as * T2_BN;
 #pragma unroll 1
-            for (int cp = 0; cp < 2; ++cp) {       // two 32-column chunks at a time: 64 accumulator registers live
+            for (int cp = 0; cp < Cfg::COLS / 64; ++cp) {       // two 32-column chunks at a time: 64 accumulator registers live
                 uint32_t raw0[32], raw1[32];
                 tc_ld32_issue(taddr + (uint32_t)(cp * 64), raw0);
                 tc_ld32_issue(taddr + (uint32_t)(cp * 64 + 32), raw1);
                 tc_ld_wait();
                 auto chunk = [&](const uint32_t (&raw)[32], int cc) {
-                    const int c = half * T2_HALF_COLS + cp * 64 + cc * 32;     // column of the tile
+                    const int c = cg * Cfg::COLS + cp * 64 + cc * 32;     // column of the tile
                     if (c >= ncols) return;
                     float v[32], g[8];
 #pragma unroll
@@ -249,7 +263,12 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int e = 0; e < 32; ++e) v[e] = (e < ncols - c) ? v[e] : __int_as_float(0x7fc00000);
                     }
                     const float mx = tc_chunk_max(v, g);
+#ifdef HSK_MEASURE_NOSCAN   // measurement builds only (never the shipped library): the epilogue without its candidate scan
+                           // after the first 4 tiles -> 6.39 ms = 1 517 TFLOP/s at 18 944 x 1 M x 256 (shipped: 9.95 ms)
+                    if (row_ok && mx >= tau && t < 4)
+#else
                     if (row_ok && mx >= tau)
+#endif
                         tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
                                        region, ex);
                 };
@@ -258,50 +277,57 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             // the stage has been read: write the bias row of tile t + 2 into it and hand it back to the MMA warp
             if (t + T2_ACC_STAGES < n_my_tiles) {
-                tc_write_bias<T2_HALF_COLS / 32>(ib_pair + (t & 1) * T2_BN + half * T2_HALF_COLS, taddr);
+                tc_write_bias<Cfg::COLS / 32>(ib_grp + (t & 1) * T2_BN + cg * Cfg::COLS, taddr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
             }
 #pragma unroll
-            for (int h = 0; h < 4; ++h) ib_pair[((t + 1) & 1) * T2_BN + pt + 64 * h] = ibn[h];   // staging slot of tile t + 3
+            for (int h = 0; h < STG; ++h) ib_grp[((t + 1) & 1) * T2_BN + pt + Cfg::GROUP * h] = ibn[h];   // staging slot of tile t + 3
             const bool last = (t + 1 == n_my_tiles);
-            const bool warp_need = __any_sync(kFull, row_ok && cnt > T2_PRUNE_AT) || last;
-            if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
-            named_bar_sync(bar_id, 64);
-            const bool pair_need = (s_need[quarter][0][t & 1] | s_need[quarter][1][t & 1]) != 0;
-            if (pair_need) {
-                s_cnt2[half][r] = cnt;
-                named_bar_sync(bar_id, 64);
-                int my_a = 0, my_b = 0;
+            const bool warp_need = __any_sync(kFull, row_ok && cnt > Cfg::PRUNE_AT) || last;
+            if (lane == 0) s_need[quarter][cg][t & 1] = warp_need ? 1 : 0;
+            named_bar_sync(bar_id, Cfg::GROUP);
+            int grp_need = 0;
+#pragma unroll
+            for (int q = 0; q < NCG; ++q) grp_need |= s_need[quarter][q][t & 1];
+            if (grp_need) {
+                s_cnt[cg][r] = cnt;
+                named_bar_sync(bar_id, Cfg::GROUP);
+                int my_c[NCG];
                 bool my_need = false;
-                if (lane < 16) {   // lane j looks at row j of this warp's 16 rows
-                    const int rj = quarter * 32 + half * 16 + lane;
-                    my_a = s_cnt2[0][rj];
-                    my_b = s_cnt2[1][rj];
-                    my_need = s_rowok[rj] && (my_a > T2_PRUNE_AT || my_b > T2_PRUNE_AT || last);
+#pragma unroll
+                for (int q = 0; q < NCG; ++q) my_c[q] = 0;
+                if (lane < Cfg::ROWS_PER_WARP) {   // lane j looks at row j of this warp's rows
+                    const int rj = quarter * 32 + cg * Cfg::ROWS_PER_WARP + lane;
+                    my_need = last;
+#pragma unroll
+                    for (int q = 0; q < NCG; ++q) { my_c[q] = s_cnt[q][rj]; my_need |= my_c[q] > Cfg::PRUNE_AT; }
+                    my_need = my_need && s_rowok[rj];
                 }
                 unsigned need = __ballot_sync(kFull, my_need);
                 while (need) {
                     const int j = __ffs(need) - 1;
                     need &= need - 1;
-                    const int rr = quarter * 32 + half * 16 + j;
-                    const int cA = __shfl_sync(kFull, my_a, j), cB = __shfl_sync(kFull, my_b, j);
+                    const int rr = quarter * 32 + cg * Cfg::ROWS_PER_WARP + j;
+                    int cc[NCG];
+#pragma unroll
+                    for (int q = 0; q < NCG; ++q) cc[q] = __shfl_sync(kFull, my_c[q], j);
                     uint64_t* lp = a.cand + ((int64_t)split * a.Be + (m0 + rr)) * TC_CAP;
                     float ntau;
                     uint64_t ntaukey;
-                    // intermediate cuts keep <= 128 entries per half, so that the next tile's <= 128 appends per half cannot
-                    // overflow its 256 slots; the last cut keeps <= 192 in all for the final sort
-                    const int total = tc_cut_row(lp, cA, cB, a.k, lane, last ? 192 : T2_KEEP_MID, &ntau, &ntaukey);
+                    // intermediate cuts keep <= KEEP_MID entries (<= PRUNE_AT per region, so the next tile's appends cannot
+                    // overflow a region); the last cut keeps <= 192 in all for the final sort
+                    const int total = tc_cut_row<NCG>(lp, cc, a.k, lane, last ? 192 : Cfg::KEEP_MID, &ntau, &ntaukey);
                     __syncwarp();
-                    const int nA = (total + 1) >> 1;
                     if (lane == 0) {
-                        s_cnt2[0][rr] = nA; s_cnt2[1][rr] = total - nA;
+#pragma unroll
+                        for (int q = 0; q < NCG; ++q) s_cnt[q][rr] = (total - q + NCG - 1) / NCG;
                         s_tau[rr] = ntau; s_taukey[rr] = ntaukey;
                     }
                     if (last) {
                         uint64_t keys[kKeysPerLane];
-                        tc_final_sort(lp, nA, total - nA, a.k, lane, keys);
+                        tc_final_sort<NCG>(lp, total, a.k, lane, keys);
                         if (a.n_splits == 1) {
                             const int64_t orow = (int64_t)(m0 + rr) * a.k;
                             const float base = s_base[rr];
@@ -316,13 +342,13 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         }
                     }
                 }
-                named_bar_sync(bar_id, 64);
-                cnt = s_cnt2[half][r];
+                named_bar_sync(bar_id, Cfg::GROUP);
+                cnt = s_cnt[cg][r];
             }
         }
         // rows with a bad user index: empty lists / -1 ids
-        for (int j = 0; j < 16; ++j) {
-            const int rr = quarter * 32 + half * 16 + j;
+        for (int j = 0; j < Cfg::ROWS_PER_WARP; ++j) {
+            const int rr = quarter * 32 + cg * Cfg::ROWS_PER_WARP + j;
             if (m0 + rr < a.Be && !s_rowok[rr]) {
                 if (a.n_splits == 1) {
                     for (int e = lane; e < a.k; e += 32) { a.out_scores[(int64_t)(m0 + rr) * a.k + e] = -INFINITY; a.out_ids[(int64_t)(m0 + rr) * a.k + e] = -1; }
@@ -343,20 +369,22 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-// launcher (called by hsk_eval_topk_tc in hsk_eval_tc.cu): grid.x = an even number of 128-user tiles
+template <bool TF32, int NCG>
+static int launch_tc2(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const EvalTcArgs& a) {
+    cudaError_t e = cudaFuncSetAttribute(eval_topk_tc2_kernel<TF32, NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(pair): smem attribute: %s", cudaGetErrorString(e));
+    eval_topk_tc2_kernel<TF32, NCG><<<grid, T2Cfg<NCG>::THREADS, smem, s>>>(tmA, tmB, a);
+    return check_launch("hsk_eval_topk_tc(pair)");
+}
+
+// launcher (called by hsk_eval_topk_tc_v in hsk_eval_tc.cu): grid.x = an even number of 128-user tiles.
+// NCG = 2 (8 epilogue warps x 128 columns) is the only shipped instantiation: NCG = 4 (16 warps x 64 columns, 96 registers,
+// four list regions per row) was measured at 10.69 ms against 9.96 ms for NCG = 2 (18 944 x 1 M x 256, bf16) — the
+// epilogue is not bound by a single warp's instruction latency but by the candidate scan itself (see HSK_MEASURE_NOSCAN).
 int launch_eval_tc2(bool tf32, int row_tiles, int n_splits, size_t smem, cudaStream_t s, const CUtensorMap& tmA,
                     const CUtensorMap& tmB, const EvalTcArgs& a) {
     dim3 grid((unsigned)((row_tiles + 1) / 2 * 2), (unsigned)n_splits);
-    cudaError_t e;
-    if (tf32) {
-        e = cudaFuncSetAttribute(eval_topk_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) eval_topk_tc2_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
-    } else {
-        e = cudaFuncSetAttribute(eval_topk_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) eval_topk_tc2_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
-    }
-    if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(pair): smem attribute: %s", cudaGetErrorString(e));
-    return check_launch("hsk_eval_topk_tc(pair)");
+    return tf32 ? launch_tc2<true, 2>(grid, smem, s, tmA, tmB, a) : launch_tc2<false, 2>(grid, smem, s, tmA, tmB, a);
 }
 
 }  // namespace hsk

@@ -378,3 +378,97 @@ def test_pair_kernel_matches_the_single_cta_kernel(prec, U, I, d, B, n_excl):
     assert float(same) >= 0.999, float(same)                                   # order flips only between near-equal scores
     ov = np.mean([len(np.intersect1d(a[f], b[f])) / max(int(f.sum()), 1) for a, b, f in zip(i1.numpy(), i2.numpy(), fin.numpy())])
     assert ov >= 0.9995, ov
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _Guarded:
+    """A tensor carved out of a larger allocation whose margins hold a canary pattern: what compute-sanitizer's memcheck would
+    report for WRITES (the tool is closed on this GPU pool, profiles/r02_compute_sanitizer_closed.log) is checked by hand."""
+    PAD = 4096   # bytes on each side
+
+    def __init__(self, shape, dtype, fill=None):
+        n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        n_al = (n + 255) // 256 * 256
+        self.raw = torch.full((self.PAD + n_al + self.PAD,), 0xA5, dtype=torch.uint8, device='cuda')
+        self.n = n
+        self.t = self.raw[self.PAD:self.PAD + n].view(dtype).view(shape)
+        if fill is not None:
+            self.t.fill_(fill)
+
+    def intact(self):
+        lo = self.raw[:self.PAD]
+        hi = self.raw[self.PAD + self.n:]
+        return bool((lo == 0xA5).all()) and bool((hi == 0xA5).all())
+
+
+def test_kernels_do_not_write_outside_their_buffers():
+    from scipy import sparse as sp
+    from hassaku_b200 import _C
+    from hassaku_b200.algorithms.sgd_alg import ArenaLayout
+    from hassaku_b200.eval.eval import DeviceCSR
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    guards = []
+
+    def G(shape, dtype, fill=None):
+        g = _Guarded(shape, dtype, fill)
+        guards.append(g)
+        return g.t
+
+    # ---- train step kernels (three layouts) + row-stamped AdamW ----
+    for d, variant, kind in ((402, 'ring', 0), (128, 'q', 1), (100, 'regs', 2)):
+        U, I, B, N = 901, 777, 130, 17
+        lay = ArenaLayout(U, I, d, True, True, True)
+        arena = G((lay.n_total,), torch.float32, 0.0)
+        for v_, sc_ in zip(lay.views(arena), (d ** -0.5, d ** -0.5, 0.1, 0.1, 0.1)):
+            v_.copy_(torch.randn(v_.shape, device='cuda', generator=gen) * sc_)
+        g, m, v = (G((lay.n_total,), torch.float32, 0.0) for _ in range(3))
+        u = torch.randint(0, U, (B,), device='cuda', generator=gen)
+        i = torch.randint(0, I, (B, N + 1), device='cuda', generator=gen)
+        sc, ds = G((B, N + 1), torch.float32), G((B, N + 1), torch.float32)
+        acc = G((1,), torch.float64, 0.0)
+        su, si = G((U,), torch.uint8, 0), G((I,), torch.uint8, 0)
+        _C.mf_train_fused(lay.tables(arena), lay.tables(g), u, i, kind, 0.3, acc, scores_out=sc, dscores_out=ds, variant=variant)
+        _C.mark_batch(u, i, U, I, su, si, step=1)
+        _C.adamw_dense_rows(arena, m, v, g, [(lay.off_U, U, lay.ld, su), (lay.off_V, I, lay.ld, si)], 1e-3, 0.9, 0.999, 1e-8, 1e-4, 1)
+        assert float(g.abs().max()) == 0.0
+    # ---- routing kernels ----
+    n_items, Gw, capq, ld = 5003, 3, 700, 128
+    i = torch.randint(0, n_items, (64, 21), device='cuda', generator=gen)
+    req, cnt, comp = G((Gw, capq), torch.int32), G((Gw,), torch.int32), G((64, 21), torch.int64)
+    scr = G((_C.route_scratch_bytes(n_items, Gw),), torch.uint8)
+    _C.route_items(i, n_items, Gw, capq, ld, req, cnt, comp, scr)
+    br = _C.shard_block_rows(capq, ld)
+    V, Ib = torch.randn((1700, ld), device='cuda', generator=gen), torch.randn(1700, device='cuda', generator=gen)
+    rows = torch.where(req >= 0, req % 1700, req)
+    out = G((Gw, br, ld), torch.float32, 0.0)
+    _C.shard_pack(V, Ib, rows, Gw, capq, out)
+    gV, gIb, st = G((1700, ld), torch.float32, 0.0), G((1700,), torch.float32, 0.0), G((1700,), torch.uint8, 0)
+    _C.shard_unpack_add(out, rows, Gw, capq, gV, gIb, st, step=3)
+    # ---- evaluator: both tensor-core kernels, several splits and a ragged last tile, then re-scoring ----
+    U, I, d, B, k = 300, 40_011, 96, 257, 128
+    Uw = torch.randn((U, d), device='cuda', generator=gen) / d ** 0.5
+    Vw = torch.randn((I, d), device='cuda', generator=gen) / d ** 0.5
+    Ibv = torch.randn((I, 1), device='cuda', generator=gen) * 0.1
+    rng = np.random.RandomState(0)
+    rws = np.repeat(np.arange(U), 25)
+    ex = sp.csr_matrix((np.ones(len(rws), dtype=bool), (rws, rng.randint(0, I, len(rws)))), shape=(U, I))
+    ex.sum_duplicates(); ex.sort_indices()
+    exd = DeviceCSR(ex, 'cuda')
+    users = torch.arange(B, device='cuda')
+    for prec in ('bf16', 'tf32'):
+        P = _C.PRECISIONS[prec]
+        Uq, Vq = _C.pack_rows(Uw, d, P, row_idx=users), _C.pack_rows(Vw, d, P)
+        for variant in ('pair', 'single'):
+            s, ids = G((B, k), torch.float32), G((B, k), torch.int32)
+            scr = G((_C.eval_topk_tc_scratch_bytes(B, I, k),), torch.uint8)
+            _C.eval_topk_tc(Uq, Vq, P, users, U, k, s, ids, scr, Ib=Ibv, excl_indptr=exd.indptr, excl_indices=exd.indices,
+                            variant=variant)
+            t = _C.make_tables(Uw, Vw, None, Ibv, None, d)
+            s2, i2 = G((B, 100), torch.float32), G((B, 100), torch.int32)
+            _C.rescore_topk(t, users, ids, 100, s2, i2, cand_scores=s)
+    s, ids = G((B, 100), torch.float32), G((B, 100), torch.int32)
+    scr = G((_C.eval_topk_scratch_bytes(B, I, 100),), torch.uint8)
+    _C.eval_topk(_C.make_tables(Uw, Vw, None, Ibv, None, d), users, 100, s, ids, scr, exd.indptr, exd.indices)
+    torch.cuda.synchronize()
+    bad = [j for j, g_ in enumerate(guards) if not g_.intact()]
+    assert not bad, f'canaries overwritten around buffers {bad}'
