@@ -224,7 +224,7 @@ def workload_config(wname, wl, U, I, world=1):
            'embedding_dim': d, 'train_batch_size': B, 'train_batch_is': 'per GPU (weak scaling)', 'global_batch': B * world,
            'neg_train': N, 'rec_loss': loss, 'optimizer': 'adamw (dense, torch-faithful)', 'lr': lr, 'wd': wd,
            'item_bias': True, 'precision': 'fp32 exact (train); bf16 tcgen05 + fp32 re-scoring (eval)',
-           'parallelism': 'single GPU' if world == 1 else f'item+user row-sharded x{world}, NCCL all-to-all (sparse exchange, CUDA graph)'}
+           'parallelism': 'single GPU' if world == 1 else f'item+user row-sharded x{world}, one process per GPU (item-row exchange: see the line\'s `exchange` block)'}
     cfg['l2'] = ('inputs larger than L2: 6.2 GB of parameters + optimizer state per step, no flush' if big else
                  'flushed between timed steps (tables + optimizer state fit L2); value_l2_warm = back to back')
     return cfg
@@ -910,8 +910,8 @@ def run_ours_sharded(args, wl):
             dist.destroy_process_group()
 
 
-def parity_check_train(smf, full_sd, u_loc, i_loc, B, N, loss, shift, lr, wd, dev, rank, world, d):
-    """One sharded step (eager sparse exchange) against the single-GPU step on the union batch, on rank 0."""
+def parity_check_train(smf, full_sd, u_loc, i_loc, B, N, loss, shift, lr, wd, dev, rank, world, d, exchange='sparse'):
+    """One sharded step (eager, the exchange that is timed) against the single-GPU step on the union batch, on rank 0."""
     import torch
     import torch.distributed as dist
     from hassaku_b200 import _C
@@ -922,7 +922,7 @@ def parity_check_train(smf, full_sd, u_loc, i_loc, B, N, loss, shift, lr, wd, de
     dist.all_gather_into_tensor(u_all, u_loc)
     dist.all_gather_into_tensor(i_all, i_loc)
     smf.loss_accum.zero_()
-    smf.step(u_loc, i_loc, B * world, loss, shift, lr, wd, exchange='sparse')
+    smf.step(u_loc, i_loc, B * world, loss, shift, lr, wd, exchange=exchange)
     l_sh = smf.pop_loss()
     got = smf.full_state_dict(to_cpu=False)
     smf.check_status()
@@ -964,6 +964,7 @@ def _run_ours_sharded(args, wl, holder):
     (weak scaling: global batch = N x 8192), device routing + NCCL all-to-all, captured as one CUDA graph."""
     import torch
     import torch.distributed as dist
+    from hassaku_b200 import _C
     from hassaku_b200.algorithms.sgd_alg import ArenaLayout
     from hassaku_b200.data.synthetic import make_device_interactions
     from hassaku_b200.sharded import ShardedMF, exchange_capacity
@@ -1025,9 +1026,11 @@ def _run_ours_sharded(args, wl, holder):
     # ---- parity self-check (outside every timed region) ----
     parity = {'train': None, 'eval': None}
     try:
-        ok, worst = parity_check_train(smf, full_sd, u_dev[0], i_dev[0], B, N, loss, shift, lr, wd, dev, rank, world, d)
+        ok, worst = parity_check_train(smf, full_sd, u_dev[0], i_dev[0], B, N, loss, shift, lr, wd, dev, rank, world, d,
+                                       exchange=exchange.replace('_graph', ''))
         parity['train'] = {'ok': bool(ok), 'max_rel_err': worst,
-                           'what': 'one sharded step (sparse exchange) vs the single-GPU step on the union batch, from the same state'}
+                           'what': f'one sharded step ({exchange.replace("_graph", "")} exchange) vs the single-GPU step on the union '
+                                   f'batch, from the same state'}
     except Exception as ex:
         parity['train'] = {'ok': False, 'error': repr(ex)}
     # fresh state for the measurement
@@ -1095,7 +1098,7 @@ def _run_ours_sharded(args, wl, holder):
     ms_e2e = D.max(a2.elapsed_time(b2))
     assert math.isfinite(loss_host), 'training diverged'
     # per-kernel view of one EAGER step on rank 0's stream (collectives included): which part limits the step
-    eager = 'sparse' if exchange.startswith('sparse') else 'dense'
+    eager = exchange.replace('_graph', '')
     e0, e1 = _events(2)
     D.barrier()
     e0.record()
@@ -1105,6 +1108,35 @@ def _run_ours_sharded(args, wl, holder):
     D.barrier()
     ms_eager = D.max(e0.elapsed_time(e1)) / 10
     capq = exchange_capacity(B * (N + 1), I, world)
+    phases = None
+    if exchange.startswith('peer'):
+        # the peer step's parts, every rank at once (so the NVLink load is the step's): barrier, step kernel, AdamW
+        P_, lay_ = smf._peer_setup(), smf.layout
+        u_loc_ = smf.ops.local_index(u_dev[0], world, 0)
+        q0, q1, q2, q3, q4, q5 = _events(6)
+        D.barrier()
+        q0.record()
+        for _ in range(20):
+            smf._barrier()
+        q1.record()
+        smf._barrier()
+        q2.record()
+        for _ in range(5):
+            smf.ops.train_fused_peer(lay_, smf.arena, smf.g, P_['items'], I, u_loc_, i_dev[0], Bg, _C.LOSS_KINDS[loss], shift,
+                                     smf.loss_accum, smf.t + 1, None)
+        q3.record()
+        smf._barrier()
+        smf.g.zero_()
+        smf._barrier()
+        q4.record()
+        for _ in range(5):
+            smf.ops.adamw(smf.arena, smf.m, smf.v, smf.g, smf._segments(True, True), 0.0, 0.0, smf.t + 1, True)
+        q5.record()
+        D.barrier()
+        phases = {'barrier_ms': D.max(q0.elapsed_time(q1)) / 20, 'fused_peer_ms': D.max(q2.elapsed_time(q3)) / 5,
+                  'adamw_rows_ms': D.max(q4.elapsed_time(q5)) / 5,
+                  'nvlink_gbs_per_direction_in_kernel': 2 * B * (N + 2) * (d + 1) * 4 * (world - 1) / world / (D.max(q2.elapsed_time(q3)) / 5 * 1e-3) / 1e9,
+                  'what': 'max over ranks, all ranks running the same part at once; AdamW with lr = 0 (same traffic, state untouched)'}
     smf.close()
     holder.remove(smf)
     del smf
@@ -1135,12 +1167,19 @@ def _run_ours_sharded(args, wl, holder):
                 'e2e': {'value': triples * K / (ms_e2e * 1e-3), 'unit': 'triples/s',
                         'h2d_bytes_per_step': int(u_pin[0].numel() * 8 + i_pin[0].numel() * 8) * world, 'd2h_bytes_per_step': 8,
                         'ms_per_step': ms_e2e / K},
-                'gpu_launches': 14 * K * world,
-                'gpu_launches_note': 'per rank and step, own kernels inside the graph: route (5) + pack + local_index + mark_rows + fused + '
-                                     'unpack_add + adamw_rows = 11, + 3 NCCL all-to-all kernels',
-                'exchange': {'kind': exchange, 'capq_rows_per_owner': capq,
-                             'bytes_per_gpu_per_direction': int(2 * world * (capq + math.ceil(capq / 128)) * 128 * 4) if exchange.startswith('sparse') else None,
-                             'eager_ms_per_step': ms_eager, 'graph_ms_per_step': ms_step},
+                'gpu_launches': (4 if exchange.startswith('peer') else 11) * K * world,
+                'gpu_launches_note': ('per rank and step, own kernels inside the graph: local_index + mark_rows + fused_peer (item rows '
+                                      'read from / gradients reduced into the owners over NVLink) + adamw_rows = 4, + 2 NCCL barriers'
+                                      if exchange.startswith('peer') else
+                                      'per rank and step, own kernels inside the graph: route (5) + pack + local_index + mark_rows + fused + '
+                                      'unpack_add + adamw_rows = 11, + 3 NCCL all-to-all kernels'),
+                'exchange': {'kind': exchange, 'capq_rows_per_owner': capq if exchange.startswith('sparse') else None,
+                             'bytes_per_gpu_per_direction': (int(2 * world * (capq + math.ceil(capq / 128)) * 128 * 4) if exchange.startswith('sparse')
+                                                             else int(2 * B * (N + 2) * (d + 1) * 4 * (world - 1) / world) if exchange.startswith('peer')
+                                                             else None),
+                             'bytes_note': 'NVLink bytes per GPU and direction and step: rows served + gradients sent (= rows fetched + '
+                                           'gradients received)',
+                             'eager_ms_per_step': ms_eager, 'graph_ms_per_step': ms_step, 'phases': phases},
                 'roofline': {'kernel': 'whole step (per GPU)', 'bound': 'hbm', 'unit': 'GB/s',
                              'achieved': per_gpu_bytes / (ms_step * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
                              'frac': per_gpu_bytes / (ms_step * 1e-3) / 1e9 / peaks['hbm_gbs'], 'traffic': None,
@@ -1204,7 +1243,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU legs (profiling runs)')
-    ap.add_argument('--exchange', default='sparse_graph', choices=['sparse', 'sparse_graph', 'dense', 'dense_graph'],
+    ap.add_argument('--exchange', default='sparse_graph', choices=['sparse', 'sparse_graph', 'dense', 'dense_graph', 'peer', 'peer_graph'],
                     help='N > 1: item-row exchange of the sharded step')
     ap.add_argument('--no-eval', action='store_true', help='skip the cfg5 full-rank evaluation sweep')
     ap.add_argument('--no-also', action='store_true', help='N = 1: skip the cfg2 / cfg3 / loader side lines')

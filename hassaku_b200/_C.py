@@ -43,6 +43,16 @@ class RowSegment(C.Structure):
     _fields_ = [('offset', C.c_int64), ('n_rows', C.c_int64), ('ld', C.c_int32), ('stamps', C.c_void_p)]
 
 
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
+
+
+class PeerItems(C.Structure):
+    """struct hsk_peer_items (include/hassaku_b200.h): the item side of every rank's tables, mapped into this process."""
+    _fields_ = [('world', C.c_int32), ('V', C.c_void_p * MAX_PEERS), ('gV', C.c_void_p * MAX_PEERS),
+                ('Ib', C.c_void_p * MAX_PEERS), ('gIb', C.c_void_p * MAX_PEERS), ('stamps', C.c_void_p * MAX_PEERS)]
+
+
 _lib = None
 
 
@@ -59,6 +69,10 @@ def _declare(lib):
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_n': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_v': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, i32, vp]),
+        'hsk_peer_export': (i32, [vp, vp, C.POINTER(C.c_int64)]),
+        'hsk_peer_open': (i32, [vp, C.POINTER(C.c_void_p)]),
+        'hsk_peer_close': (i32, [vp]),
+        'hsk_mf_train_fused_peer': (i32, [T, T, C.POINTER(PeerItems), vp, vp, i32, i32, i64, i32, f32, vp, i64, vp, vp, vp]),
         'hsk_gather_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_shard_local_index': (i32, [vp, i64, i32, i64, vp, vp]),
         'hsk_scatter_add_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
@@ -230,6 +244,55 @@ def mf_train_fused(tables: MfTables, grads: MfTables, u_idx, i_idx, loss_kind: i
 def mf_train_fused_n(tables: MfTables, grads: MfTables, u_idx, i_idx, B_global: int, loss_kind: int, neg_shift: float,
                      loss_accum, status=None):
     mf_train_fused(tables, grads, u_idx, i_idx, loss_kind, neg_shift, loss_accum, status=status, B_global=B_global)
+
+
+def peer_export(t: torch.Tensor):
+    """(handle bytes, offset) of the device allocation behind `t` for the peers of this node (hsk_peer_export)."""
+    h = C.create_string_buffer(PEER_HANDLE_BYTES)
+    off = C.c_int64(0)
+    with _on_device_of(t):
+        _check(lib().hsk_peer_export(t.data_ptr(), h, C.byref(off)), 'hsk_peer_export')
+    return bytes(h.raw), int(off.value)
+
+
+def peer_open(handle: bytes, device) -> int:
+    """Map a peer's allocation into this process; returns its base address here (hsk_peer_open)."""
+    base = C.c_void_p(0)
+    with torch.cuda.device(device):
+        _check(lib().hsk_peer_open(C.create_string_buffer(handle, PEER_HANDLE_BYTES), C.byref(base)), 'hsk_peer_open')
+    return int(base.value)
+
+
+def peer_close(base: int):
+    _check(lib().hsk_peer_close(C.c_void_p(base)), 'hsk_peer_close')
+
+
+def make_peer_items(V_ptrs, gV_ptrs, Ib_ptrs=None, gIb_ptrs=None, stamp_ptrs=None) -> PeerItems:
+    """Device addresses (ints, valid in THIS process) of every rank's local item tables, rank order."""
+    G = len(V_ptrs)
+    if not 1 <= G <= MAX_PEERS:
+        raise ValueError(f'peer exchange supports 1..{MAX_PEERS} ranks, got {G}')
+    p = PeerItems()
+    p.world = G
+    for q in range(G):
+        p.V[q], p.gV[q] = V_ptrs[q], gV_ptrs[q]
+        p.Ib[q] = Ib_ptrs[q] if Ib_ptrs else None
+        p.gIb[q] = gIb_ptrs[q] if gIb_ptrs else None
+        p.stamps[q] = stamp_ptrs[q] if stamp_ptrs else None
+    return p
+
+
+def mf_train_fused_peer(tables: MfTables, grads: MfTables, peers: PeerItems, u_idx, i_idx, B_global: int, loss_kind: int,
+                        neg_shift: float, loss_accum, step: int = 0, step_dev=None, status=None):
+    """hsk_mf_train_fused_peer: the step kernel over peer-mapped item shards (rows <= 128 floats)."""
+    _req(u_idx, torch.int64, 'u_idx'); _req(i_idx, torch.int64, 'i_idx'); _req(loss_accum, torch.float64, 'loss_accum')
+    if step_dev is not None:
+        _req(step_dev, torch.int64, 'step_dev')
+    B, N1 = i_idx.shape
+    with _on_device_of(u_idx, i_idx, loss_accum, step_dev, status) as st:
+        _check(lib().hsk_mf_train_fused_peer(C.byref(tables), C.byref(grads), C.byref(peers), u_idx.data_ptr(), i_idx.data_ptr(),
+                                             B, N1, B_global, loss_kind, neg_shift, loss_accum.data_ptr(), step, _ptr(step_dev),
+                                             _ptr(status), st), 'hsk_mf_train_fused_peer')
 
 
 def gather_rows(src, idx, dst, status=None):

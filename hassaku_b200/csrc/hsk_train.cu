@@ -479,6 +479,41 @@ extern "C" int hsk_mf_train_fused_n(const hsk_mf_tables* t, const hsk_mf_tables*
                                 dscores_out, status, HSK_TRAIN_AUTO, stream);
 }
 
+extern "C" int hsk_mf_train_fused_peer(const hsk_mf_tables* t, const hsk_mf_tables* g, const hsk_peer_items* peers,
+                                       const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t B_global,
+                                       int loss_kind, float neg_shift, double* loss_accum, int64_t step,
+                                       const int64_t* step_dev, int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(t && g && peers && t->Uw && g->Uw && u_idx && i_idx, "hsk_mf_train_fused_peer: null pointer");
+    HSK_REQUIRE(peers->world >= 1 && peers->world <= HSK_MAX_PEERS, "hsk_mf_train_fused_peer: world must be 1..%d", HSK_MAX_PEERS);
+    HSK_REQUIRE(B >= 0 && N1 >= 1 && B_global >= B, "hsk_mf_train_fused_peer: bad batch sizes (B=%d N1=%d)", B, N1);
+    HSK_REQUIRE(t->d >= 1 && t->ld >= t->d && (t->ld % 4) == 0 && g->ld == t->ld, "hsk_mf_train_fused_peer: bad row layout");
+    HSK_REQUIRE(t->n_items >= 1 && t->n_items < 0x7FFFFFFFll, "hsk_mf_train_fused_peer: the global item count must fit 31 bits");
+    HSK_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "hsk_mf_train_fused_peer: unknown loss kind %d", loss_kind);
+    HSK_REQUIRE(loss_kind != HSK_LOSS_BPR || N1 >= 2, "hsk_mf_train_fused_peer: bpr needs at least one negative");
+    HSK_REQUIRE(aligned16(t->Uw) && aligned16(g->Uw), "hsk_mf_train_fused_peer: tables must be 16-byte aligned");
+    HSK_REQUIRE((!t->Ub || g->Ub) && (!t->Gb || g->Gb), "hsk_mf_train_fused_peer: missing bias gradient buffer");
+    for (int q = 0; q < peers->world; ++q) {
+        HSK_REQUIRE(peers->V[q] && peers->gV[q] && aligned16(peers->V[q]) && aligned16(peers->gV[q]),
+                    "hsk_mf_train_fused_peer: item tables of rank %d missing or misaligned", q);
+        HSK_REQUIRE((peers->Ib[q] != nullptr) == (peers->Ib[0] != nullptr) && (peers->gIb[q] != nullptr) == (peers->Ib[0] != nullptr) &&
+                        (peers->stamps[q] != nullptr) == (peers->stamps[0] != nullptr),
+                    "hsk_mf_train_fused_peer: item bias / stamps must be set on every rank or on none");
+    }
+    if (B == 0) return HSK_OK;
+    TrainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Uw = t->Uw; a.Ub = t->Ub; a.Gb = t->Gb;
+    a.gU = g->Uw; a.gUb = t->Ub ? g->Ub : nullptr; a.gGb = t->Gb ? g->Gb : nullptr;
+    a.n_users = t->n_users; a.n_items = t->n_items;
+    a.B = B; a.N1 = N1; a.ld = t->ld; a.nvec = t->ld / 4;
+    a.u_idx = u_idx; a.i_idx = i_idx;
+    a.status = status; a.loss_kind = loss_kind; a.neg_shift = neg_shift; a.loss_accum = loss_accum;
+    a.inv_count = loss_kind == HSK_LOSS_BPR ? 1.0 / ((double)B_global * (double)(N1 - 1))
+                : loss_kind == HSK_LOSS_BCE ? 1.0 / ((double)B_global * (double)N1) : 1.0 / (double)B_global;
+    a.j_per_cta = N1;
+    return launch_train_fused_peer(a, *peers, hsk_row_stamp(step), step_dev, loss_kind, as_stream(stream));
+}
+
 extern "C" int hsk_mf_train_fused_v(const hsk_mf_tables* t, const hsk_mf_tables* g, const int64_t* u_idx,
                                     const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind, float neg_shift,
                                     double* loss_accum, float* scores_out, float* dscores_out, int32_t* status,

@@ -40,4 +40,9 @@ int launch_train_fused_tma(const TrainArgs& a, int loss_kind, cudaStream_t s);
 // shape is outside its range and the caller should use the warp-per-row kernels
 int launch_train_fused_q(const TrainArgs& a, int loss_kind, cudaStream_t s);
 
+// hsk_train_q.cu: the same kernel with the item tables sharded over the ranks of a node and mapped into this address
+// space (hsk_mf_train_fused_peer): rows gathered from / gradients reduced into the owners' memory over NVLink
+int launch_train_fused_peer(const TrainArgs& a, const hsk_peer_items& peers, int stamp_host, const int64_t* step_dev, int loss_kind,
+                            cudaStream_t s);
+
 }  // namespace hsk

@@ -30,6 +30,19 @@ struct QRow {
 #pragma unroll
         for (int k = 0; k < K4; ++k) v[k] = (k < K4 - 1 || last_ok) ? __ldg(p + 8 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // a row that may live in a PEER's memory (NVLink): ordinary coherent loads, not the read-only path
+    __device__ __forceinline__ void load_peer(const float* row, int l, bool last_ok) {
+        const float4* p = reinterpret_cast<const float4*>(row) + l;
+#pragma unroll
+        for (int k = 0; k < K4; ++k) {
+            if (k < K4 - 1 || last_ok) {
+                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                             : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "l"(p + 8 * k) : "memory");
+            } else {
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
     __device__ __forceinline__ float dot(const QRow& o) const {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -57,6 +70,17 @@ struct QRow {
         for (int k = 0; k < K4; ++k)
             if (k < K4 - 1 || last_ok) atomicAdd(p + 8 * k, make_float4(a * v[k].x, a * v[k].y, a * v[k].z, a * v[k].w));
     }
+    // the same into a peer's gradient table: system scope — the addition is performed in the OWNER's L2, atomically with the
+    // other ranks' and the owner's own contributions
+    __device__ __forceinline__ void red_peer(float* dst, float a, int l, bool last_ok) const {
+        float4* p = reinterpret_cast<float4*>(dst) + l;
+#pragma unroll
+        for (int k = 0; k < K4; ++k)
+            if (k < K4 - 1 || last_ok)
+                asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p + 8 * k), "f"(a * v[k].x),
+                             "f"(a * v[k].y), "f"(a * v[k].z), "f"(a * v[k].w)
+                             : "memory");
+    }
 };
 
 __device__ __forceinline__ float group_sum(float v) {   // over the 8 lanes of a quarter-warp; every lane gets the sum
@@ -72,8 +96,54 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-template <int K4, int LOSS>
-__global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArgs a) {
+// PEER mode (hsk_mf_train_fused_peer): the item tables are sharded over the ranks of a node, item i = row i / world of rank
+// i % world, every rank's shard mapped into this address space
+struct PeerArgs {
+    hsk_peer_items p;
+    int lg;                 // log2(world) when world is a power of two, else -1
+    int stamp_host;
+    const int64_t* step_dev;
+};
+struct ItemAt {             // where one item's row / bias / gradients / stamp live
+    const float* v;
+    float* g;
+    const float* ib;
+    float* gib;
+    uint8_t* st;
+};
+template <bool PEER>
+__device__ __forceinline__ ItemAt item_at(const TrainArgs& a, const PeerArgs& pv, int64_t it, int ld) {
+    ItemAt x;
+    if (!PEER) {
+        x.v = a.Vw + it * ld; x.g = a.gV + it * ld; x.ib = a.Ib ? a.Ib + it : nullptr; x.gib = a.gIb ? a.gIb + it : nullptr;
+        x.st = nullptr;
+        return x;
+    }
+    const uint32_t i = (uint32_t)it;            // global item ids < 2^31 (checked at launch)
+    uint32_t own, row;
+    if (pv.lg >= 0) { own = i & ((1u << pv.lg) - 1u); row = i >> pv.lg; }
+    else { row = i / (uint32_t)pv.p.world; own = i - row * (uint32_t)pv.p.world; }
+    const int64_t off = (int64_t)row * ld;
+    x.v = pv.p.V[own] + off; x.g = pv.p.gV[own] + off;
+    x.ib = pv.p.Ib[own] ? pv.p.Ib[own] + row : nullptr;
+    x.gib = pv.p.gIb[own] ? pv.p.gIb[own] + row : nullptr;
+    x.st = pv.p.stamps[own] ? pv.p.stamps[own] + row : nullptr;
+    return x;
+}
+template <bool PEER, int K4>
+__device__ __forceinline__ void load_item(QRow<K4>& r, const float* row, int l, bool last_ok) {
+    if (PEER) r.load_peer(row, l, last_ok); else r.load(row, l, last_ok);
+}
+template <bool PEER>
+__device__ __forceinline__ float load_bias(const float* p) {
+    if (!PEER) return __ldg(p);
+    float x;
+    asm volatile("ld.global.f32 %0, [%1];\n" : "=f"(x) : "l"(p) : "memory");
+    return x;
+}
+
+template <int K4, int LOSS, bool PEER>
+__device__ __forceinline__ void mf_train_fused_q_body(const TrainArgs& a, const PeerArgs& pv) {
     extern __shared__ float sm_scores_all[];   // sampled softmax: [groups per CTA][N1]
     const int lane = threadIdx.x & 31, l = lane & 7;
     const int gid = threadIdx.x >> 3;                                   // group within the CTA
@@ -93,14 +163,10 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
     }
     const int64_t rowoff = (int64_t)(live ? b : 0) * N1;
     const int64_t* __restrict__ irow = a.i_idx + rowoff;
-    const float* __restrict__ Vw = a.Vw;
-    const float* __restrict__ Ibp = a.Ib;
-    float* __restrict__ gV = a.gV;
-    float* __restrict__ gIb = a.gIb;
-    const bool has_ub = a.Ub != nullptr, has_ib = a.Ib != nullptr, has_gb = a.Gb != nullptr;
+    const bool has_ub = a.Ub != nullptr, has_ib = PEER ? pv.p.Ib[0] != nullptr : a.Ib != nullptr, has_gb = a.Gb != nullptr;
+    const uint8_t stamp = PEER ? (uint8_t)(pv.step_dev ? 1 + (int)(*pv.step_dev % 255) : pv.stamp_host) : (uint8_t)0;
     const float ubv = (has_ub && live) ? a.Ub[u] : 0.f, gbv = has_gb ? a.Gb[0] : 0.f;
     const float invf = (float)a.inv_count;
-    constexpr bool do_red = true;
 
     QRow<K4> ur, gu;
     gu.zero();
@@ -116,10 +182,11 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
             if (!pos_ok && l == 0 && a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
         }
         QRow<K4> v0;
-        if (pos_ok) v0.load(Vw + i0 * ld, l, last_ok); else v0.zero();
+        const ItemAt x0 = item_at<PEER>(a, pv, pos_ok ? i0 : 0, ld);
+        if (pos_ok) load_item<PEER>(v0, x0.v, l, last_ok); else v0.zero();
         s0 = group_sum(ur.dot(v0));
         if (has_ub) s0 += ubv;
-        if (has_ib && pos_ok) s0 += __ldg(Ibp + i0);
+        if (has_ib && pos_ok) s0 += load_bias<PEER>(x0.ib);
         if (has_gb) s0 += gbv;
         live = live && pos_ok;     // a sample whose positive is invalid contributes nothing (as the warp-per-row kernels)
     }
@@ -140,13 +207,15 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
                 it[q] = ok[q] ? irow[j + q] : 0;
                 if (ok[q] && bad_index(it[q], a.n_items)) {
                     ok[q] = false;
+                    it[q] = 0;
                     if (l == 0 && a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
                 }
             }
 #pragma unroll
             for (int q = 0; q < kQUnroll; ++q) {
-                if (ok[q]) r[q].load(Vw + it[q] * ld, l, last_ok); else r[q].zero();
-                ib[q] = (ok[q] && has_ib) ? __ldg(Ibp + it[q]) : 0.f;
+                const ItemAt x = item_at<PEER>(a, pv, it[q], ld);
+                if (ok[q]) load_item<PEER>(r[q], x.v, l, last_ok); else r[q].zero();
+                ib[q] = (ok[q] && has_ib) ? load_bias<PEER>(x.ib) : 0.f;
             }
 #pragma unroll
             for (int q = 0; q < kQUnroll; ++q) {
@@ -177,19 +246,22 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
         int64_t it[kQUnroll];
         bool ok[kQUnroll];
         float ib[kQUnroll];
+        ItemAt at[kQUnroll];
 #pragma unroll
         for (int q = 0; q < kQUnroll; ++q) {
             ok[q] = live && (j + q < N1);
             it[q] = ok[q] ? irow[j + q] : 0;
             if (ok[q] && bad_index(it[q], a.n_items)) {
                 ok[q] = false;
+                it[q] = 0;
                 if (LOSS != HSK_LOSS_SAMPLED_SOFTMAX && l == 0 && a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
             }
         }
 #pragma unroll
         for (int q = 0; q < kQUnroll; ++q) {
-            if (ok[q]) r[q].load(Vw + it[q] * ld, l, last_ok); else r[q].zero();
-            ib[q] = (LOSS != HSK_LOSS_SAMPLED_SOFTMAX && ok[q] && has_ib) ? __ldg(Ibp + it[q]) : 0.f;
+            at[q] = item_at<PEER>(a, pv, it[q], ld);
+            if (ok[q]) load_item<PEER>(r[q], at[q].v, l, last_ok); else r[q].zero();
+            ib[q] = (LOSS != HSK_LOSS_SAMPLED_SOFTMAX && ok[q] && has_ib) ? load_bias<PEER>(at[q].ib) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < kQUnroll; ++q) {
@@ -222,9 +294,10 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
             dsum += dsj;
             gu.axpy(dsj, r[q]);
             if (ok[q]) {
-                if (do_red) ur.red(gV + it[q] * ld, dsj, l, last_ok);
+                if (PEER) ur.red_peer(at[q].g, dsj, l, last_ok); else ur.red(at[q].g, dsj, l, last_ok);
                 if (l == 0) {
-                    if (gIb) atomicAdd(gIb + it[q], dsj);
+                    if (at[q].gib) { if (PEER) atomicAdd_system(at[q].gib, dsj); else atomicAdd(at[q].gib, dsj); }
+                    if (PEER && at[q].st) *at[q].st = stamp;
                     if (LOSS != HSK_LOSS_SAMPLED_SOFTMAX && a.scores_out) a.scores_out[rowoff + j + q] = sj;
                     if (a.dscores_out) a.dscores_out[rowoff + j + q] = dsj;
                 }
@@ -236,12 +309,14 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
     if (live) {
         if (LOSS == HSK_LOSS_BPR) {
             QRow<K4> v0;
-            v0.load(Vw + i0 * ld, l, last_ok);
+            const ItemAt x0 = item_at<PEER>(a, pv, i0, ld);
+            load_item<PEER>(v0, x0.v, l, last_ok);
             gu.axpy(ds0, v0);
-            if (do_red) ur.red(gV + i0 * ld, ds0, l, last_ok);
+            if (PEER) ur.red_peer(x0.g, ds0, l, last_ok); else ur.red(x0.g, ds0, l, last_ok);
             dsum += ds0;
             if (l == 0) {
-                if (gIb) atomicAdd(gIb + i0, ds0);
+                if (x0.gib) { if (PEER) atomicAdd_system(x0.gib, ds0); else atomicAdd(x0.gib, ds0); }
+                if (PEER && x0.st) *x0.st = stamp;
                 if (a.scores_out) a.scores_out[rowoff] = s0;
                 if (a.dscores_out) a.dscores_out[rowoff] = ds0;
             }
@@ -256,6 +331,48 @@ __global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArg
     double lw = (l == 0) ? (double)loss_local : 0.0;
     lw = warp_sum(lw);
     if (lane == 0 && a.loss_accum && lw != 0.0) atomicAdd(a.loss_accum, lw);
+}
+
+template <int K4, int LOSS>
+__global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_q_kernel(TrainArgs a) {
+    PeerArgs none;     // never read: every use is behind `if (PEER)`
+    mf_train_fused_q_body<K4, LOSS, false>(a, none);
+}
+template <int K4, int LOSS>
+__global__ void __launch_bounds__(kQWarps * 32) mf_train_fused_peer_kernel(TrainArgs a, PeerArgs pv) {
+    mf_train_fused_q_body<K4, LOSS, true>(a, pv);
+}
+
+template <int LOSS>
+static int launch_q_peer(const TrainArgs& a, const PeerArgs& pv, cudaStream_t s) {
+    const int k4 = (a.nvec + 7) / 8;
+    const int spc = kQWarps * 4;
+    const dim3 grid((a.B + spc - 1) / spc);
+    const size_t smem = (LOSS == HSK_LOSS_SAMPLED_SOFTMAX) ? sizeof(float) * (size_t)spc * a.N1 : 0;
+    switch (k4) {
+        case 1: mf_train_fused_peer_kernel<1, LOSS><<<grid, kQWarps * 32, smem, s>>>(a, pv); break;
+        case 2: mf_train_fused_peer_kernel<2, LOSS><<<grid, kQWarps * 32, smem, s>>>(a, pv); break;
+        case 3: mf_train_fused_peer_kernel<3, LOSS><<<grid, kQWarps * 32, smem, s>>>(a, pv); break;
+        default: mf_train_fused_peer_kernel<4, LOSS><<<grid, kQWarps * 32, smem, s>>>(a, pv); break;
+    }
+    return check_launch("hsk_mf_train_fused_peer");
+}
+
+int launch_train_fused_peer(const TrainArgs& a, const hsk_peer_items& peers, int stamp_host, const int64_t* step_dev, int loss_kind,
+                            cudaStream_t s) {
+    if (a.nvec > 32) return set_err(HSK_ERR_UNSUPPORTED, "hsk_mf_train_fused_peer: rows of at most 128 floats (ld=%d)", a.ld);
+    if (loss_kind == HSK_LOSS_SAMPLED_SOFTMAX && (size_t)a.N1 * kQWarps * 4 * sizeof(float) > 40 * 1024)
+        return set_err(HSK_ERR_UNSUPPORTED, "hsk_mf_train_fused_peer: sampled softmax supports at most %d slots per sample",
+                       (int)(40 * 1024 / (kQWarps * 4 * sizeof(float))));
+    PeerArgs pv;
+    pv.p = peers;
+    pv.lg = -1;
+    for (int b = 0; b < 4; ++b) if ((1 << b) == peers.world) pv.lg = b;
+    pv.stamp_host = stamp_host;
+    pv.step_dev = step_dev;
+    if (loss_kind == HSK_LOSS_BPR) return launch_q_peer<HSK_LOSS_BPR>(a, pv, s);
+    if (loss_kind == HSK_LOSS_BCE) return launch_q_peer<HSK_LOSS_BCE>(a, pv, s);
+    return launch_q_peer<HSK_LOSS_SAMPLED_SOFTMAX>(a, pv, s);
 }
 
 template <int LOSS>

@@ -88,6 +88,12 @@ class CudaOps:
         g = _C.make_tables(gU, gVc[:, :lay.d], gUb, gIbc, gGb, lay.d)
         _C.mf_train_fused_n(t, g, u_local, compact_idx, B_global, kind, shift, loss_accum, self.status)
 
+    def train_fused_peer(self, lay: ArenaLayout, arena, g_arena, peers, n_items_global, u_local, i_global, B_global, kind, shift,
+                         loss_accum, step, step_dev):
+        t, g = lay.tables(arena), lay.tables(g_arena)
+        t.n_items = g.n_items = n_items_global      # i_global holds GLOBAL ids; the item tables come from `peers`
+        _C.mf_train_fused_peer(t, g, peers, u_local, i_global, B_global, kind, shift, loss_accum, step, step_dev, self.status)
+
     def adamw(self, arena, m, v, g, segments, lr, wd, t, decoupled=True, consts_dev=None, step_dev=None):
         """torch.optim.AdamW / Adam over the local arena; `segments` = row ranges whose untouched rows skip the gradient
         traffic (see hsk_adamw_dense_rows); consts_dev / step_dev: graph mode."""
@@ -120,6 +126,7 @@ class ShardedMF:
         self.stamp_users = torch.zeros(max(self.spec.n_local_users, 1), dtype=torch.uint8, device=self.device)
         self.stamp_items = torch.zeros(max(self.spec.n_local_items, 1), dtype=torch.uint8, device=self.device)
         self._sparse, self._dense, self._graphs = {}, None, {}
+        self._peer = None
 
     # ---- collectives (skipped at world 1, where every exchange is the identity) ----
     def _a2a(self, out: torch.Tensor, inp: torch.Tensor):
@@ -328,6 +335,82 @@ class ShardedMF:
         self.ops.adamw(self.arena, self.m, self.v, self.g, self._segments(sparse_users, False), lr, wd, step, decoupled,
                        consts_dev=consts_dev, step_dev=step_dev)
 
+    # ---- PEER exchange: no exchange buffers at all — the step kernel reads the item rows from, and reduces their
+    # gradients into, the owners' memory over NVLink ----
+    PEER_MAX_LD = 128
+
+    def peer_supported(self) -> bool:
+        return self.device.type == 'cuda' and self.spec.world <= _C.MAX_PEERS and self.layout.ld <= self.PEER_MAX_LD
+
+    def _peer_setup(self):
+        """Once: every rank exports the allocations behind its parameter arena, gradient arena and item stamps (CUDA IPC),
+        maps its peers' and builds the table of item-shard addresses the kernel indexes by owner."""
+        if self._peer is not None:
+            return self._peer
+        G, r, lay = self.spec.world, self.spec.rank, self.layout
+        if not self.peer_supported():
+            raise _C.HskError(f'the peer exchange needs CUDA, at most {_C.MAX_PEERS} ranks on one node and rows of at most '
+                              f'{self.PEER_MAX_LD} floats (world {G}, ld {lay.ld}): use the sparse / dense exchange')
+        mine = {'off_V': lay.off_V, 'off_Ib': lay.off_Ib}
+        local = (self.arena, self.g, self.stamp_items)
+        if G > 1:
+            mine['exports'] = [_C.peer_export(t) for t in local]
+            every = [None] * G
+            dist.all_gather_object(every, mine, group=self.group)
+        else:
+            every = [mine]
+        opened = {}
+
+        def addr(q, which):          # address in THIS process of tensor `which` of rank q
+            if q == r:
+                return local[which].data_ptr()
+            handle, off = every[q]['exports'][which]
+            if (q, handle) not in opened:
+                opened[(q, handle)] = _C.peer_open(handle, self.device)
+            return opened[(q, handle)] + off
+
+        has_ib = lay.off_Ib >= 0
+        V = [addr(q, 0) + 4 * every[q]['off_V'] for q in range(G)]
+        gV = [addr(q, 1) + 4 * every[q]['off_V'] for q in range(G)]
+        Ib = [addr(q, 0) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
+        gIb = [addr(q, 1) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
+        st = [addr(q, 2) for q in range(G)]
+        self._peer = {'items': _C.make_peer_items(V, gV, Ib, gIb, st), 'opened': opened,
+                      'bar': torch.zeros(1, dtype=torch.float32, device=self.device)}
+        return self._peer
+
+    def _barrier(self):
+        """Stream-ordered cross-rank barrier (graph-capturable): the work every rank enqueued before it is complete before
+        anything enqueued after it starts on any rank."""
+        if self.spec.world > 1:
+            dist.all_reduce(self._peer['bar'], group=self.group)
+
+    def _peer_body(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled, capq=None, consts_dev=None,
+                   step_dev=None):
+        P = self._peer_setup()
+        G, lay = self.spec.world, self.layout
+        step = self.t + 1
+        self._barrier()      # every rank's parameters (previous AdamW, a load, a restore) and zeroed gradients are in place
+        u_local = self.ops.local_index(u_global, G, 0)
+        self.ops.mark_rows(u_local, lay.n_users, self.stamp_users, step, step_dev)
+        self.ops.train_fused_peer(lay, self.arena, self.g, P['items'], self.spec.n_items, u_local, i_global, B_global,
+                                  _C.LOSS_KINDS[loss_kind], neg_shift, self.loss_accum, step, step_dev)
+        self._barrier()      # every rank's gradient contributions and stamps have landed at their owners
+        gGb = lay.views(self.g)[4]
+        if gGb is not None:
+            self._all_reduce(gGb)
+        self.ops.adamw(self.arena, self.m, self.v, self.g, self._segments(True, True), lr, wd, step, decoupled,
+                       consts_dev=consts_dev, step_dev=step_dev)
+
+    def train_step_peer(self, u_global: torch.Tensor, i_global: torch.Tensor, B_global: int, loss_kind: str, neg_shift: float,
+                        lr: float, wd: float, decoupled: bool = True, capq=None):
+        """The step with the PEER exchange (see _peer_body): 2 barriers + 4 kernels, nothing staged."""
+        self._peer_body(u_global, i_global.contiguous(), B_global, loss_kind, neg_shift, lr, wd, decoupled)
+        self.t += 1
+
+    def train_step_peer_graphed(self, *a, capq=None):
+        return self._graphed(self._peer_body, 'peer', *a, capq)
+
     def train_step_dense(self, u_global: torch.Tensor, i_global: torch.Tensor, B_global: int, loss_kind: str,
                          neg_shift: float, lr: float, wd: float, decoupled: bool = True, capq=None):
         """Same step with a DENSE exchange (see _dense_body).  The right choice when B (N + 1) >> n_items (cfg2: 418 k
@@ -408,6 +491,12 @@ class ShardedMF:
         gc.collect()
         if self.device.type == 'cuda':
             torch.cuda.synchronize()
+        if self._peer is not None:
+            if self.spec.world > 1:
+                dist.barrier(group=self.group)      # no peer is still inside a kernel that addresses this rank's memory
+            for base in self._peer['opened'].values():
+                _C.peer_close(base)
+            self._peer = None
 
     def step(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled=True, exchange='auto', capq=None):
         """Dispatch on the expected fraction of distinct items: dense exchange when the batch covers the item table."""
@@ -415,7 +504,8 @@ class ShardedMF:
             dense = i_global.numel() >= 2 * self.spec.n_items // self.spec.world
             exchange = ('dense' if dense else 'sparse') + ('_graph' if exchange == 'auto_graph' else '')
         fn = {'dense': self.train_step_dense, 'dense_graph': self.train_step_dense_graphed, 'sparse': self.train_step,
-              'sparse_graph': self.train_step_graphed}[exchange]
+              'sparse_graph': self.train_step_graphed, 'peer': self.train_step_peer,
+              'peer_graph': self.train_step_peer_graphed}[exchange]
         with nvtx.range('hsk.sharded_step'):
             return fn(u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled, capq=capq)
 

@@ -144,6 +144,39 @@ HSK_API int hsk_shard_unpack_add(const float* in, int ld, int64_t n_local, const
                                  float* gIb /* nullable */, uint8_t* stamps /* nullable */, int64_t step,
                                  const int64_t* step_dev /* nullable: overrides step */, int32_t* status, hsk_stream_t stream);
 
+/* ---- PEER exchange of the item-sharded step: one kernel over NVLink peer memory instead of route / pack / all-to-all /
+ * unpack (SURVEY 8e's exchange, fused into the step kernel).  Every rank of a node maps the item side of every other
+ * rank's tables into its address space (CUDA IPC), then hsk_mf_train_fused_peer gathers the item rows of ITS samples
+ * straight from their owners' HBM (128-byte loads over NVLink), and sends the row / bias gradients home as
+ * red.relaxed.sys.global.add (performed in the owner's L2) together with the owner's row stamps
+ * (hsk_adamw_dense_rows).  The caller brackets it with two cross-rank barriers per step: all peers' AdamW done -> kernel ->
+ * all peers' kernels done -> AdamW.
+ *   hsk_peer_export  handle of the device allocation that contains `ptr` + the offset of ptr in it (send both to the peers)
+ *   hsk_peer_open    maps a peer's allocation: *base_out (keep for hsk_peer_close), the peer's `ptr` = base + offset;
+ *                    open each distinct handle once per process
+ *   hsk_mf_train_fused_peer  t / g: the LOCAL tables (user side used: Uw, Ub, Gb and their gradients; t->n_users local,
+ *       t->n_items = the GLOBAL item count); peers->V[q] etc. = rank q's local item tables (own rank included), item i =
+ *       row i / world of rank i % world; u_idx local rows, i_idx GLOBAL ids; normalisers from B_global as in
+ *       hsk_mf_train_fused_n; stamps as hsk_shard_unpack_add.  Rows of at most 128 floats (quarter-warp kernel). */
+#define HSK_MAX_PEERS 8
+typedef struct hsk_peer_items {
+    int32_t world;
+    const float* V[HSK_MAX_PEERS];   /* [n_local_q, ld] */
+    float* gV[HSK_MAX_PEERS];
+    const float* Ib[HSK_MAX_PEERS];  /* all NULL or all set */
+    float* gIb[HSK_MAX_PEERS];
+    uint8_t* stamps[HSK_MAX_PEERS];  /* all NULL or all set */
+} hsk_peer_items;
+#define HSK_PEER_HANDLE_BYTES 64
+HSK_API int hsk_peer_export(const void* ptr, void* handle /* [HSK_PEER_HANDLE_BYTES] */, int64_t* offset);
+HSK_API int hsk_peer_open(const void* handle, void** base_out);
+HSK_API int hsk_peer_close(void* base);
+HSK_API int hsk_mf_train_fused_peer(const hsk_mf_tables* t, const hsk_mf_tables* g, const hsk_peer_items* peers,
+                                    const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind,
+                                    float neg_shift, double* loss_accum, int64_t step,
+                                    const int64_t* step_dev /* nullable: overrides step */, int32_t* status,
+                                    hsk_stream_t stream);
+
 /* Owner-sharded index arithmetic of the multi-GPU step (row i lives on rank i % world at local row i / world):
  * out[e] = (idx[e] % world) * rank_stride + idx[e] / world.  rank_stride = rows per rank of a rank-major replica
  * (dense exchange), or 0 for the plain local row.  Negative indices pass through unchanged so that the consumer's

@@ -205,13 +205,15 @@ def test_shard_pack_and_unpack_add_match_the_torch_contract():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('exchange', ['sparse', 'sparse_graph', 'dense', 'dense_graph'])
+@pytest.mark.parametrize('exchange', ['sparse', 'sparse_graph', 'dense', 'dense_graph', 'peer', 'peer_graph'])
 @pytest.mark.parametrize('kind,flags', [('bpr', (False, True, False)), ('sampled_softmax', (True, True, False)),
                                         ('bce', (True, True, True))])
 def test_sharded_step_at_world_1_equals_the_single_gpu_step(exchange, kind, flags):
     """ShardedMF with world 1 (no process group: every exchange is the identity) runs the complete routed pipeline —
     hsk_route_items, pack, compact table, fused kernel with global normalisers, unpack-add, row-stamped AdamW, eager and
-    as a captured CUDA graph — and must reproduce FusedMFTrainStep on the same batches.  (No global bias under sampled
+    as a captured CUDA graph — and must reproduce FusedMFTrainStep on the same batches.  'peer': the step kernel over the
+    peer table (hsk_mf_train_fused_peer; one rank = its own memory through the same owner / row addressing, system-scope
+    reductions and kernel-written stamps).  (No global bias under sampled
     softmax: its gradient sum_j (softmax_j - [j = 0]) is mathematically zero, so Adam normalises pure rounding noise.)"""
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
     from hassaku_b200.sharded import ShardedMF

@@ -94,7 +94,8 @@ def test_sharded_step_and_eval_match_single_gpu(world, tmp_path):
 
 def _worker_graph(rank, world, port, out_dir):
     """The CUDA-graph replays of the dense and of the sparse (device-routed, fixed-capacity all-to-all) step equal their
-    eager versions (fixed local batch shape)."""
+    eager versions (fixed local batch shape); the peer exchange (item rows read from / gradients reduced into the owners'
+    memory by the step kernel, CUDA IPC mappings) equals the sparse one, eager and captured."""
     import faulthandler
     faulthandler.dump_traceback_later(60, exit=True)
     models = []
@@ -111,7 +112,7 @@ def _worker_graph(rank, world, port, out_dir):
         with torch.no_grad():
             for p in full.parameters():
                 p.copy_(torch.randn_like(p) * (1 / math.sqrt(d) if p.shape[-1] == d else 0.1))
-        for eager, graphed in (('dense', 'dense_graph'), ('sparse', 'sparse_graph')):
+        for eager, graphed in (('dense', 'dense_graph'), ('sparse', 'sparse_graph'), ('sparse', 'peer'), ('peer', 'peer_graph')):
             a = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
             b = ShardedMF(U, I, d, use_item_bias=True, world=world, rank=rank, device=dev)
             models += [a, b]
@@ -132,7 +133,9 @@ def _worker_graph(rank, world, port, out_dir):
             # atomics order differs run to run; the arithmetic is identical.  Bound: the per-step tolerance of the parity
             # tests (rtol 1e-5 + the Adam-eps conditioning term 2e-3 lr for elements whose gradient nearly cancels)
             assert err < 1e-5 + 2e-3 * 1e-3, (eager, err)
-            assert abs(a.pop_loss() - b.pop_loss()) < 1e-9
+            la, lb = a.pop_loss(), b.pop_loss()
+            # same kernel eager / captured: fp64 accumulation of identical terms; sparse vs peer: two kernels (fp32 summation order)
+            assert abs(la - lb) < (1e-9 if eager == graphed.replace('_graph', '') else 1e-6 * abs(la)), (eager, graphed, la, lb)
             assert float(a.g.abs().max()) == 0.0 and float(b.g.abs().max()) == 0.0
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
