@@ -998,7 +998,7 @@ def _run_ours_sharded(args, wl, holder):
         u_dev = [torch.from_numpy(u * world + rank).to(dev) for u in us]     # local row -> global user id
         i_dev = [torch.from_numpy(x).to(dev) for x in its]
         n_train = int(mine.nnz)
-        if exchange.startswith('sparse') and B * (N + 1) >= 2 * I // world:
+        if not exchange.startswith('dense') and B * (N + 1) >= 2 * I // world:
             exchange = 'dense_graph'        # the batch covers the item table: dense exchange (see ShardedMF.step)
     torch.cuda.empty_cache()
 
@@ -1017,12 +1017,15 @@ def _run_ours_sharded(args, wl, holder):
     def make_smf(U_, I_, d_, std, seed, keep_full=False):
         sd = full_tables(U_, I_, d_, std, seed)
         s = ShardedMF(U_, I_, d_, use_item_bias=True, world=world, rank=rank, device=dev)
+        s.peer_barrier = args.peer_barrier
         holder.append(s)
         s.load_full_state_dict(sd)
         return (s, sd) if keep_full else s
 
     shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
     smf, full_sd = make_smf(U, I, d, None, 64, keep_full=True)
+    if exchange.startswith('peer') and not smf.peer_supported():
+        exchange = 'sparse_graph'           # rows longer than 128 floats / more than 8 ranks: the all-to-all exchange
     # ---- parity self-check (outside every timed region) ----
     parity = {'train': None, 'eval': None}
     try:
@@ -1243,7 +1246,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU legs (profiling runs)')
-    ap.add_argument('--exchange', default='sparse_graph', choices=['sparse', 'sparse_graph', 'dense', 'dense_graph', 'peer', 'peer_graph'],
+    ap.add_argument('--peer-barrier', default='kernel', choices=['kernel', 'nccl'], help='peer exchange: cross-rank barrier')
+    ap.add_argument('--exchange', default='peer_graph', choices=['sparse', 'sparse_graph', 'dense', 'dense_graph', 'peer', 'peer_graph'],
                     help='N > 1: item-row exchange of the sharded step')
     ap.add_argument('--no-eval', action='store_true', help='skip the cfg5 full-rank evaluation sweep')
     ap.add_argument('--no-also', action='store_true', help='N = 1: skip the cfg2 / cfg3 / loader side lines')

@@ -19,6 +19,7 @@ LOSS_KINDS = {'bpr': 0, 'sampled_softmax': 1, 'bce': 2}
 STATUS_BAD_INDEX = 1
 STATUS_CAPACITY = 2
 STATUS_SAMPLER_ROUNDS = 4
+STATUS_BARRIER_TIMEOUT = 8
 PRECISIONS = {'fp32': 0, 'tf32': 1, 'bf16': 2}
 TRAIN_VARIANTS = {'auto': 0, 'regs': 1, 'ring': 2, 'q': 3}   # HSK_TRAIN_* of hsk_mf_train_fused_v
 # kernel choice used by mf_train_fused / mf_train_fused_n of THIS binding (parity tests and scripts/kbench.py set it; the
@@ -53,6 +54,11 @@ class PeerItems(C.Structure):
                 ('Ib', C.c_void_p * MAX_PEERS), ('gIb', C.c_void_p * MAX_PEERS), ('stamps', C.c_void_p * MAX_PEERS)]
 
 
+class PeerFlags(C.Structure):
+    """struct hsk_peer_flags: every rank's barrier flag array (hsk_peer_barrier)."""
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('flags', C.c_void_p * MAX_PEERS)]
+
+
 _lib = None
 
 
@@ -72,6 +78,7 @@ def _declare(lib):
         'hsk_peer_export': (i32, [vp, vp, C.POINTER(C.c_int64)]),
         'hsk_peer_open': (i32, [vp, C.POINTER(C.c_void_p)]),
         'hsk_peer_close': (i32, [vp]),
+        'hsk_peer_barrier': (i32, [C.POINTER(PeerFlags), vp, vp, vp]),
         'hsk_mf_train_fused_peer': (i32, [T, T, C.POINTER(PeerItems), vp, vp, i32, i32, i64, i32, f32, vp, i64, vp, vp, vp]),
         'hsk_gather_rows': (i32, [vp, i32, vp, i64, i64, vp, vp, vp]),
         'hsk_shard_local_index': (i32, [vp, i64, i32, i64, vp, vp]),
@@ -280,6 +287,21 @@ def make_peer_items(V_ptrs, gV_ptrs, Ib_ptrs=None, gIb_ptrs=None, stamp_ptrs=Non
         p.gIb[q] = gIb_ptrs[q] if gIb_ptrs else None
         p.stamps[q] = stamp_ptrs[q] if stamp_ptrs else None
     return p
+
+
+def make_peer_flags(flag_ptrs, rank: int) -> PeerFlags:
+    f = PeerFlags()
+    f.world, f.rank = len(flag_ptrs), rank
+    for q, a in enumerate(flag_ptrs):
+        f.flags[q] = a
+    return f
+
+
+def peer_barrier(flags: PeerFlags, epoch, status=None):
+    """hsk_peer_barrier on the current stream of epoch's device."""
+    _req(epoch, torch.int32, 'epoch')
+    with _on_device_of(epoch, status) as st:
+        _check(lib().hsk_peer_barrier(C.byref(flags), epoch.data_ptr(), _ptr(status), st), 'hsk_peer_barrier')
 
 
 def mf_train_fused_peer(tables: MfTables, grads: MfTables, peers: PeerItems, u_idx, i_idx, B_global: int, loss_kind: int,

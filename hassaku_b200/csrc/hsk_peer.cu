@@ -26,6 +26,47 @@ static int address_range(const void* ptr, CUdeviceptr* base, size_t* size) {
 
 }  // namespace hsk
 
+namespace hsk {
+
+constexpr long long kBarrierSpinCycles = 40ll * 1000 * 1000 * 1000;   // ~20 s at 2 GHz
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(hsk_peer_flags f, uint32_t* epoch, int32_t* status) {
+    __shared__ uint32_t e_s;
+    const int q = threadIdx.x;
+    if (q == 0) e_s = *epoch + 1u;
+    __syncthreads();
+    const uint32_t e = e_s;
+    if (q < f.world) {
+        // everything this GPU did before (previous kernels on the stream, their peer stores / reductions included) is
+        // ordered before the arrival flag
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f.flags[q] + f.rank), "r"(e) : "memory");
+        const uint32_t* mine = f.flags[f.rank] + q;
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+            if ((int32_t)(v - e) >= 0) break;          // rank q has arrived at this barrier (or already at the next one)
+            if (clock64() - t0 > kBarrierSpinCycles) {
+                if (status) atomicOr(status, HSK_STATUS_BARRIER_TIMEOUT);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (q == 0) *epoch = e;
+}
+
+}  // namespace hsk
+
+extern "C" int hsk_peer_barrier(const hsk_peer_flags* f, uint32_t* epoch, int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(f && epoch, "hsk_peer_barrier: null pointer");
+    HSK_REQUIRE(f->world >= 1 && f->world <= HSK_MAX_PEERS && f->rank >= 0 && f->rank < f->world, "hsk_peer_barrier: bad world / rank");
+    for (int q = 0; q < f->world; ++q) HSK_REQUIRE(f->flags[q], "hsk_peer_barrier: flags of rank %d missing", q);
+    hsk::peer_barrier_kernel<<<1, 32, 0, hsk::as_stream(stream)>>>(*f, epoch, status);
+    return hsk::check_launch("hsk_peer_barrier");
+}
+
 static_assert(sizeof(cudaIpcMemHandle_t) == HSK_PEER_HANDLE_BYTES, "IPC handle size");
 
 extern "C" int hsk_peer_export(const void* ptr, void* handle, int64_t* offset) {

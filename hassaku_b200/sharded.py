@@ -338,6 +338,7 @@ class ShardedMF:
     # ---- PEER exchange: no exchange buffers at all — the step kernel reads the item rows from, and reduces their
     # gradients into, the owners' memory over NVLink ----
     PEER_MAX_LD = 128
+    peer_barrier = 'kernel'      # 'kernel': hsk_peer_barrier (flags in peer memory); 'nccl': a 4-byte all-reduce
 
     def peer_supported(self) -> bool:
         return self.device.type == 'cuda' and self.spec.world <= _C.MAX_PEERS and self.layout.ld <= self.PEER_MAX_LD
@@ -352,11 +353,17 @@ class ShardedMF:
             raise _C.HskError(f'the peer exchange needs CUDA, at most {_C.MAX_PEERS} ranks on one node and rows of at most '
                               f'{self.PEER_MAX_LD} floats (world {G}, ld {lay.ld}): use the sparse / dense exchange')
         mine = {'off_V': lay.off_V, 'off_Ib': lay.off_Ib}
-        local = (self.arena, self.g, self.stamp_items)
+        flags = torch.zeros(_C.MAX_PEERS, dtype=torch.int32, device=self.device)      # barrier arrival flags, written by the peers
+        local = (self.arena, self.g, self.stamp_items, flags)
         if G > 1:
+            import socket
+            mine['host'] = socket.gethostname()
             mine['exports'] = [_C.peer_export(t) for t in local]
             every = [None] * G
             dist.all_gather_object(every, mine, group=self.group)
+            if len({e['host'] for e in every}) != 1:
+                raise _C.HskError('the peer exchange maps the other ranks\' memory (CUDA IPC over NVLink): all ranks must run on '
+                                  'one node — use the sparse / dense exchange across nodes')
         else:
             every = [mine]
         opened = {}
@@ -376,14 +383,22 @@ class ShardedMF:
         gIb = [addr(q, 1) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
         st = [addr(q, 2) for q in range(G)]
         self._peer = {'items': _C.make_peer_items(V, gV, Ib, gIb, st), 'opened': opened,
-                      'bar': torch.zeros(1, dtype=torch.float32, device=self.device)}
+                      'bar': torch.zeros(1, dtype=torch.float32, device=self.device),
+                      'flags': flags, 'flag_table': _C.make_peer_flags([addr(q, 3) for q in range(G)], r),
+                      'epoch': torch.zeros(1, dtype=torch.int32, device=self.device)}
+        if G > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)       # every rank's flags are zero and mapped before the first arrival is written
         return self._peer
 
     def _barrier(self):
         """Stream-ordered cross-rank barrier (graph-capturable): the work every rank enqueued before it is complete before
         anything enqueued after it starts on any rank."""
         if self.spec.world > 1:
-            dist.all_reduce(self._peer['bar'], group=self.group)
+            if self.peer_barrier == 'kernel':
+                _C.peer_barrier(self._peer['flag_table'], self._peer['epoch'], self.status)
+            else:
+                dist.all_reduce(self._peer['bar'], group=self.group)
 
     def _peer_body(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled, capq=None, consts_dev=None,
                    step_dev=None):
@@ -528,6 +543,8 @@ class ShardedMF:
                 what.append('an out-of-range user / item index')
             if st & _C.STATUS_CAPACITY:
                 what.append('an overflow of the fixed-capacity exchange buffers (raise capq)')
+            if st & _C.STATUS_BARRIER_TIMEOUT:
+                what.append('a peer barrier that timed out (a rank is missing or ran a different number of steps)')
             raise _C.HskError(f'rank {self.spec.rank}: the sharded step reported ' + ' and '.join(what or [f'status {st}']))
 
     def _csr_cache(self, m):

@@ -42,7 +42,7 @@ typedef void* hsk_stream_t; /* cudaStream_t */
 
 enum { HSK_OK = 0, HSK_ERR_INVALID = -1, HSK_ERR_CUDA = -2, HSK_ERR_UNSUPPORTED = -3 };
 enum { HSK_LOSS_BPR = 0, HSK_LOSS_SAMPLED_SOFTMAX = 1, HSK_LOSS_BCE = 2 }; /* train/rec_losses.py:142-145 */
-enum { HSK_STATUS_BAD_INDEX = 1, HSK_STATUS_CAPACITY = 2, HSK_STATUS_SAMPLER_ROUNDS = 4 };
+enum { HSK_STATUS_BAD_INDEX = 1, HSK_STATUS_CAPACITY = 2, HSK_STATUS_SAMPLER_ROUNDS = 4, HSK_STATUS_BARRIER_TIMEOUT = 8 };
 enum { HSK_PREC_FP32 = 0, HSK_PREC_TF32 = 1, HSK_PREC_BF16 = 2 }; /* evaluator scoring precision */
 /* kernel selection of hsk_mf_train_fused_v: every variant computes the same step (parity tests, A/B measurements) */
 enum { HSK_TRAIN_AUTO = 0, HSK_TRAIN_REGS = 1, HSK_TRAIN_RING = 2, HSK_TRAIN_QWARP = 3 };
@@ -171,6 +171,17 @@ typedef struct hsk_peer_items {
 HSK_API int hsk_peer_export(const void* ptr, void* handle /* [HSK_PEER_HANDLE_BYTES] */, int64_t* offset);
 HSK_API int hsk_peer_open(const void* handle, void** base_out);
 HSK_API int hsk_peer_close(void* base);
+/* Cross-rank barrier on the stream (graph-capturable, no host argument changes between replays): every rank owns an
+ * array of HSK_MAX_PEERS uint32 flags (zero-initialised, peer-mapped like the tables) and a local uint32 epoch counter
+ * (zero-initialised).  The kernel bumps the epoch, stores it (st.release.sys) into flags[rank] of EVERY rank and spins
+ * (ld.acquire.sys on its own flags) until every rank's epoch has arrived: work enqueued before the barrier on any rank
+ * is complete before work enqueued after it starts on any rank.  All ranks must call it the same number of times; a
+ * rank that waits longer than ~20 s gives up and sets HSK_STATUS_BARRIER_TIMEOUT. */
+typedef struct hsk_peer_flags {
+    int32_t world, rank;
+    uint32_t* flags[HSK_MAX_PEERS];
+} hsk_peer_flags;
+HSK_API int hsk_peer_barrier(const hsk_peer_flags* f, uint32_t* epoch, int32_t* status, hsk_stream_t stream);
 HSK_API int hsk_mf_train_fused_peer(const hsk_mf_tables* t, const hsk_mf_tables* g, const hsk_peer_items* peers,
                                     const int64_t* u_idx, const int64_t* i_idx, int B, int N1, int64_t B_global, int loss_kind,
                                     float neg_shift, double* loss_accum, int64_t step,

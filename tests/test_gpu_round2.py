@@ -215,6 +215,7 @@ def test_sharded_step_at_world_1_equals_the_single_gpu_step(exchange, kind, flag
     peer table (hsk_mf_train_fused_peer; one rank = its own memory through the same owner / row addressing, system-scope
     reductions and kernel-written stamps).  (No global bias under sampled
     softmax: its gradient sum_j (softmax_j - [j = 0]) is mathematically zero, so Adam normalises pure rounding noise.)"""
+    from hassaku_b200 import _C
     from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
     from hassaku_b200.sharded import ShardedMF
     from hassaku_b200.train.optim import DenseAdam
@@ -240,12 +241,17 @@ def test_sharded_step_at_world_1_equals_the_single_gpu_step(exchange, kind, flag
     smf.load_full_state_dict(sd0)
     shift = float(loss_fn.neg_shift())
     rng = np.random.RandomState(9)
+    # the peer step is the quarter-warp kernel: the single-GPU side runs the same kernel, so that gradients which are
+    # mathematically zero (the user bias under sampled softmax) carry the same rounding noise into Adam's normalisation
+    variant0 = _C.TRAIN_VARIANT
     try:
         for s in range(5):
             u = torch.from_numpy(rng.randint(0, U, B).astype(np.int64)).cuda()
             i = torch.from_numpy(rng.randint(0, I, (B, N + 1)).astype(np.int64)).cuda()
             i[:, 2] = i[:, 1]
+            _C.TRAIN_VARIANT = 'q' if exchange.startswith('peer') else variant0
             step(u, i)
+            _C.TRAIN_VARIANT = variant0
             smf.step(u, i, B, kind, shift, lr, wd, exchange=exchange)
             l_single, l_sh = step.pop_loss_sum(), smf.pop_loss()
             assert abs(l_single - l_sh) <= 1e-5 * abs(l_single), (s, l_single, l_sh)
@@ -256,6 +262,7 @@ def test_sharded_step_at_world_1_equals_the_single_gpu_step(exchange, kind, flag
             assert err < 1e-5 + 2e-3 * lr, (n, err)
         assert float(smf.g.abs().max()) == 0.0
     finally:
+        _C.TRAIN_VARIANT = variant0
         smf.close()
 
 
