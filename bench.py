@@ -77,6 +77,30 @@ def measured_peaks():
     return p['hbm_gbs'], p['source']
 
 
+def measure_l2_copy_peak(dev):
+    """Measured L2 bandwidth of THIS GPU (GB/s, read + write bytes): the best of three L2-resident streaming passes run 100 x
+    back to back — a 16 MB -> 16 MB copy, an in-place add over 48 MB, a sum over 48 MB (launch gaps included, so a lower
+    bound of the L2 peak).  The denominator for the L2-resident workloads (cfg2 / cfg3 `value_l2_warm`)."""
+    import torch
+    x = torch.zeros(16 << 20, dtype=torch.uint8, device=dev)
+    y = torch.zeros(16 << 20, dtype=torch.uint8, device=dev)
+    z = torch.zeros(12 << 20, dtype=torch.float32, device=dev)
+    best = {}
+    for name, fn, nbytes in (('copy 16 MB -> 16 MB', lambda: y.copy_(x), 2.0 * x.numel()),
+                             ('in-place add, 48 MB', lambda: z.add_(1.0), 2.0 * z.numel() * 4),
+                             ('sum, 48 MB', lambda: z.sum(), 1.0 * z.numel() * 4)):
+        for _ in range(5):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(100):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        best[name] = nbytes * 100 / (a.elapsed_time(b) * 1e-3) / 1e9
+    return max(best.values()), best
+
+
 def committed_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this bench
     command (profiles/r02_traffic.json: {workload: {kernel: {'bytes': ..., 'capture': file}}}), or None."""
@@ -843,6 +867,20 @@ def run_ours(args, wl):
             except Exception as ex:
                 also[w2] = {'error': repr(ex)}
             torch.cuda.empty_cache()
+        try:
+            l2, l2_all = measure_l2_copy_peak(dev)
+            also['peaks'] = {'l2_gbs': l2, 'l2_probes_gbs': l2_all,
+                             'how': 'best of three L2-resident streaming passes (torch kernels, 100 launches back to back, launch gaps '
+                                    'included): a lower bound of the L2 peak'}
+            for w2 in ('cfg2', 'cfg3'):
+                if 'value_l2_warm' in also.get(w2, {}):
+                    ab2 = algorithmic_bytes(also[w2]['config']['n_users'], also[w2]['config']['n_items'], WORKLOADS[w2][1], WORKLOADS[w2][2], WORKLOADS[w2][3])
+                    ms_warm = WORKLOADS[w2][2] * WORKLOADS[w2][3] / also[w2]['value_l2_warm'] * 1e3
+                    also[w2]['roofline_l2_warm'] = {'bound': 'l2', 'unit': 'GB/s', 'achieved': ab2['total'] / (ms_warm * 1e-3) / 1e9, 'peak': l2,
+                                                    'frac': ab2['total'] / (ms_warm * 1e-3) / 1e9 / l2,
+                                                    'note': 'back-to-back steps (no flush): algorithmic bytes of the step against the measured L2 streaming bandwidth (a lower bound of the peak, so the fraction can exceed 1)'}
+        except Exception as ex:
+            also['peaks'] = {'error': repr(ex)}
         try:
             also['loaders'] = bench_sampler_and_fit(dev)
         except Exception as ex:

@@ -74,12 +74,20 @@ struct QRow {
     // other ranks' and the owner's own contributions
     __device__ __forceinline__ void red_peer(float* dst, float a, int l, bool last_ok) const {
         float4* p = reinterpret_cast<float4*>(dst) + l;
+#if defined(HSK_MEASURE_PEER_NORED)      // measurement builds only (profiles/r02_peer_exchange.md): what the reductions cost on the link
+        (void)p;
+#elif defined(HSK_MEASURE_PEER_STORE)    // ... and what the same bytes cost as plain stores (WRONG results)
+#pragma unroll
+        for (int k = 0; k < K4; ++k)
+            if (k < K4 - 1 || last_ok) p[8 * k] = make_float4(a * v[k].x, a * v[k].y, a * v[k].z, a * v[k].w);
+#else
 #pragma unroll
         for (int k = 0; k < K4; ++k)
             if (k < K4 - 1 || last_ok)
                 asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p + 8 * k), "f"(a * v[k].x),
                              "f"(a * v[k].y), "f"(a * v[k].z), "f"(a * v[k].w)
                              : "memory");
+#endif
     }
 };
 
