@@ -12,6 +12,9 @@ int main(void) {
     struct hsk_mf_tables t;
     memset(&t, 0, sizeof t);
     printf("hsk_version %d\n", hsk_version());
+    /* struct sizes: tests/test_cabi_and_host.py compares them with the ctypes mirrors of hassaku_b200/_C.py */
+    printf("sizeof hsk_mf_tables=%d hsk_row_segment=%d hsk_peer_items=%d hsk_peer_flags=%d\n", (int)sizeof(struct hsk_mf_tables),
+           (int)sizeof(struct hsk_row_segment), (int)sizeof(struct hsk_peer_items), (int)sizeof(struct hsk_peer_flags));
     printf("kpad(d=256, bf16) = %d\n", hsk_eval_tc_kpad(256, HSK_PREC_BF16));
     printf("scratch(Be=8192, I=1000000, k=100) = %lld bytes\n", (long long)hsk_eval_topk_scratch_bytes(8192, 1000000, 100));
     /* argument validation happens before any CUDA call: a null table is rejected with a message, nothing is launched */

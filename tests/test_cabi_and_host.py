@@ -255,3 +255,10 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
                    check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert 'hsk_version' in out and 'tables are null' in out
+    # the ctypes mirrors have the layout the C compiler gives the header's structs
+    import ctypes
+    import re
+    from hassaku_b200 import _C
+    sizes = dict((k, int(v)) for k, v in re.findall(r'(hsk_\w+)=(\d+)', out))
+    assert sizes == {'hsk_mf_tables': ctypes.sizeof(_C.MfTables), 'hsk_row_segment': ctypes.sizeof(_C.RowSegment),
+                     'hsk_peer_items': ctypes.sizeof(_C.PeerItems), 'hsk_peer_flags': ctypes.sizeof(_C.PeerFlags)}, sizes
