@@ -171,6 +171,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ib_pair[pt + 64] = ib_at(TC_ACC_STAGES, pt + 64);
         named_bar_sync(bar_id, 64);
 
+        int next_cut = 4;          // 128-item tiles after which every row is cut: 4, 6, 9, 13, ... (x 3 / 2)
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t % TC_ACC_STAGES;
             const int64_t n0 = (int64_t)(t_begin + t) * TC_BN;
@@ -218,7 +219,14 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // pair barrier, one flag load per tile.  Only when a list may overflow (or at the last tile) do the two warps
             // exchange their counts and run the cut protocol (two more pair barriers).
             const bool last = (t + 1 == n_my_tiles);
-            const bool warp_need = __any_sync(kFull, row_ok && cnt > prune_at) || last;
+            // scheduled cut of EVERY row after the same tiles (geometric schedule, see hsk_eval_tc2.cu); the fill trigger stays
+            // as the safety net for score streams that are not in random order
+            bool sched = false;
+            if (t + 1 == next_cut) {
+                sched = true;
+                next_cut += next_cut / 2;
+            }
+            const bool warp_need = __any_sync(kFull, row_ok && cnt > prune_at) || last || sched;
             if (lane == 0) s_need[quarter][half][t & 1] = warp_need ? 1 : 0;
             named_bar_sync(bar_id, 64);
             const bool pair_need = (s_need[quarter][0][t & 1] | s_need[quarter][1][t & 1]) != 0;
@@ -231,7 +239,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int rj = quarter * 32 + half * 16 + lane;
                     my_a = s_cnt2[0][rj];
                     my_b = s_cnt2[1][rj];
-                    my_need = s_rowok[rj] && (my_a > prune_at || my_b > prune_at || last);
+                    my_need = s_rowok[rj] && (my_a > prune_at || my_b > prune_at || last || sched);
                 }
                 unsigned need = __ballot_sync(kFull, my_need);
                 while (need) {

@@ -28,6 +28,10 @@ constexpr int T2_ACC_STAGES = 2;             // 2 x 256 fp32 columns
 // lane quarter split the tile's columns): NCG = 2 -> 8 epilogue warps x 128 columns, NCG = 4 -> 16 warps x 64 columns.
 // A row's 512-entry candidate list has one region per column group; a tile appends at most COLS keys to a region, so a
 // region is cut when it holds more than RCAP - COLS, and an intermediate cut keeps <= NCG * (RCAP - COLS) = 256 entries.
+#ifndef HSK_T2_SCHED_NUM
+#define HSK_T2_SCHED_NUM 3     // schedule ratio 3 / 2 (measurement builds override: profiles/r02_eval_tc2_stall_analysis.md)
+#define HSK_T2_SCHED_DEN 2
+#endif
 template <int NCG> struct T2Cfg {
     static constexpr int WARPS = 4 * NCG;
     static constexpr int THREADS = 64 + WARPS * 32;
@@ -35,6 +39,11 @@ template <int NCG> struct T2Cfg {
     static constexpr int RCAP = TC_CAP / NCG;
     static constexpr int PRUNE_AT = RCAP - COLS;
     static constexpr int KEEP_MID = NCG * PRUNE_AT;
+#ifdef HSK_T2_TRIG
+    static constexpr int TRIG = HSK_T2_TRIG;         // measurement builds: cut trigger A/B
+#else
+    static constexpr int TRIG = PRUNE_AT;
+#endif
     static constexpr int GROUP = NCG * 32;           // threads that share a lane quarter
     static constexpr int ROWS_PER_WARP = 32 / NCG;   // rows a warp cuts / finalises
 };
@@ -233,6 +242,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int h = 0; h < STG; ++h) ib_grp[pt + Cfg::GROUP * h] = ib_at(T2_ACC_STAGES, pt + Cfg::GROUP * h);   // slot 0 <- tile 2
         named_bar_sync(bar_id, Cfg::GROUP);
 
+        int next_cut = 2;          // tiles after which every row is cut: 2, 3, 4, 6, 9, 13, ... (ratio HSK_T2_SCHED_NUM / DEN)
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
             const int64_t n0 = (int64_t)(t_begin + t) * T2_BN;
@@ -285,7 +295,18 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int h = 0; h < STG; ++h) ib_grp[((t + 1) & 1) * T2_BN + pt + Cfg::GROUP * h] = ibn[h];   // staging slot of tile t + 3
             const bool last = (t + 1 == n_my_tiles);
-            const bool warp_need = __any_sync(kFull, row_ok && cnt > Cfg::PRUNE_AT) || last;
+            // scheduled cut: EVERY row of the CTA pair is cut after the same tiles, a geometric schedule (the k-th best score of a
+            // random stream needs ~k new candidates per doubling of the items seen).  Cuts triggered by a region filling up
+            // hit a different row in nearly every tile and each one stalled the warp pair, then the accumulator stage, then
+            // the MMA and the other CTA for ~1.5 k cycles; now the stall is paid ~20 times per launch by all warps at once and
+            // the fill trigger only fires for rows whose scores do not arrive in random order.
+            bool sched = false;
+            if (t + 1 == next_cut) {
+                sched = true;
+                const int step = (next_cut * (HSK_T2_SCHED_NUM - HSK_T2_SCHED_DEN)) / HSK_T2_SCHED_DEN;
+                next_cut += step > 1 ? step : 1;
+            }
+            const bool warp_need = __any_sync(kFull, row_ok && cnt > Cfg::TRIG) || last || sched;
             if (lane == 0) s_need[quarter][cg][t & 1] = warp_need ? 1 : 0;
             named_bar_sync(bar_id, Cfg::GROUP);
             int grp_need = 0;
@@ -300,9 +321,9 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 for (int q = 0; q < NCG; ++q) my_c[q] = 0;
                 if (lane < Cfg::ROWS_PER_WARP) {   // lane j looks at row j of this warp's rows
                     const int rj = quarter * 32 + cg * Cfg::ROWS_PER_WARP + lane;
-                    my_need = last;
+                    my_need = last || sched;
 #pragma unroll
-                    for (int q = 0; q < NCG; ++q) { my_c[q] = s_cnt[q][rj]; my_need |= my_c[q] > Cfg::PRUNE_AT; }
+                    for (int q = 0; q < NCG; ++q) { my_c[q] = s_cnt[q][rj]; my_need |= my_c[q] > Cfg::TRIG; }
                     my_need = my_need && s_rowok[rj];
                 }
                 unsigned need = __ballot_sync(kFull, my_need);
