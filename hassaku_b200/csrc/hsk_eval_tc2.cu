@@ -217,7 +217,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int bar_id = 1 + quarter;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * Cfg::COLS);
         float* ib_grp = &s_ib[quarter][0][0];
-        const int pt = cg * 32 + lane;       // thread index within the lane-quarter group
+        const int sc0 = cg * Cfg::COLS + lane;   // a warp stages the bias values of ITS columns: sc0 + 32 h, h < STG
         constexpr int STG = T2_BN / Cfg::GROUP;   // bias values a thread stages per tile
         ExCursor ex;
         ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
@@ -230,7 +230,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // prologue: bias rows of the first two tiles into the stages (through the group's staging tile), stages to the MMA warp
         for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
 #pragma unroll
-            for (int h = 0; h < STG; ++h) ib_grp[pt + Cfg::GROUP * h] = ib_at(ts, pt + Cfg::GROUP * h);
+            for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_at(ts, sc0 + 32 * h);
             named_bar_sync(bar_id, Cfg::GROUP);
             tc_write_bias<Cfg::COLS / 32>(ib_grp + cg * Cfg::COLS, tlane + (uint32_t)ts * T2_BN);
             tc_fence_before();
@@ -239,7 +239,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             named_bar_sync(bar_id, Cfg::GROUP);
         }
 #pragma unroll
-        for (int h = 0; h < STG; ++h) ib_grp[pt + Cfg::GROUP * h] = ib_at(T2_ACC_STAGES, pt + Cfg::GROUP * h);   // slot 0 <- tile 2
+        for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_at(T2_ACC_STAGES, sc0 + 32 * h);   // slot 0 <- tile 2
         named_bar_sync(bar_id, Cfg::GROUP);
 
         int next_cut = 2;          // tiles after which every row is cut: 2, 3, 4, 6, 9, 13, ... (ratio HSK_T2_SCHED_NUM / DEN)
@@ -252,7 +252,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // the bias values the NEXT iteration writes (tile t + 3): in flight during this tile
             float ibn[STG];
 #pragma unroll
-            for (int h = 0; h < STG; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, pt + Cfg::GROUP * h);
+            for (int h = 0; h < STG; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, sc0 + 32 * h);
             mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)as * T2_BN;
@@ -293,7 +293,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
             }
 #pragma unroll
-            for (int h = 0; h < STG; ++h) ib_grp[((t + 1) & 1) * T2_BN + pt + Cfg::GROUP * h] = ibn[h];   // staging slot of tile t + 3
+            for (int h = 0; h < STG; ++h) ib_grp[((t + 1) & 1) * T2_BN + sc0 + 32 * h] = ibn[h];   // staging slot of tile t + 3
             const bool last = (t + 1 == n_my_tiles);
             // scheduled cut: EVERY row of the CTA pair is cut after the same tiles, a geometric schedule (the k-th best score of a
             // random stream needs ~k new candidates per doubling of the items seen).  Cuts triggered by a region filling up
@@ -306,12 +306,17 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int step = (next_cut * (HSK_T2_SCHED_NUM - HSK_T2_SCHED_DEN)) / HSK_T2_SCHED_DEN;
                 next_cut += step > 1 ? step : 1;
             }
+#ifdef HSK_MEASURE_NOPAIRBAR   // measurement builds only: no fill trigger, so no per-tile barrier of the two warps (UNSAFE for sorted streams)
+            __syncwarp();
+            int grp_need = (last || sched) ? 1 : 0;
+#else
             const bool warp_need = __any_sync(kFull, row_ok && cnt > Cfg::TRIG) || last || sched;
             if (lane == 0) s_need[quarter][cg][t & 1] = warp_need ? 1 : 0;
             named_bar_sync(bar_id, Cfg::GROUP);
             int grp_need = 0;
 #pragma unroll
             for (int q = 0; q < NCG; ++q) grp_need |= s_need[quarter][q][t & 1];
+#endif
             if (grp_need) {
                 s_cnt[cg][r] = cnt;
                 named_bar_sync(bar_id, Cfg::GROUP);
