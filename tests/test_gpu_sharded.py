@@ -213,3 +213,69 @@ def _worker_tc_eval(rank, world, port, out_dir):
 def test_sharded_tensor_core_evaluation_matches_single_gpu(tmp_path):
     mp.spawn(_worker_tc_eval, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / 'ok').exists()
+
+
+def _worker_trainer(rank, world, port, out_dir):
+    """ShardedTrainer.fit (the multi-GPU Trainer.fit): trains, validates with the sharded evaluator, stops early, writes the
+    reference-format checkpoint — and the checkpoint evaluates to the reported best metric on ONE GPU."""
+    import faulthandler
+    faulthandler.dump_traceback_later(120, exit=True)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    tr = None
+    try:
+        from hassaku_b200.algorithms.sgd_alg import SGDMatrixFactorization
+        from hassaku_b200.data.dataloader import EvalLoader, NegativeSampler, TrainDataLoader
+        from hassaku_b200.data.dataset import FullEvalDataset, TrainRecDataset
+        from hassaku_b200.data.synthetic import make_interactions
+        from hassaku_b200.eval.eval import FullEvaluator, evaluate_recommender_algorithm
+        from hassaku_b200.train.rec_losses import RecBayesianPersonalizedRankingLoss
+        from hassaku_b200.train.sharded_trainer import ShardedTrainer
+        U, I, d = 1500, 6000, 64          # batch slots << items: the peer exchange is the one chosen
+        dev = torch.device('cuda', rank)
+        data = make_interactions(U, I, 60000, seed=4, n_user_groups=2)
+        train_ds = TrainRecDataset.from_interactions(data.train, data.user_group, 2)
+        val_ds = FullEvalDataset.from_interactions(data.val, data.train, 'val', data.user_group, 2)
+        torch.manual_seed(7)
+        model = SGDMatrixFactorization(U, I, d, use_item_bias=True)           # same seed on every rank = DataParallel's replica
+        loader = TrainDataLoader(NegativeSampler(train_ds, 10), train_ds, batch_size=512, shuffle=True, device=dev)
+        conf = {'device': 'cuda', 'lr': 1e-2, 'wd': 1e-5, 'optimizer': 'adamw', 'n_epochs': 8, 'optimizing_metric': 'ndcg@10',
+                'max_patience': 3, 'model_path': os.path.join(out_dir, 'model'), 'seed': 3,
+                'running_settings': {'use_wandb': False, 'batch_verbose': False}}
+        tr = ShardedTrainer(model, loader, EvalLoader(val_ds, 512), RecBayesianPersonalizedRankingLoss(), conf)
+        assert tr._exchange_name() == 'peer_graph'
+        init = tr.val()['ndcg@10']
+        best = tr.fit()
+        assert best['ndcg@10'] > 1.5 * init and best['best_epoch'] >= 0, (init, best['ndcg@10'], best['best_epoch'])
+        # every rank reports the same dict
+        t = torch.tensor([best['ndcg@10']], dtype=torch.float64, device=dev)
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float(lo) == float(hi)
+        dist.barrier()
+        if rank == 0:
+            # the checkpoint is a reference-format state_dict: a fresh single-GPU model loads it and scores the same
+            single = SGDMatrixFactorization(U, I, d, use_item_bias=True)
+            single.load_model_from_path(conf['model_path'])
+            single.to(dev)
+            ref = evaluate_recommender_algorithm(single, EvalLoader(val_ds, 512),
+                                                 FullEvaluator(True, 2, val_ds.user_to_user_group), dev)
+            assert abs(ref['ndcg@10'] - best['ndcg@10']) <= 1e-9, (ref['ndcg@10'], best['ndcg@10'])
+            open(os.path.join(out_dir, 'ok'), 'w').write('ok')
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    finally:
+        if tr is not None:
+            tr.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [1, 2])
+def test_sharded_trainer_fit(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs >= {world} GPUs')
+    mp.spawn(_worker_trainer, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()
