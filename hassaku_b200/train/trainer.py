@@ -4,7 +4,9 @@ control flow, early stopping, best-model checkpointing and returned dict — wit
 hsk_mf_train_fused (gather + score + loss + gradient scatter in one pass) and hsk_adamw_dense.
 
 Differences from the reference, all deliberate:
-  * no nn.DataParallel wrap (trainer.py:38-40): one process per GPU; multi-GPU is hassaku_b200.sharded
+  * no nn.DataParallel wrap (trainer.py:38-40): one process per GPU; when torch.distributed is initialised with more than
+    one rank (torchrun), `Trainer(...)` returns a `ShardedTrainer` (hassaku_b200/train/sharded_trainer.py) unless
+    conf['multi_gpu'] == 'off'
   * the three `.item()` syncs per step (trainer.py:141-143) become one device-side fp64 accumulator read once per
     epoch; the reported `epoch_train_*` values are the same quantities
   * device 'cpu' is rejected loudly — there is no CPU path
@@ -49,6 +51,12 @@ class Trainer:
                 logging.info(f'{type(model).__name__} / {type(rec_loss).__name__} is outside the fused MF path: '
                              f'handing it to the reference Trainer')
                 return ref(model, train_loader, val_loader, rec_loss, conf)
+        if cls is Trainer and fused and (conf or {}).get('multi_gpu', 'auto') != 'off':
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # launched under torchrun with one rank per GPU: the sharded trainer is this path's nn.DataParallel
+                from hassaku_b200.train.sharded_trainer import ShardedTrainer
+                return ShardedTrainer(model, train_loader, val_loader, rec_loss, conf)
         return super().__new__(cls)
 
     def __init__(self, model: SGDMatrixFactorization, train_loader: data.DataLoader, val_loader: data.DataLoader,

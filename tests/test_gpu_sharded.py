@@ -245,6 +245,12 @@ def _worker_trainer(rank, world, port, out_dir):
                 'running_settings': {'use_wandb': False, 'batch_verbose': False}}
         tr = ShardedTrainer(model, loader, EvalLoader(val_ds, 512), RecBayesianPersonalizedRankingLoss(), conf)
         assert tr._exchange_name() == 'peer_graph'
+        if world > 1:      # under an initialised process group the reference-named Trainer IS the sharded one
+            from hassaku_b200.train.trainer import Trainer
+            t2 = Trainer(model, loader, EvalLoader(val_ds, 512), RecBayesianPersonalizedRankingLoss(), conf)
+            assert type(t2) is ShardedTrainer
+            t2.close()
+            assert type(Trainer(model, loader, EvalLoader(val_ds, 512), RecBayesianPersonalizedRankingLoss(), dict(conf, multi_gpu='off'))) is Trainer
         init = tr.val()['ndcg@10']
         best = tr.fit()
         assert best['ndcg@10'] > 1.5 * init and best['best_epoch'] >= 0, (init, best['ndcg@10'], best['best_epoch'])
