@@ -1062,8 +1062,15 @@ def _run_ours_sharded(args, wl, holder):
 
     shift = float(np.log(I / N)) if loss == 'sampled_softmax' else 0.0
     smf, full_sd = make_smf(U, I, d, None, 64, keep_full=True)
-    if exchange.startswith('peer') and not smf.peer_supported():
-        exchange = 'sparse_graph'           # rows longer than 128 floats / more than 8 ranks: the all-to-all exchange
+    exchange_fallback = None
+    if exchange.startswith('peer'):
+        if not smf.peer_supported():
+            exchange, exchange_fallback = 'sparse_graph', 'rows longer than 128 floats or more than 8 ranks'
+        else:
+            try:
+                smf._peer_setup()            # collective; raises on EVERY rank if any rank cannot export / map (CUDA IPC)
+            except Exception as ex:
+                exchange, exchange_fallback = 'sparse_graph', repr(ex)
     # ---- parity self-check (outside every timed region) ----
     parity = {'train': None, 'eval': None}
     try:
@@ -1214,7 +1221,7 @@ def _run_ours_sharded(args, wl, holder):
                                       if exchange.startswith('peer') else
                                       'per rank and step, own kernels inside the graph: route (5) + pack + local_index + mark_rows + fused + '
                                       'unpack_add + adamw_rows = 11, + 3 NCCL all-to-all kernels'),
-                'exchange': {'kind': exchange, 'capq_rows_per_owner': capq if exchange.startswith('sparse') else None,
+                'exchange': {'kind': exchange, 'fallback_from_peer': exchange_fallback, 'capq_rows_per_owner': capq if exchange.startswith('sparse') else None,
                              'bytes_per_gpu_per_direction': (int(2 * world * (capq + math.ceil(capq / 128)) * 128 * 4) if exchange.startswith('sparse')
                                                              else int(2 * B * (N + 2) * (d + 1) * 4 * (world - 1) / world) if exchange.startswith('peer')
                                                              else None),

@@ -358,9 +358,16 @@ class ShardedMF:
         if G > 1:
             import socket
             mine['host'] = socket.gethostname()
-            mine['exports'] = [_C.peer_export(t) for t in local]
+            try:
+                mine['exports'] = [_C.peer_export(t) for t in local]
+            except _C.HskError as ex:        # e.g. an allocator that cannot export (expandable segments): tell the peers
+                mine['error'] = str(ex)
             every = [None] * G
             dist.all_gather_object(every, mine, group=self.group)
+            errs = [f"rank {q}: {e['error']}" for q, e in enumerate(every) if 'error' in e]
+            if errs:
+                raise _C.HskError('the peer exchange is not available (CUDA IPC export failed: ' + '; '.join(errs) +
+                                  '): use the sparse / dense exchange')
             if len({e['host'] for e in every}) != 1:
                 raise _C.HskError('the peer exchange maps the other ranks\' memory (CUDA IPC over NVLink): all ranks must run on '
                                   'one node — use the sparse / dense exchange across nodes')
@@ -377,14 +384,29 @@ class ShardedMF:
             return opened[(q, handle)] + off
 
         has_ib = lay.off_Ib >= 0
-        V = [addr(q, 0) + 4 * every[q]['off_V'] for q in range(G)]
-        gV = [addr(q, 1) + 4 * every[q]['off_V'] for q in range(G)]
-        Ib = [addr(q, 0) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
-        gIb = [addr(q, 1) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
-        st = [addr(q, 2) for q in range(G)]
+        failure = None
+        try:
+            V = [addr(q, 0) + 4 * every[q]['off_V'] for q in range(G)]
+            gV = [addr(q, 1) + 4 * every[q]['off_V'] for q in range(G)]
+            Ib = [addr(q, 0) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
+            gIb = [addr(q, 1) + 4 * every[q]['off_Ib'] for q in range(G)] if has_ib else None
+            st = [addr(q, 2) for q in range(G)]
+            fl = [addr(q, 3) for q in range(G)]
+        except _C.HskError as ex:
+            failure = str(ex)
+        if G > 1:       # every rank learns whether EVERY rank could map its peers (same collectives on every path)
+            ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                for base in opened.values():
+                    _C.peer_close(base)
+                raise _C.HskError('the peer exchange is not available (mapping a peer\'s memory failed' +
+                                  (f': {failure}' if failure else ' on another rank') + '): use the sparse / dense exchange')
+        elif failure:
+            raise _C.HskError(failure)
         self._peer = {'items': _C.make_peer_items(V, gV, Ib, gIb, st), 'opened': opened,
                       'bar': torch.zeros(1, dtype=torch.float32, device=self.device),
-                      'flags': flags, 'flag_table': _C.make_peer_flags([addr(q, 3) for q in range(G)], r),
+                      'flags': flags, 'flag_table': _C.make_peer_flags(fl, r),
                       'epoch': torch.zeros(1, dtype=torch.int32, device=self.device)}
         if G > 1:
             torch.cuda.synchronize(self.device)

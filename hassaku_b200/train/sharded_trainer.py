@@ -99,6 +99,15 @@ class ShardedTrainer:
         self.val_dataset = val_loader.dataset
         self.eval_batch = int(getattr(val_loader, 'batch_size', 8192))
         self.best_value = self.best_metrics = self.best_epoch = None
+        # 'auto' takes the peer exchange only if every rank can map its peers' memory (collective check, once)
+        self._peer_ok = self.smf.peer_supported()
+        if self._peer_ok and self.exchange == 'auto':
+            try:
+                self.smf._peer_setup()
+            except _C.HskError as ex:
+                self._peer_ok = False
+                if self.rank == 0:
+                    logging.warning(f'peer exchange unavailable, using the all-to-all exchange: {ex}')
         if self.rank == 0:
             logging.info(f'Built ShardedTrainer: world={G}, global batch={self.local_batch * G} ({self.local_batch} per rank), '
                          f'steps per epoch={self.steps_per_epoch}, exchange={self._exchange_name()}')
@@ -111,7 +120,7 @@ class ShardedTrainer:
             if n_slots >= 2 * self.smf.spec.n_items // self.world:
                 ex = 'dense'               # the batch covers the item table (ShardedMF.step's rule)
             else:
-                ex = 'peer' if self.smf.peer_supported() else 'sparse'
+                ex = 'peer' if self._peer_ok else 'sparse'
         return ex + '_graph'
 
     def _train_one_epoch(self) -> dict:
