@@ -778,7 +778,10 @@ def bench_eval(args, dev, D, world, rank, smf_factory=None):
                      'frac': res.get('tflops_kernel', tf / world) / peaks['bf16_tflops'],
                      'sweep': {'achieved_per_gpu': tf / world, 'peak': peaks['bf16_tflops_sustained'], 'peak_kind': 'sustained bf16 (inside a long sweep)',
                                'frac': tf / world / peaks['bf16_tflops_sustained']},
-                     'algorithmic_flops_per_user': 2.0 * I * d, 'traffic': None, 'peak_source': peaks['source']},
+                     'algorithmic_flops_per_user': 2.0 * I * d,
+                     'traffic': (committed_traffic('cfg5', 'eval_topk_tc_kernel') or {}).get('bytes') if world == 1 else None,
+                     'traffic_note': 'DRAM bytes of one 18 944-user launch from the committed ncu capture (profiles/r02_traffic.json); the kernel is tensor-bound, the operands (0.5 GB of packed item rows) stream from L2 / HBM once per CTA pair',
+                     'peak_source': peaks['source']},
         'data_gen_s': gen_s,
     })
     return res
