@@ -75,6 +75,7 @@ def _declare(lib):
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_n': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_v': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, i32, vp]),
+        'hsk_topk_tag_means': (i32, [vp, i32, i32, vp, i64, i32, C.POINTER(C.c_int), i32, vp, vp, vp]),
         'hsk_peer_export': (i32, [vp, vp, C.POINTER(C.c_int64)]),
         'hsk_peer_open': (i32, [vp, C.POINTER(C.c_void_p)]),
         'hsk_peer_close': (i32, [vp]),
@@ -625,6 +626,20 @@ def topk_dense(logits, k: int, out_scores, out_ids):
     with _on_device_of(logits, out_scores, out_ids) as st:
         _check(lib().hsk_topk_dense(logits.data_ptr(), rows, cols, logits.stride(0), k, out_scores.data_ptr(),
                                     out_ids.data_ptr(), st), 'hsk_topk_dense')
+
+
+def topk_tag_means(top_ids, item_tag, ks, out=None, status=None):
+    """hsk_topk_tag_means: [B, len(ks), T] mean tag rows of the first k ranked items, for every k in ks."""
+    _req(top_ids, torch.int32, 'top_ids'); _req(item_tag, torch.float32, 'item_tag')
+    B, k_list = top_ids.shape
+    n_items, T = item_tag.shape
+    if out is None:
+        out = torch.empty((B, len(ks), T), dtype=torch.float32, device=top_ids.device)
+    arr = (C.c_int * len(ks))(*[int(k) for k in ks])
+    with _on_device_of(top_ids, item_tag, out, status) as st:
+        _check(lib().hsk_topk_tag_means(top_ids.data_ptr(), B, k_list, item_tag.data_ptr(), n_items, T, arr, len(ks), out.data_ptr(),
+                                        _ptr(status), st), 'hsk_topk_tag_means')
+    return out
 
 
 def _ks_array(ks):

@@ -250,9 +250,19 @@ class FullEvaluatorCalibrationDecorator(FullEvaluator):
                 self._cal_group = g.to(device=dev, dtype=torch.int64)
         u = u_idxs.to(dev, torch.int64)
         B, T = len(u), self.item_tag_mtx.shape[-1]
-        chunk = max(1, min(B, self._MAX_GATHER_BYTES // max(1, ks[0] * T * 4)))
         res = torch.empty((B, len(ks), 3), dtype=torch.float32, device=dev)
-        for s in range(0, B, chunk):
+        if dev.type == 'cuda':
+            # one pass over each user's ranked list (hsk_topk_tag_means) instead of the [B, k, T] gather
+            p = self.user_tag_mtx[u]
+            tag = self.item_tag_mtx if self.item_tag_mtx.dtype == torch.float32 else self.item_tag_mtx.float()
+            q_all = _C.topk_tag_means(top_ids[:, :ks[0]].to(torch.int32).contiguous(), tag.contiguous(), ks).to(p.dtype)
+            for t, k in enumerate(ks):
+                q = self.beta_smoothening * p + (1 - self.beta_smoothening) * q_all[:, t]      # eval.py:180-182
+                res[:, t, 0] = hellinger_distance(p, q)
+                res[:, t, 1] = jensen_shannon_distance(p, q)
+                res[:, t, 2] = kl_divergence(p, q)                                              # target first (eval.py:192)
+        chunk = max(1, min(B, self._MAX_GATHER_BYTES // max(1, ks[0] * T * 4)))
+        for s in range(0, B if dev.type != 'cuda' else 0, chunk):    # host tensors (stub evaluators in the CPU tests): torch ops
             p = self.user_tag_mtx[u[s:s + chunk]]                               # training distribution [b, T]
             rows = self.item_tag_mtx[top_ids[s:s + chunk, :ks[0]].long()]        # [b, k_max, T]
             for t, k in enumerate(ks):

@@ -144,6 +144,13 @@ HSK_API int hsk_shard_unpack_add(const float* in, int ld, int64_t n_local, const
                                  float* gIb /* nullable */, uint8_t* stamps /* nullable */, int64_t step,
                                  const int64_t* step_dev /* nullable: overrides step */, int32_t* status, hsk_stream_t stream);
 
+/* ---- f3: FullEvaluatorCalibrationDecorator's recommendation distributions (eval/eval.py:174-179) ------------------
+ * out[b, t, :] = (1 / ks[t]) * sum over j < ks[t] of item_tag[top_ids[b, j], :]   (top_ids int32 [B, k_list] ranked, -1 =
+ * padding, skipped; item_tag fp32 [n_items, T] row-major; ks host array of n_ks <= 8 values, each <= k_list; out fp32
+ * [B, n_ks, T]).  One pass over the ranked list per user instead of the reference's [B, k, T] gather. */
+HSK_API int hsk_topk_tag_means(const int32_t* top_ids, int B, int k_list, const float* item_tag, int64_t n_items, int T,
+                               const int* ks /* host */, int n_ks, float* out, int32_t* status, hsk_stream_t stream);
+
 /* ---- PEER exchange of the item-sharded step: one kernel over NVLink peer memory instead of route / pack / all-to-all /
  * unpack (SURVEY 8e's exchange, fused into the step kernel).  Every rank of a node maps the item side of every other
  * rank's tables into its address space (CUDA IPC), then hsk_mf_train_fused_peer gathers the item rows of ITS samples

@@ -249,3 +249,29 @@ def test_ring_kernel_equals_the_register_gather_kernel(U, I, d, B, N, kind, bias
     _C.mf_train_fused(lay.tables(arena), lay.tables(torch.zeros_like(arena)), u, i_bad, _C.LOSS_KINDS[kind], 0.0,
                       torch.zeros(1, dtype=torch.float64, device='cuda'), status=st)
     assert int(st.item()) & _C.STATUS_BAD_INDEX
+
+
+@pytest.mark.parametrize('T', [3, 20, 70])
+def test_topk_tag_means_matches_the_reference_gather(T):
+    """hsk_topk_tag_means = item_tag_mtx[top ids][:, :k].sum(1) / k of eval/eval.py:174-179 for every k at once (fp64 running
+    sums, one rounding), padding ids (-1) skipped."""
+    from hassaku_b200 import _C
+    torch.manual_seed(T)
+    B, I, kl = 257, 5000, 100
+    tag = torch.rand(I, T, device='cuda')
+    tag = tag / tag.sum(-1, keepdim=True)
+    ids = torch.stack([torch.randperm(I, device='cuda')[:kl] for _ in range(B)]).to(torch.int32)
+    ks = [100, 50, 10, 5]
+    got = _C.topk_tag_means(ids, tag, ks)
+    rows = tag.double()[ids.long()]
+    for t, k in enumerate(ks):
+        want = rows[:, :k].sum(1) / k
+        assert float((got[:, t].double() - want).abs().max()) < 1e-7
+    ids[3, 40:] = -1                                  # a short list: the divisor stays k (the reference has no short lists)
+    got = _C.topk_tag_means(ids, tag, ks)
+    want = rows[3, :40].sum(0) / 100
+    assert float((got[3, 0].double() - want).abs().max()) < 1e-7
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ids[5, 0] = I + 7
+    _C.topk_tag_means(ids, tag, ks, status=st)
+    assert int(st.item()) & _C.STATUS_BAD_INDEX
