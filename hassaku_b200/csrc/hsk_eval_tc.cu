@@ -201,14 +201,10 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float v[32], g[8];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                    if (ncols - c < 32) {            // ragged last tile: columns beyond the table become NaN (never a candidate)
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = (e < ncols - c) ? v[e] : __int_as_float(0x7fc00000);
-                    }
                     const float mx = tc_chunk_max(v, g);
                     if (row_ok && mx >= tau)
                         tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
-                                       region, ex);
+                                       region, ex, ncols - c);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);

@@ -171,8 +171,11 @@ __device__ __forceinline__ float tc_chunk_max(const float (&v)[32], float (&g)[8
 //   this version: an 8-bit mask of the groups whose maximum reaches the threshold (8 compares), then per set bit the group's
 //   4 values pulled out of the register array by a 3-level select tree (28 selects, no local memory)   10.7 ms
 // — every taken branch in this divergent path costs an instruction-fetch bubble, selects do not.
+// `nvalid`: columns of the chunk that exist (32 except in the table's ragged last tile, whose missing rows TMA fills with
+// zeros: their scores are never candidates).  The bound is applied HERE, at the append, so that the hot path reads the
+// accumulator registers in place (patching the chunk's values instead cost 32 register moves per chunk).
 __device__ __forceinline__ void tc_scan_groups(const float (&v)[32], const float (&g)[8], float tau, uint64_t taukey, uint32_t gid0,
-                                               uint32_t id_stride, int& cnt, uint64_t* region, ExCursor& ex) {
+                                               uint32_t id_stride, int& cnt, uint64_t* region, ExCursor& ex, int nvalid) {
     uint32_t gm = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) gm |= (g[j] >= tau) ? (1u << j) : 0u;
@@ -188,14 +191,14 @@ __device__ __forceinline__ void tc_scan_groups(const float (&v)[32], const float
         for (int i = 0; i < 4; ++i) a4[i] = (j & 1) ? a8[4 + i] : a8[i];
         uint32_t em = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) em |= (a4[q] >= tau) ? (1u << q) : 0u;     // NaN (a column beyond the table) never passes
+        for (int q = 0; q < 4; ++q) em |= (a4[q] >= tau) ? (1u << q) : 0u;
         while (em) {
             const int q = __ffs(em) - 1;
             em &= em - 1;
             const float x = (q & 2) ? ((q & 1) ? a4[3] : a4[2]) : ((q & 1) ? a4[1] : a4[0]);
             const uint32_t gid = gid0 + (uint32_t)(4 * j + q) * id_stride;
             const uint64_t key = make_key(x, gid);
-            if (key > taukey && !ex_excluded(ex, gid)) region[cnt++] = key;
+            if (key > taukey && 4 * j + q < nvalid && !ex_excluded(ex, gid)) region[cnt++] = key;
         }
     }
 }

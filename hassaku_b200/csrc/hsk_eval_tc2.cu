@@ -268,10 +268,6 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     float v[32], g[8];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                    if (ncols - c < 32) {            // ragged last tile: columns beyond the table become NaN (never a candidate)
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = (e < ncols - c) ? v[e] : __int_as_float(0x7fc00000);
-                    }
                     const float mx = tc_chunk_max(v, g);
 #ifdef HSK_MEASURE_NOSCAN   // measurement builds only (never the shipped library): the epilogue without its candidate scan
                            // after the first 4 tiles -> 6.39 ms = 1 517 TFLOP/s at 18 944 x 1 M x 256 (shipped: 9.95 ms)
@@ -280,7 +276,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (row_ok && mx >= tau)
 #endif
                         tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
-                                       region, ex);
+                                       region, ex, ncols - c);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);
