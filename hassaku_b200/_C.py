@@ -75,6 +75,9 @@ def _declare(lib):
         'hsk_mf_train_fused': (i32, [T, T, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_n': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, vp]),
         'hsk_mf_train_fused_v': (i32, [T, T, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp, i32, vp]),
+        'hsk_eval_topk_tc_shards_scratch_bytes': (i64, [i32, vp, i32, i32]),
+        'hsk_eval_topk_tc_shards': (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+        'hsk_rescore_topk_shards': (i32, [T, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]),
         'hsk_topk_tag_means': (i32, [vp, i32, i32, vp, i64, i32, C.POINTER(C.c_int), i32, vp, vp, vp]),
         'hsk_peer_export': (i32, [vp, vp, C.POINTER(C.c_int64)]),
         'hsk_peer_open': (i32, [vp, C.POINTER(C.c_void_p)]),
@@ -564,6 +567,47 @@ def eval_topk_tc(Uq, Vq, precision: int, u_idx, n_users: int, k: int, top_scores
                                         _ptr(excl_indptr), _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(),
                                         scratch.data_ptr(), scratch.numel() * scratch.element_size(), _ptr(status),
                                         EVAL_TC_VARIANTS[variant or EVAL_TC_VARIANT], st), 'hsk_eval_topk_tc')
+
+
+class ItemShards:
+    """The item tables of every rank of a node as seen from THIS process (device addresses): packed tensor-core operands
+    `Vq` [rows_q, kpad], fp32 rows `V` [rows_q, ld], item bias `Ib` [rows_q] (None: no bias), rank order.  Item id =
+    q + n_shards * row."""
+
+    def __init__(self, rows, Vq=None, V=None, Ib=None):
+        self.n = len(rows)
+        if not 1 <= self.n <= MAX_PEERS:
+            raise ValueError(f'1..{MAX_PEERS} item shards, got {self.n}')
+        self.rows = (C.c_int64 * self.n)(*[int(r) for r in rows])
+        arr = lambda ptrs: (C.c_void_p * self.n)(*[int(p) for p in ptrs]) if ptrs is not None else None
+        self.Vq, self.V, self.Ib = arr(Vq), arr(V), arr(Ib)
+
+
+def eval_topk_tc_shards_scratch_bytes(Be: int, shards: ItemShards, k: int) -> int:
+    return int(lib().hsk_eval_topk_tc_shards_scratch_bytes(Be, shards.rows, shards.n, k))
+
+
+def eval_topk_tc_shards(Uq, shards: ItemShards, precision: int, u_idx, n_users: int, k: int, top_scores, top_ids, scratch, Ub=None,
+                        Gb=None, excl_indptr=None, excl_indices=None, status=None, u_rows=None):
+    """hsk_eval_topk_tc_shards: tcgen05 scoring of the batch against ALL item shards (peer-mapped packed tables)."""
+    _req(u_idx, torch.int64, 'u_idx'); _req(top_scores, torch.float32, 'top_scores'); _req(top_ids, torch.int32, 'top_ids')
+    with _on_device_of(Uq, u_idx, top_scores, top_ids, scratch, Ub, Gb, excl_indptr, excl_indices, status, u_rows) as st:
+        _check(lib().hsk_eval_topk_tc_shards(Uq.data_ptr(), shards.Vq, shards.rows, shards.Ib, shards.n, Uq.shape[1], precision,
+                                             _ptr(Ub), _ptr(Gb), u_idx.data_ptr(), _ptr(u_rows), u_idx.numel(), n_users,
+                                             _ptr(excl_indptr), _ptr(excl_indices), k, top_scores.data_ptr(), top_ids.data_ptr(),
+                                             scratch.data_ptr(), scratch.numel() * scratch.element_size(), _ptr(status), st),
+               'hsk_eval_topk_tc_shards')
+
+
+def rescore_topk_shards(tables: MfTables, shards: ItemShards, u_rows, cand_ids, k: int, top_scores, top_ids, status=None,
+                        cand_scores=None):
+    """hsk_rescore_topk_shards: fp32 re-scoring with the item rows read from the (peer-mapped) shards."""
+    _req(u_rows, torch.int64, 'u_rows'); _req(cand_ids, torch.int32, 'cand_ids')
+    Be, n_cand = cand_ids.shape
+    with _on_device_of(u_rows, cand_ids, top_scores, top_ids, status, cand_scores) as st:
+        _check(lib().hsk_rescore_topk_shards(C.byref(tables), shards.V, shards.rows, shards.Ib, shards.n, u_rows.data_ptr(), Be,
+                                             cand_ids.data_ptr(), _ptr(cand_scores), n_cand, k, top_scores.data_ptr(),
+                                             top_ids.data_ptr(), _ptr(status), st), 'hsk_rescore_topk_shards')
 
 
 def rescore_topk(tables: MfTables, u_rows, cand_ids, k: int, top_scores, top_ids, id_offset: int = 0, id_stride: int = 1,

@@ -353,10 +353,9 @@ static int make_map(CUtensorMap* map, const void* base, bool tf32, int kpad, int
 }
 
 // `bn` = items per tile: TC_BN (one-CTA kernel) or 2 * TC_BN (CTA-pair kernel, whose row tiles come in pairs)
-static void tc_plan(int Be, int64_t n_local, int bn, int* n_tiles, int* tiles_per_split, int* n_splits) {
+static void tc_plan_tiles(int Be, int nt, bool pair, int* n_tiles, int* tiles_per_split, int* n_splits) {
     int row_tiles = (Be + TC_BM - 1) / TC_BM;
-    if (bn > TC_BN) row_tiles = (row_tiles + 1) / 2 * 2;
-    const int nt = (int)((n_local + bn - 1) / bn);
+    if (pair) row_tiles = (row_tiles + 1) / 2 * 2;
     const int want = sm_count();
     int splits = 1;
     if (row_tiles * 4 < want * 3) splits = (want + row_tiles - 1) / row_tiles;   // >= 75 % of the SMs busy: no split
@@ -368,10 +367,13 @@ static void tc_plan(int Be, int64_t n_local, int bn, int* n_tiles, int* tiles_pe
     *tiles_per_split = tps;
     *n_splits = (nt + tps - 1) / tps;
 }
+static void tc_plan(int Be, int64_t n_local, int bn, int* n_tiles, int* tiles_per_split, int* n_splits) {
+    tc_plan_tiles(Be, (int)((n_local + bn - 1) / bn), bn > TC_BN, n_tiles, tiles_per_split, n_splits);
+}
 
 // hsk_eval_tc2.cu
 int launch_eval_tc2(bool tf32, int row_tiles, int n_splits, size_t smem, cudaStream_t s, const CUtensorMap& tmA,
-                    const CUtensorMap& tmB, const EvalTcArgs& a);
+                    const EvalTcMaps& tmB, const EvalTcArgs& a);
 
 }  // namespace hsk
 
@@ -417,14 +419,16 @@ extern "C" int hsk_eval_topk_tc(const void* Uq, const void* Vq, int kpad, int pr
                               stream);
 }
 
-extern "C" int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
-                                  const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
-                                  int64_t n_local, int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr,
-                                  const int32_t* excl_indices, int k, float* top_scores, int32_t* top_ids, void* scratch,
-                                  int64_t scratch_bytes, int32_t* status, int variant, hsk_stream_t stream) {
+// One launch over `n_shards` packed item tables (1: the plain entry points; > 1: hsk_eval_topk_tc_shards, pair kernel only).
+static int eval_tc_launch(const void* Uq, int n_shards, const void* const* Vq, const int64_t* rows, const float* const* Ib, int kpad,
+                          int precision, const float* Ub, const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be,
+                          int64_t n_users, int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr,
+                          const int32_t* excl_indices, int k, float* top_scores, int32_t* top_ids, void* scratch,
+                          int64_t scratch_bytes, int32_t* status, int variant, hsk_stream_t stream) {
     HSK_REQUIRE(variant >= HSK_EVAL_TC_AUTO && variant <= HSK_EVAL_TC_PAIR, "hsk_eval_topk_tc_v: unknown kernel variant %d", variant);
     const bool pair = variant != HSK_EVAL_TC_SINGLE;
-    HSK_REQUIRE(Uq && Vq && u_idx && top_scores && top_ids, "hsk_eval_topk_tc: null pointer");
+    HSK_REQUIRE(n_shards >= 1 && n_shards <= kMaxItemShards && (pair || n_shards == 1), "hsk_eval_topk_tc: 1..%d item shards (pair kernel)", kMaxItemShards);
+    HSK_REQUIRE(Uq && Vq && rows && Ib && u_idx && top_scores && top_ids, "hsk_eval_topk_tc: null pointer");
     HSK_REQUIRE(precision == HSK_PREC_TF32 || precision == HSK_PREC_BF16, "hsk_eval_topk_tc: precision must be TF32 or BF16");
     const bool tf32 = precision == HSK_PREC_TF32;
     const int per_kb = tf32 ? 32 : 64;
@@ -432,26 +436,43 @@ extern "C" int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int 
     const int num_kb = kpad / per_kb;
     if (num_kb > TC_MAX_KB)
         return set_err(HSK_ERR_UNSUPPORTED, "hsk_eval_topk_tc: embedding_dim too large for the tensor-core mode (kpad=%d)", kpad);
-    HSK_REQUIRE((reinterpret_cast<uintptr_t>(Uq) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vq) & 15) == 0, "hsk_eval_topk_tc: operands must be 16-byte aligned");
-    HSK_REQUIRE(k >= 1 && k <= kMaxK && Be >= 0 && n_local >= 1, "hsk_eval_topk_tc: bad sizes");
-    HSK_REQUIRE(id_stride >= 1 && id_offset >= 0 && id_offset + (n_local - 1) * id_stride < 0x7FFFFFFFll, "hsk_eval_topk_tc: bad id mapping");
+    HSK_REQUIRE((reinterpret_cast<uintptr_t>(Uq) & 15) == 0, "hsk_eval_topk_tc: operands must be 16-byte aligned");
+    HSK_REQUIRE(k >= 1 && k <= kMaxK && Be >= 0, "hsk_eval_topk_tc: bad sizes");
     HSK_REQUIRE((excl_indptr == nullptr) == (excl_indices == nullptr), "hsk_eval_topk_tc: exclusion CSR needs both arrays");
-    if (Be == 0) return HSK_OK;
+    const int bn = pair ? 2 * TC_BN : TC_BN;
+    int64_t max_rows = 0;
+    int nt = 0;
     EvalTcArgs a;
     memset(&a, 0, sizeof(a));
-    a.Ub = Ub; a.Ib = Ib; a.Gb = Gb; a.u_idx = u_idx; a.u_rows = u_rows; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
-    a.n_users = n_users; a.n_local = n_local; a.id_offset = id_offset; a.id_stride = id_stride;
+    for (int q = 0; q < n_shards; ++q) {
+        HSK_REQUIRE(Vq[q] && (reinterpret_cast<uintptr_t>(Vq[q]) & 15) == 0 && rows[q] >= 1, "hsk_eval_topk_tc: item table %d missing, misaligned or empty", q);
+        nt += (int)((rows[q] + bn - 1) / bn);
+        a.shard_tile_end[q] = nt;
+        a.shard_rows[q] = rows[q];
+        a.shard_Ib[q] = Ib[q];
+        if (rows[q] > max_rows) max_rows = rows[q];
+    }
+    HSK_REQUIRE(id_stride >= 1 && id_offset >= 0 && id_offset + ((n_shards - 1) + (int64_t)n_shards * (max_rows - 1)) * id_stride < 0x7FFFFFFFll,
+                "hsk_eval_topk_tc: bad id mapping");
+    if (Be == 0) return HSK_OK;
+    a.n_shards = n_shards;
+    a.Ub = Ub; a.Ib = Ib[0]; a.Gb = Gb; a.u_idx = u_idx; a.u_rows = u_rows; a.excl_indptr = excl_indptr; a.excl_indices = excl_indices;
+    a.n_users = n_users; a.n_local = rows[0]; a.id_offset = id_offset; a.id_stride = id_stride;
     a.Be = Be; a.k = k; a.num_kb = num_kb; a.kelems_per_kb = per_kb;
-    tc_plan(Be, n_local, pair ? 2 * TC_BN : TC_BN, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
+    tc_plan_tiles(Be, nt, pair, &a.n_tiles, &a.tiles_per_split, &a.n_splits);
     const int64_t need = (int64_t)a.n_splits * Be * TC_CAP * (int64_t)sizeof(uint64_t);
     HSK_REQUIRE(scratch && scratch_bytes >= need, "hsk_eval_topk_tc: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
     a.cand = reinterpret_cast<uint64_t*>(scratch);
     a.out_scores = top_scores; a.out_ids = top_ids; a.status = status;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA;
+    EvalTcMaps tmB;
+    memset(&tmB, 0, sizeof(tmB));
     int rc = make_map(&tmA, Uq, tf32, kpad, Be, per_kb);
     if (rc) return rc;
-    rc = make_map(&tmB, Vq, tf32, kpad, n_local, per_kb);
-    if (rc) return rc;
+    for (int q = 0; q < n_shards; ++q) {
+        rc = make_map(&tmB.m[q], Vq[q], tf32, kpad, rows[q], per_kb);
+        if (rc) return rc;
+    }
     int n_stages = (200 * 1024 - num_kb * TC_TILE_BYTES) / TC_TILE_BYTES;   // ~200 KB of the 227 KB for operands
     if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
     if (n_stages < 2) n_stages = 2;
@@ -466,14 +487,45 @@ extern "C" int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int 
         e = cudaSuccess;
     } else if (tf32) {
         e = cudaFuncSetAttribute(eval_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+        if (e == cudaSuccess) eval_topk_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmA, tmB.m[0], a);
     } else {
         e = cudaFuncSetAttribute(eval_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) eval_topk_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a);
+        if (e == cudaSuccess) eval_topk_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB.m[0], a);
     }
     if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc: smem attribute: %s", cudaGetErrorString(e));
     rc = check_launch("hsk_eval_topk_tc");
     if (rc) return rc;
     if (a.n_splits > 1) rc = launch_merge_keys(a.cand, a.n_splits, Be, TC_CAP, k, top_scores, top_ids, s, Ub, Gb, u_rows ? u_rows : u_idx, u_rows ? (int64_t)1 << 62 : n_users);
     return rc;
+}
+
+extern "C" int hsk_eval_topk_tc_v(const void* Uq, const void* Vq, int kpad, int precision, const float* Ub, const float* Ib,
+                                  const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
+                                  int64_t n_local, int64_t id_offset, int64_t id_stride, const int64_t* excl_indptr,
+                                  const int32_t* excl_indices, int k, float* top_scores, int32_t* top_ids, void* scratch,
+                                  int64_t scratch_bytes, int32_t* status, int variant, hsk_stream_t stream) {
+    HSK_REQUIRE(Vq && n_local >= 1, "hsk_eval_topk_tc: null pointer / empty item table");
+    return eval_tc_launch(Uq, 1, &Vq, &n_local, &Ib, kpad, precision, Ub, Gb, u_idx, u_rows, Be, n_users, id_offset, id_stride,
+                          excl_indptr, excl_indices, k, top_scores, top_ids, scratch, scratch_bytes, status, variant, stream);
+}
+
+extern "C" int64_t hsk_eval_topk_tc_shards_scratch_bytes(int Be, const int64_t* shard_rows, int n_shards, int k) {
+    (void)k;
+    if (!shard_rows || n_shards < 1) return 0;
+    int nt = 0;
+    for (int q = 0; q < n_shards; ++q) nt += (int)((shard_rows[q] + 2 * TC_BN - 1) / (2 * TC_BN));
+    int n_tiles, tps, ns;
+    tc_plan_tiles(Be > 0 ? Be : 1, nt > 0 ? nt : 1, true, &n_tiles, &tps, &ns);
+    return (int64_t)ns * (Be > 0 ? Be : 1) * TC_CAP * (int64_t)sizeof(uint64_t);
+}
+
+extern "C" int hsk_eval_topk_tc_shards(const void* Uq, const void* const* Vq_shards, const int64_t* shard_rows,
+                                       const float* const* Ib_shards, int n_shards, int kpad, int precision, const float* Ub,
+                                       const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
+                                       const int64_t* excl_indptr, const int32_t* excl_indices, int k, float* top_scores,
+                                       int32_t* top_ids, void* scratch, int64_t scratch_bytes, int32_t* status, hsk_stream_t stream) {
+    const float* no_bias[kMaxItemShards] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return eval_tc_launch(Uq, n_shards, Vq_shards, shard_rows, Ib_shards ? Ib_shards : no_bias, kpad, precision, Ub, Gb, u_idx, u_rows, Be,
+                          n_users, 0, 1, excl_indptr, excl_indices, k, top_scores, top_ids, scratch, scratch_bytes, status,
+                          HSK_EVAL_TC_PAIR, stream);
 }

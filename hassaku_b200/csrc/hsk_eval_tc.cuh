@@ -20,6 +20,7 @@ constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;   // TMA warp + MMA warp + 8 
 constexpr int TC_ACC_STAGES = 4;           // accumulator stages in TMEM: 4 x 128 fp32 columns = all 512 columns
 constexpr int TC_KPL = 16;                 // candidate keys per lane in the epilogue lists
 constexpr int TC_CAP = 32 * TC_KPL;        // 512-entry lists: a cut every ~(512 - 128 - k) appends instead of ~28
+constexpr int kMaxItemShards = 8;  // = HSK_MAX_PEERS
 constexpr int TC_MAX_KB = 8;      // kpad * elem_size <= 1024 bytes -> d <= 512 (bf16) / 256 (tf32)
 
 struct EvalTcArgs {
@@ -37,6 +38,15 @@ struct EvalTcArgs {
     float* out_scores;
     int32_t* out_ids;
     int32_t* status;
+    // item SHARDS behind one launch of the CTA-pair kernel (hsk_eval_topk_tc_shards; 1 = one table): shard q holds the items
+    // q + n_shards * row, its rows are tiles [shard_tile_end[q - 1], shard_tile_end[q]) of the launch, walked shard by shard
+    int n_shards;
+    int shard_tile_end[kMaxItemShards];
+    int64_t shard_rows[kMaxItemShards];
+    const float* shard_Ib[kMaxItemShards];
+};
+struct EvalTcMaps {                 // the shards' packed tables (one TMA descriptor each)
+    CUtensorMap m[kMaxItemShards];
 };
 
 // ---- PTX wrappers ----

@@ -91,7 +91,7 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t adesc, uin
 }
 template <bool TF32, int NCG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2Cfg<NCG>::THREADS, 1)
-eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EvalTcArgs a) {
+eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ EvalTcMaps tmBs, EvalTcArgs a) {
     using Cfg = T2Cfg<NCG>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_a, bar_tfull[T2_ACC_STAGES], bar_tempty[T2_ACC_STAGES];
@@ -160,17 +160,20 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===== TMA producer (both CTAs) =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA));
-            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB));
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmBs.m[0]));
             if (leader) mbar_expect_tx(&bar_a, 2u * (uint32_t)a.num_kb * TC_TILE_BYTES);
             for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d_pair(smA + (size_t)kb * TC_TILE_BYTES, &tmA, kb * a.kelems_per_kb, m0, &bar_a);
             int s = 0;
             uint32_t ph = 0;
+            int q = 0;
             for (int t = 0; t < n_my_tiles; ++t) {
-                const int n0 = (t_begin + t) * T2_BN + (int)cta * TC_BN;      // this CTA's half of the tile
+                while (q + 1 < a.n_shards && t_begin + t >= a.shard_tile_end[q]) ++q;       // the shard this tile belongs to
+                const int lt = t_begin + t - (q ? a.shard_tile_end[q - 1] : 0);
+                const int n0 = lt * T2_BN + (int)cta * TC_BN;      // this CTA's half of the tile (rows of shard q)
                 for (int kb = 0; kb < a.num_kb; ++kb) {
                     mbar_wait(&bar_empty[s], ph ^ 1u);
                     if (leader) mbar_expect_tx(&bar_full[s], 2u * TC_TILE_BYTES);
-                    tma_load_2d_pair(smB + (size_t)s * TC_TILE_BYTES, &tmB, kb * a.kelems_per_kb, n0, &bar_full[s]);
+                    tma_load_2d_pair(smB + (size_t)s * TC_TILE_BYTES, &tmBs.m[q], kb * a.kelems_per_kb, n0, &bar_full[s]);
                     if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -221,11 +224,23 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr int STG = T2_BN / Cfg::GROUP;   // bias values a thread stages per tile
         ExCursor ex;
         ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
-        // bias value of column `col` of tile `tt` (0 beyond the table / without item bias)
-        auto ib_at = [&](int tt, int col) -> float {
-            const int64_t n = (int64_t)(t_begin + tt) * T2_BN + col;
-            return (a.Ib && tt < n_my_tiles && n < a.n_local) ? __ldg(a.Ib + n) : 0.f;
+        // tile `tt` of this CTA -> its shard and the first row of the tile inside the shard
+        auto shard_of = [&](int tt, int& q, int64_t& n0) {
+            const int gt = t_begin + tt;
+            q = 0;
+            while (q + 1 < a.n_shards && gt >= a.shard_tile_end[q]) ++q;
+            n0 = (int64_t)(gt - (q ? a.shard_tile_end[q - 1] : 0)) * T2_BN;
         };
+        // bias value of column `col` of tile `tt` (0 beyond the shard / without item bias)
+        auto ib_at = [&](int tt, int col) -> float {
+            if (tt >= n_my_tiles) return 0.f;
+            int q;
+            int64_t n0;
+            shard_of(tt, q, n0);
+            const float* ibq = a.shard_Ib[q];
+            return (ibq && n0 + col < a.shard_rows[q]) ? __ldg(ibq + n0 + col) : 0.f;
+        };
+        int cur_q = 0;
 
         // prologue: bias rows of the first two tiles into the stages (through the group's staging tile), stages to the MMA warp
         for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
@@ -245,8 +260,17 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int next_cut = 2;          // tiles after which every row is cut: 2, 3, 4, 6, 9, 13, ... (ratio HSK_T2_SCHED_NUM / DEN)
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
-            const int64_t n0 = (int64_t)(t_begin + t) * T2_BN;
-            const int ncols = (int)min((int64_t)T2_BN, a.n_local - n0);
+            int q;
+            int64_t n0;
+            shard_of(t, q, n0);
+            if (q != cur_q) {      // the next shard's item ids start low again: rewind the exclusion cursor
+                cur_q = q;
+                ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
+            }
+            const int ncols = (int)min((int64_t)T2_BN, a.shard_rows[q] - n0);
+            // item id of (shard q, row n) = id_offset + (q + n_shards * n) * id_stride
+            const uint32_t id_step = (uint32_t)(a.n_shards * a.id_stride);
+            const uint32_t id_base = (uint32_t)(a.id_offset + ((int64_t)q + a.n_shards * n0) * a.id_stride);
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
             // the bias values the NEXT iteration writes (tile t + 3): in flight during this tile
@@ -275,8 +299,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #else
                     if (row_ok && mx >= tau)
 #endif
-                        tc_scan_groups(v, g, tau, taukey, (uint32_t)(a.id_offset + (n0 + c) * a.id_stride), (uint32_t)a.id_stride, cnt,
-                                       region, ex, ncols - c);
+                        tc_scan_groups(v, g, tau, taukey, id_base + (uint32_t)c * id_step, id_step, cnt, region, ex, ncols - c);
                 };
                 chunk(raw0, 0);
                 chunk(raw1, 1);
@@ -392,7 +415,7 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <bool TF32, int NCG>
-static int launch_tc2(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const EvalTcArgs& a) {
+static int launch_tc2(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const EvalTcMaps& tmB, const EvalTcArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(eval_topk_tc2_kernel<TF32, NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err(HSK_ERR_CUDA, "hsk_eval_topk_tc(pair): smem attribute: %s", cudaGetErrorString(e));
     eval_topk_tc2_kernel<TF32, NCG><<<grid, T2Cfg<NCG>::THREADS, smem, s>>>(tmA, tmB, a);
@@ -404,7 +427,7 @@ static int launch_tc2(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap&
 // four list regions per row) was measured at 10.69 ms against 9.96 ms for NCG = 2 (18 944 x 1 M x 256, bf16) — the
 // epilogue is not bound by a single warp's instruction latency but by the candidate scan itself (see HSK_MEASURE_NOSCAN).
 int launch_eval_tc2(bool tf32, int row_tiles, int n_splits, size_t smem, cudaStream_t s, const CUtensorMap& tmA,
-                    const CUtensorMap& tmB, const EvalTcArgs& a) {
+                    const EvalTcMaps& tmB, const EvalTcArgs& a) {
     dim3 grid((unsigned)((row_tiles + 1) / 2 * 2), (unsigned)n_splits);
     return tf32 ? launch_tc2<true, 2>(grid, smem, s, tmA, tmB, a) : launch_tc2<false, 2>(grid, smem, s, tmA, tmB, a);
 }

@@ -30,6 +30,12 @@ struct RescoreArgs {
     float* out_scores;
     int32_t* out_ids;
     int32_t* status;
+    // item tables sharded over the ranks of a node and mapped here (hsk_rescore_topk_shards): item id = q + n_shards * row of
+    // shard q; n_shards <= 1: the one table Vw / Ib with the id_offset / id_stride mapping
+    int n_shards;
+    const float* shard_V[HSK_MAX_PEERS];
+    const float* shard_Ib[HSK_MAX_PEERS];
+    int64_t shard_rows[HSK_MAX_PEERS];
 };
 
 // POSITIONAL (item-sharded evaluation): no selection — out_scores[row, c] = the fp32 score of candidate c if THIS shard owns
@@ -57,6 +63,7 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
     // lane l looks up candidate r * 32 + l: id -> local row (id = id_offset + local * id_stride)
     int64_t loc[kRescoreKPL];
     int32_t gid[kRescoreKPL];
+    int own[kRescoreKPL];
     bool masked[kRescoreKPL];
 #pragma unroll
     for (int r = 0; r < kRescoreKPL; ++r) {
@@ -66,7 +73,18 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
         // low-precision pass reports it with score -inf, and -inf it stays (eval/eval.py:250-251)
         masked[r] = a.cand_scores && c < a.n_cand && a.cand_scores[(int64_t)row * a.n_cand + c] == -INFINITY;
         loc[r] = -1;
-        if (gid[r] >= 0) {
+        own[r] = 0;
+        if (gid[r] >= 0 && a.n_shards > 1) {
+            const int q = gid[r] % a.n_shards;
+            const int64_t l = gid[r] / a.n_shards;
+            if (l >= a.shard_rows[q]) {
+                if (a.status) atomicOr(a.status, HSK_STATUS_BAD_INDEX);
+                gid[r] = -1;
+            } else {
+                loc[r] = l;
+                own[r] = q;
+            }
+        } else if (gid[r] >= 0) {
             const int64_t rel = (int64_t)gid[r] - a.id_offset;
             const int64_t l = rel / a.id_stride;
             if (rel < 0 || l * a.id_stride != rel || l >= a.n_local) {
@@ -88,7 +106,9 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 l[q] = __shfl_sync(kFull, loc[r], j0 + q);
-                if (l[q] >= 0) vr[q].load(a.Vw + l[q] * a.ld, a.nvec, lane); else vr[q].zero();
+                const int oq = __shfl_sync(kFull, own[r], j0 + q);
+                const float* vb = a.n_shards > 1 ? a.shard_V[oq] : a.Vw;
+                if (l[q] >= 0) vr[q].load(vb + l[q] * a.ld, a.nvec, lane); else vr[q].zero();
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -97,7 +117,8 @@ __global__ void __launch_bounds__(256) rescore_topk_kernel(RescoreArgs a) {
             }
         }
         if (loc[r] >= 0) {
-            if (a.Ib) sc += __ldg(a.Ib + loc[r]);
+            const float* ibq = a.n_shards > 1 ? a.shard_Ib[own[r]] : a.Ib;
+            if (ibq) sc += __ldg(ibq + loc[r]);
             key[r] = make_key(masked[r] ? -INFINITY : sc, (uint32_t)gid[r]);
         }
         if (POSITIONAL) {
@@ -143,6 +164,38 @@ extern "C" int hsk_rescore_topk(const hsk_mf_tables* t, const int64_t* u_rows, i
     cudaStream_t s = as_stream(stream);
     HSK_DISPATCH_NV(nv, (rescore_topk_kernel<NV, false><<<blocks, 256, 0, s>>>(a)));
     return check_launch("hsk_rescore_topk");
+}
+
+extern "C" int hsk_rescore_topk_shards(const hsk_mf_tables* t, const float* const* V_shards, const int64_t* shard_rows,
+                                       const float* const* Ib_shards, int n_shards, const int64_t* u_rows, int Be,
+                                       const int32_t* cand_ids, const float* cand_scores, int n_cand, int k, float* top_scores,
+                                       int32_t* top_ids, int32_t* status, hsk_stream_t stream) {
+    HSK_REQUIRE(t && t->Uw && V_shards && shard_rows && u_rows && cand_ids && top_scores && top_ids, "hsk_rescore_topk_shards: null pointer");
+    HSK_REQUIRE(n_shards >= 1 && n_shards <= HSK_MAX_PEERS, "hsk_rescore_topk_shards: 1..%d shards", HSK_MAX_PEERS);
+    HSK_REQUIRE(t->d >= 1 && t->ld >= t->d && t->ld % 4 == 0 && t->ld <= 1024 && aligned16(t->Uw), "hsk_rescore_topk_shards: bad table shape");
+    HSK_REQUIRE(n_cand >= 1 && n_cand <= kRescoreMax && k >= 1 && k <= n_cand && Be >= 0, "hsk_rescore_topk_shards: need 1 <= k <= n_cand <= %d", kRescoreMax);
+    if (Be == 0) return HSK_OK;
+    RescoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Uw = t->Uw; a.Ub = t->Ub; a.Gb = t->Gb;
+    a.u_idx = u_rows; a.cand = cand_ids; a.cand_scores = cand_scores;
+    a.n_users = t->n_users; a.id_offset = 0; a.id_stride = 1;
+    a.Be = Be; a.n_cand = n_cand; a.k = k; a.ld = t->ld; a.nvec = t->ld / 4;
+    a.out_scores = top_scores; a.out_ids = top_ids; a.status = status;
+    // the kernel's shard path is taken for n_shards > 1; one shard = the plain mapping on that table
+    a.n_shards = n_shards;
+    for (int q = 0; q < n_shards; ++q) {
+        HSK_REQUIRE(V_shards[q] && aligned16(V_shards[q]) && shard_rows[q] >= 1, "hsk_rescore_topk_shards: table of shard %d missing, misaligned or empty", q);
+        a.shard_V[q] = V_shards[q];
+        a.shard_Ib[q] = Ib_shards ? Ib_shards[q] : nullptr;
+        a.shard_rows[q] = shard_rows[q];
+    }
+    a.Vw = V_shards[0]; a.Ib = Ib_shards ? Ib_shards[0] : nullptr; a.n_local = shard_rows[0];
+    const int nv = (a.nvec + 31) / 32;
+    const int blocks = (Be + 7) / 8;
+    cudaStream_t s = as_stream(stream);
+    HSK_DISPATCH_NV(nv, (rescore_topk_kernel<NV, false><<<blocks, 256, 0, s>>>(a)));
+    return check_launch("hsk_rescore_topk_shards");
 }
 
 extern "C" int hsk_rescore_scores(const hsk_mf_tables* t, const int64_t* u_rows, int Be, int64_t id_offset, int64_t id_stride,

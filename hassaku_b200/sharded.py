@@ -127,6 +127,7 @@ class ShardedMF:
         self.stamp_items = torch.zeros(max(self.spec.n_local_items, 1), dtype=torch.uint8, device=self.device)
         self._sparse, self._dense, self._graphs = {}, None, {}
         self._peer = None
+        self._ipc = {}          # (rank, IPC handle) -> base address here of a peer's allocation (opened once, closed in close())
 
     # ---- collectives (skipped at world 1, where every exchange is the identity) ----
     def _a2a(self, out: torch.Tensor, inp: torch.Tensor):
@@ -373,7 +374,7 @@ class ShardedMF:
                                   'one node — use the sparse / dense exchange across nodes')
         else:
             every = [mine]
-        opened = {}
+        opened = self._ipc
 
         def addr(q, which):          # address in THIS process of tensor `which` of rank q
             if q == r:
@@ -398,8 +399,6 @@ class ShardedMF:
             ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
             if int(ok.item()) == 0:
-                for base in opened.values():
-                    _C.peer_close(base)
                 raise _C.HskError('the peer exchange is not available (mapping a peer\'s memory failed' +
                                   (f': {failure}' if failure else ' on another rank') + '): use the sparse / dense exchange')
         elif failure:
@@ -528,12 +527,13 @@ class ShardedMF:
         gc.collect()
         if self.device.type == 'cuda':
             torch.cuda.synchronize()
-        if self._peer is not None:
+        if self._ipc:
             if self.spec.world > 1:
                 dist.barrier(group=self.group)      # no peer is still inside a kernel that addresses this rank's memory
-            for base in self._peer['opened'].values():
+            for base in self._ipc.values():
                 _C.peer_close(base)
-            self._peer = None
+            self._ipc = {}
+        self._peer = None
 
     def step(self, u_global, i_global, B_global, loss_kind, neg_shift, lr, wd, decoupled=True, exchange='auto', capq=None):
         """Dispatch on the expected fraction of distinct items: dense exchange when the batch covers the item table."""
@@ -794,6 +794,110 @@ class ShardedMF:
         self._all_reduce(evaluator._counts)
         if getattr(evaluator, '_hit_sums', None) is not None:
             self._all_reduce(evaluator._hit_sums)
+        return evaluator.get_results()
+
+
+    def _map_peers(self, tensors: Dict[str, torch.Tensor], extra: Dict[str, int]):
+        """Collective: export `tensors` (name -> device tensor) to the peers of this node and map theirs.  Returns per rank q
+        a dict name -> address in THIS process, plus the peers' `extra` integers."""
+        G, r = self.spec.world, self.spec.rank
+        mine = dict(extra)
+        if G > 1:
+            import socket
+            mine['host'] = socket.gethostname()
+            try:
+                mine['exports'] = {n: _C.peer_export(t) for n, t in tensors.items()}
+            except _C.HskError as ex:
+                mine['error'] = str(ex)
+            every = [None] * G
+            dist.all_gather_object(every, mine, group=self.group)
+            errs = [f"rank {q}: {e['error']}" for q, e in enumerate(every) if 'error' in e]
+            if errs or len({e['host'] for e in every}) != 1:
+                raise _C.HskError('peer mapping is not available (' + ('; '.join(errs) or 'the ranks are not on one node') + ')')
+        else:
+            every = [mine]
+        out, failure = [], None
+        try:
+            for q in range(G):
+                d = {k: v for k, v in every[q].items() if k not in ('exports', 'host')}
+                for n, t in tensors.items():
+                    if q == r:
+                        d[n] = t.data_ptr()
+                    else:
+                        handle, off = every[q]['exports'][n]
+                        if (q, handle) not in self._ipc:
+                            self._ipc[(q, handle)] = _C.peer_open(handle, self.device)
+                        d[n] = self._ipc[(q, handle)] + off
+                out.append(d)
+        except _C.HskError as ex:
+            failure = str(ex)
+        if G > 1:
+            ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                raise _C.HskError('peer mapping is not available (' + (failure or 'failed on another rank') + ')')
+        elif failure:
+            raise _C.HskError(failure)
+        return out
+
+    def evaluate_streamed(self, labels_csr, exclude_csr, evaluator, batch_size: int = 18944, precision: str = 'bf16',
+                          rescore: bool = True, max_users: Optional[int] = None):
+        """Item-SHARDED tables, user-parallel scoring (one NVLink / NVSwitch node, tensor-core precisions): the item shards stay
+        where they are; every rank evaluates ITS users against ALL items with one kernel per batch that streams the other
+        ranks' packed item tables straight from their HBM (TMA loads over CUDA IPC mappings: 0.5 GB per 18 944-user batch at
+        cfg5, ~50 GB/s of a 640 GB/s link) and re-scores its candidates in fp32 from the owners' rows the same way.  No
+        replica (unlike `evaluate_replicated`), no per-shard candidate lists, no merge, no per-round collective (unlike
+        `evaluate`): the work per user is the single-GPU work, so the sweep scales with the users.  One all-reduce of the
+        metric sums at the end.  `max_users`: bound on the LOCAL users evaluated (bench samples)."""
+        from hassaku_b200.eval.eval import DeviceCSR
+        if precision not in ('tf32', 'bf16'):
+            raise ValueError("evaluate_streamed scores on the tensor cores: precision 'tf32' or 'bf16' (fp32-exact: evaluate / "
+                             "evaluate_replicated)")
+        prec = _C.PRECISIONS[precision]
+        G, r, lay, dev = self.spec.world, self.spec.rank, self.layout, self.device
+        k = max(evaluator.K_VALUES)
+        labels = labels_csr if isinstance(labels_csr, DeviceCSR) else self._csr_cache(labels_csr)
+        exclude = exclude_csr if isinstance(exclude_csr, DeviceCSR) else self._csr_cache(exclude_csr)
+        Uw, Vw, Ub, Ib, Gb = lay.views(self.arena)
+        # this rank's shard, packed once per sweep into a buffer that lives as long as the model (one IPC mapping per peer)
+        cache = self.__dict__.setdefault('_vq_cache', {})
+        Vq = cache[prec] = _C.pack_rows(Vw.detach(), lay.d, prec, out=cache.get(prec))
+        peers = self._map_peers({'Vq': Vq, 'arena': self.arena}, {'rows': lay.n_items, 'off_V': lay.off_V, 'off_Ib': lay.off_Ib})
+        shards = _C.ItemShards([p['rows'] for p in peers], Vq=[p['Vq'] for p in peers],
+                               V=[p['arena'] + 4 * p['off_V'] for p in peers],
+                               Ib=[p['arena'] + 4 * p['off_Ib'] for p in peers] if Ib is not None else None)
+        torch.cuda.synchronize(dev)
+        if G > 1:
+            dist.barrier(group=self.group)                        # every rank's packed shard is complete before anyone streams it
+        n_loc = lay.n_users if max_users is None else min(lay.n_users, max_users)
+        bs = max(1, min(batch_size, n_loc))
+        kc = min(128, k + self.RESCORE_MARGIN, self.spec.n_items) if rescore else k
+        U2d = self._table2d(self.arena, 'U')
+        t_user = _C.make_tables(U2d[:, :lay.d], self._table2d(self.arena, 'V')[:, :lay.d], Ub, Ib, Gb, lay.d)
+        scratch = torch.empty(_C.eval_topk_tc_shards_scratch_bytes(bs, shards, kc), dtype=torch.uint8, device=dev)
+        top_s = torch.empty((bs, k), dtype=torch.float32, device=dev)
+        top_i = torch.empty((bs, k), dtype=torch.int32, device=dev)
+        cand_s = torch.empty((bs, kc), dtype=torch.float32, device=dev) if kc > k else None
+        cand_i = torch.empty((bs, kc), dtype=torch.int32, device=dev) if kc > k else None
+        evaluator._prepare(dev)
+        for s0 in range(0, n_loc, bs):
+            n = min(bs, n_loc - s0)
+            rows_l = torch.arange(s0, s0 + n, dtype=torch.int64, device=dev)      # local user rows
+            gids = rows_l * G + r                                                   # their global ids (exclusion / label rows)
+            Uq = _C.pack_rows(U2d[:, :lay.d], lay.d, prec, row_idx=rows_l)
+            cs, ci = (cand_s[:n], cand_i[:n]) if kc > k else (top_s[:n], top_i[:n])
+            _C.eval_topk_tc_shards(Uq, shards, prec, gids, self.spec.n_users, kc, cs, ci, scratch, Ub=Ub, Gb=Gb,
+                                   excl_indptr=exclude.indptr, excl_indices=exclude.indices, status=self.status, u_rows=rows_l)
+            if kc > k:
+                _C.rescore_topk_shards(t_user, shards, rows_l, ci, k, top_s[:n], top_i[:n], status=self.status, cand_scores=cs)
+            evaluator.eval_batch_topk(gids, top_i[:n].contiguous(), labels)
+        self._all_reduce(evaluator._sums)
+        self._all_reduce(evaluator._counts)
+        if getattr(evaluator, '_hit_sums', None) is not None:
+            self._all_reduce(evaluator._hit_sums)
+        torch.cuda.synchronize(dev)
+        if G > 1:
+            dist.barrier(group=self.group)                        # nobody still reads this rank's packed shard when it is freed
         return evaluator.get_results()
 
 

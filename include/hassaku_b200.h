@@ -144,6 +144,26 @@ HSK_API int hsk_shard_unpack_add(const float* in, int ld, int64_t n_local, const
                                  float* gIb /* nullable */, uint8_t* stamps /* nullable */, int64_t step,
                                  const int64_t* step_dev /* nullable: overrides step */, int32_t* status, hsk_stream_t stream);
 
+/* ---- evaluation over item SHARDS that stay where they are (one NVLink / NVSwitch node): every rank evaluates ITS users
+ * against ALL items, streaming the other ranks' packed item tables straight from their HBM (TMA loads over peer mappings,
+ * hsk_peer_export / hsk_peer_open) — no replica, no per-shard top-k, no merge.  Shard q (rank q) holds the items
+ * q + n_shards * row.
+ *   hsk_eval_topk_tc_shards   = hsk_eval_topk_tc over the shards' packed tables Vq_shards[q] [shard_rows[q], kpad] (from
+ *       hsk_pack_rows) and item-bias vectors Ib_shards[q] (array or its entries nullable); CTA-pair kernel; ids returned
+ *       are global; scratch >= hsk_eval_topk_tc_shards_scratch_bytes.
+ *   hsk_rescore_topk_shards   = hsk_rescore_topk with the fp32 item rows read from the shards' tables V_shards[q]
+ *       [shard_rows[q], t->ld]; t supplies the user side (Uw, Ub, Gb, n_users, d, ld). */
+HSK_API int64_t hsk_eval_topk_tc_shards_scratch_bytes(int Be, const int64_t* shard_rows, int n_shards, int k);
+HSK_API int hsk_eval_topk_tc_shards(const void* Uq, const void* const* Vq_shards, const int64_t* shard_rows,
+                                    const float* const* Ib_shards, int n_shards, int kpad, int precision, const float* Ub,
+                                    const float* Gb, const int64_t* u_idx, const int64_t* u_rows, int Be, int64_t n_users,
+                                    const int64_t* excl_indptr, const int32_t* excl_indices, int k, float* top_scores,
+                                    int32_t* top_ids, void* scratch, int64_t scratch_bytes, int32_t* status, hsk_stream_t stream);
+HSK_API int hsk_rescore_topk_shards(const hsk_mf_tables* t, const float* const* V_shards, const int64_t* shard_rows,
+                                    const float* const* Ib_shards, int n_shards, const int64_t* u_rows, int Be,
+                                    const int32_t* cand_ids, const float* cand_scores /* nullable */, int n_cand, int k,
+                                    float* top_scores, int32_t* top_ids, int32_t* status, hsk_stream_t stream);
+
 /* ---- f3: FullEvaluatorCalibrationDecorator's recommendation distributions (eval/eval.py:174-179) ------------------
  * out[b, t, :] = (1 / ks[t]) * sum over j < ks[t] of item_tag[top_ids[b, j], :]   (top_ids int32 [B, k_list] ranked, -1 =
  * padding, skipped; item_tag fp32 [n_items, T] row-major; ks host array of n_ks <= 8 values, each <= k_list; out fp32

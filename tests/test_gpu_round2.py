@@ -481,3 +481,57 @@ def test_kernels_do_not_write_outside_their_buffers():
     torch.cuda.synchronize()
     bad = [j for j, g_ in enumerate(guards) if not g_.intact()]
     assert not bad, f'canaries overwritten around buffers {bad}'
+
+
+@pytest.mark.parametrize('S,I,Be', [(3, 10007, 200), (8, 70001, 64), (2, 513, 300)])
+def test_evaluator_over_item_shards_equals_the_single_table(S, I, Be):
+    """hsk_eval_topk_tc_shards + hsk_rescore_topk_shards over S interleaved item shards (item i = row i / S of shard i % S;
+    separate allocations here, peer-mapped tables in ShardedMF.evaluate_streamed) return exactly what the single-table calls
+    return: same candidate ids and low-precision scores, same fp32 top-k — ragged shards, exclusions, item bias, tile
+    boundaries inside and between shards, several splits (small batch) included."""
+    from hassaku_b200 import _C
+    torch.manual_seed(S * 1000 + Be)
+    d, k, kc = 64, 20, 48
+    P = _C.PRECISIONS['bf16']
+    U = 400
+    Uw = (torch.randn(U, d, device='cuda') * 0.4).contiguous()
+    Vw = (torch.randn(I, d, device='cuda') * 0.4).contiguous()
+    Ib = (torch.randn(I, device='cuda') * 0.2).contiguous()
+    Ub = (torch.randn(U, device='cuda') * 0.1).contiguous()
+    users = torch.randperm(U, device='cuda')[:Be].contiguous()
+    # exclusion CSR: ~30 sorted random items per user
+    rng = np.random.RandomState(S)
+    cols = [np.unique(rng.randint(0, I, 30)) for _ in range(U)]
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum([len(c) for c in cols])]).astype(np.int64)).cuda()
+    indices = torch.from_numpy(np.concatenate(cols).astype(np.int32)).cuda()
+    Uq = _C.pack_rows(Uw, d, P, row_idx=users)
+    # single table
+    Vq = _C.pack_rows(Vw, d, P)
+    s1, i1 = torch.empty((Be, kc), device='cuda'), torch.empty((Be, kc), dtype=torch.int32, device='cuda')
+    scr = torch.empty(_C.eval_topk_tc_scratch_bytes(Be, I, kc), dtype=torch.uint8, device='cuda')
+    _C.eval_topk_tc(Uq, Vq, P, users, U, kc, s1, i1, scr, Ub=Ub, Ib=Ib, excl_indptr=indptr, excl_indices=indices, variant='pair')
+    t = _C.make_tables(Uw, Vw, Ub.view(-1, 1), Ib.view(-1, 1), None, d)
+    r1s, r1i = torch.empty((Be, k), device='cuda'), torch.empty((Be, k), dtype=torch.int32, device='cuda')
+    _C.rescore_topk(t, users, i1, k, r1s, r1i, cand_scores=s1)
+    # S shards
+    Vs = [Vw[q::S].contiguous() for q in range(S)]
+    Ibs = [Ib[q::S].contiguous() for q in range(S)]
+    Vqs = [_C.pack_rows(v, d, P) for v in Vs]
+    shards = _C.ItemShards([v.shape[0] for v in Vs], Vq=[x.data_ptr() for x in Vqs], V=[v.data_ptr() for v in Vs],
+                           Ib=[b.data_ptr() for b in Ibs])
+    s2, i2 = torch.empty((Be, kc), device='cuda'), torch.empty((Be, kc), dtype=torch.int32, device='cuda')
+    scr2 = torch.empty(_C.eval_topk_tc_shards_scratch_bytes(Be, shards, kc), dtype=torch.uint8, device='cuda')
+    st = torch.zeros(1, dtype=torch.int32, device='cuda')
+    _C.eval_topk_tc_shards(Uq, shards, P, users, U, kc, s2, i2, scr2, Ub=Ub, excl_indptr=indptr, excl_indices=indices, status=st)
+    assert int(st.item()) == 0
+    assert torch.equal(i1, i2), 'candidate ids differ'
+    assert torch.equal(s1, s2), 'candidate scores differ'
+    r2s, r2i = torch.empty((Be, k), device='cuda'), torch.empty((Be, k), dtype=torch.int32, device='cuda')
+    _C.rescore_topk_shards(t, shards, users, i2, k, r2s, r2i, status=st, cand_scores=s2)
+    assert int(st.item()) == 0
+    assert torch.equal(r1i, r2i) and torch.equal(r1s, r2s)
+    # none of the returned ids is excluded
+    ex = {(u, int(c)) for u in range(U) for c in cols[u]}
+    got = r2i.cpu().numpy()
+    for b, u in enumerate(users.cpu().numpy()[:50]):
+        assert not any((int(u), int(x)) in ex for x in got[b])

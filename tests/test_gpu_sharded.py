@@ -194,11 +194,15 @@ def _worker_tc_eval(rank, world, port, out_dir):
                                precision=prec)
             rep = smf.evaluate_replicated(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=256,
                                           precision=prec)
-            assert sorted(got) == sorted(ref) == sorted(rep)
+            stm = smf.evaluate_streamed(data.val, data.train, FullEvaluator(True, 2, ds.user_to_user_group), batch_size=256,
+                                        precision=prec)      # the peers' packed shards streamed over NVLink (CUDA IPC mappings)
+            assert sorted(got) == sorted(ref) == sorted(rep) == sorted(stm)
             for k_, v in ref.items():
                 assert abs(got[k_] - v) <= 1e-6, (prec, k_, got[k_], v)
                 assert abs(rep[k_] - v) <= 1e-6, (prec, 'replicated', k_, rep[k_], v)
+                assert abs(stm[k_] - v) <= 1e-6, (prec, 'streamed', k_, stm[k_], v)
         assert int(smf.status.item()) == 0
+        smf.close()
         if rank == 0:
             open(os.path.join(out_dir, 'ok'), 'w').write('ok')
     except BaseException:
