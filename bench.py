@@ -755,34 +755,23 @@ def bench_eval(args, dev, D, world, rank, smf_factory=None):
                                             'region), every GPU then evaluates its own users against all items'}
         except Exception as ex:
             res['user_parallel'] = {'error': repr(ex)}
-        # item-sharded storage, user-parallel scoring: every GPU streams the peers' packed shards over NVLink (no replica, no
-        # merge).  This is the headline of the N > 1 evaluation when peer mappings are available; the merge protocol measured
-        # above stays in the line as `merge_protocol`.
-        res['merge_protocol'] = {'value': n_eval_users / (ms * 1e-3), 'unit': 'users/s', 'ms_per_sweep': ms, 'ndcg@10': r['ndcg@10'],
-                                 'e2e_users_per_s': n_eval_users / (ms_e2e * 1e-3),
-                                 'what': 'ShardedMF.evaluate: all-gather user rows, per-shard top-(k + 28), all-to-all + merge, sharded '
-                                         'fp32 re-scoring, combine'}
-        res['mode'] = 'merge_protocol'
+        # item shards that stay in place, streamed over NVLink by every GPU (ShardedMF.evaluate_streamed): exact, no replica — but
+        # remote rows are not cached in the local L2, so each of the 74 CTA pairs pulls the peers' shards over the link itself
+        # (~37 GB x (G - 1) / G per 18 944-user batch): the mode for catalogues whose packed table does not fit one GPU, measured
+        # here on two batches per rank only
         try:
-            max_local = math.ceil(n_eval_users / world)
-            smf.evaluate_streamed(labels, exclude, FullEvaluator(True, 0, None), batch_size=Bt, precision=prec, max_users=3 * Bt)
+            smf.evaluate_streamed(labels, exclude, FullEvaluator(True, 0, None), batch_size=Bt, precision=prec, max_users=Bt)
             D.barrier()
             a4, b4 = _events(2)
             a4.record()
-            r4 = smf.evaluate_streamed(labels, exclude, FullEvaluator(True, 0, None), batch_size=Bt, precision=prec, max_users=max_local)
+            smf.evaluate_streamed(labels, exclude, FullEvaluator(True, 0, None), batch_size=Bt, precision=prec, max_users=2 * Bt)
             b4.record()
             torch.cuda.synchronize()
             ms4 = D.max(a4.elapsed_time(b4))
-            D.barrier()
-            t4 = time.perf_counter()
-            r5 = smf.evaluate_streamed(labels, exclude, FullEvaluator(True, 0, None), batch_size=Bt, precision=prec, max_users=max_local)
-            torch.cuda.synchronize()
-            ms4_e2e = D.max((time.perf_counter() - t4) * 1e3)
-            ms, ms_e2e, r = ms4, ms4_e2e, r4
-            res['ndcg@10_e2e'] = r5['ndcg@10']
-            res['mode'] = 'streamed'
+            res['streamed'] = {'value': 2 * Bt * world / (ms4 * 1e-3), 'unit': 'users/s', 'sample_users': 2 * Bt * world, 'ms': ms4,
+                               'what': 'ShardedMF.evaluate_streamed on 2 batches per rank: NVLink-bound (peer rows bypass the local L2)'}
         except Exception as ex:
-            res['streamed_error'] = repr(ex)
+            res['streamed'] = {'error': repr(ex)}
         smf.check_status()
         smf.close()
         del smf
@@ -796,10 +785,7 @@ def bench_eval(args, dev, D, world, rank, smf_factory=None):
                                f'top-{k} + fp32 re-scoring of k + 28 candidates + 12 metrics', 'users_per_round': Bt,
                    'exclusions_per_user': float(exclude.indices.numel()) * world / U, 'labels_per_user': float(labels.indices.numel()) * world / U,
                    'weights': 'N(0, 1/d) embeddings, N(0, 0.05^2) item bias (the training init would rank by bias alone)',
-                   'parallelism': 'single GPU' if world == 1 else (
-                       f'item tables sharded x{world}, every GPU scores ITS users against all items, streaming the peers\' packed shards '
-                       f'over NVLink (ShardedMF.evaluate_streamed)' if res.get('mode') == 'streamed' else
-                       f'item-sharded x{world}: all-gather user rows, per-shard top-k, all-to-all + merge')},
+                   'parallelism': 'single GPU' if world == 1 else f'item-sharded x{world}: all-gather user rows, per-shard top-k, all-to-all + merge'},
         'tflops': tf,
         'e2e': {'value': n_eval_users / (ms_e2e * 1e-3), 'unit': 'users/s', 'h2d_bytes_per_step': res.pop('h2d_bytes_per_batch'),
                 'd2h_bytes_per_step': 96, 'timing': 'host wall clock: sweep call -> metric dict on the host'},

@@ -843,12 +843,15 @@ class ShardedMF:
     def evaluate_streamed(self, labels_csr, exclude_csr, evaluator, batch_size: int = 18944, precision: str = 'bf16',
                           rescore: bool = True, max_users: Optional[int] = None):
         """Item-SHARDED tables, user-parallel scoring (one NVLink / NVSwitch node, tensor-core precisions): the item shards stay
-        where they are; every rank evaluates ITS users against ALL items with one kernel per batch that streams the other
-        ranks' packed item tables straight from their HBM (TMA loads over CUDA IPC mappings: 0.5 GB per 18 944-user batch at
-        cfg5, ~50 GB/s of a 640 GB/s link) and re-scores its candidates in fp32 from the owners' rows the same way.  No
-        replica (unlike `evaluate_replicated`), no per-shard candidate lists, no merge, no per-round collective (unlike
-        `evaluate`): the work per user is the single-GPU work, so the sweep scales with the users.  One all-reduce of the
-        metric sums at the end.  `max_users`: bound on the LOCAL users evaluated (bench samples)."""
+        where they are; every rank evaluates ITS users against ALL items with one kernel per batch that reads the other ranks'
+        packed item tables straight from their HBM (TMA loads over CUDA IPC mappings) and re-scores its candidates in fp32 from
+        the owners' rows the same way.  No replica (unlike `evaluate_replicated`), no per-shard candidate lists, no merge, no
+        per-round collective (unlike `evaluate`); results are exactly the single-GPU results.
+        Cost, measured: peer rows are NOT cached in the reader's L2, so each of the 74 CTA pairs of a launch pulls the remote
+        shards over the link itself — ~37 GB x (G - 1) / G per 18 944-user batch at cfg5 against ~640 GB/s — 37 ms per batch on
+        2 GPUs where the replicated mode needs 11.  Use it for catalogues whose packed item table does not fit one GPU (the only
+        case that needs item-sharded STORAGE); otherwise `evaluate_replicated` (1.5 GB at cfg5) is 3x faster and `evaluate` keeps
+        memory per GPU at 1 / G.  `max_users`: bound on the LOCAL users evaluated (bench samples)."""
         from hassaku_b200.eval.eval import DeviceCSR
         if precision not in ('tf32', 'bf16'):
             raise ValueError("evaluate_streamed scores on the tensor cores: precision 'tf32' or 'bf16' (fp32-exact: evaluate / "
