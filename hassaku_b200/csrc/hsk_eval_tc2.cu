@@ -28,6 +28,35 @@ constexpr int T2_ACC_STAGES = 2;             // 2 x 256 fp32 columns
 // lane quarter split the tile's columns): NCG = 2 -> 8 epilogue warps x 128 columns, NCG = 4 -> 16 warps x 64 columns.
 // A row's 512-entry candidate list has one region per column group; a tile appends at most COLS keys to a region, so a
 // region is cut when it holds more than RCAP - COLS, and an intermediate cut keeps <= NCG * (RCAP - COLS) = 256 entries.
+// Position of a walk over the launch's tiles in the item shards: the shard's limits live in registers and are re-read from the
+// argument block only when the walk crosses into the next shard (once per shard, not once per tile).
+struct ShardWalk {
+    int gt, q, tile_end;      // global tile, its shard, first tile of the next shard
+    int n0, rows;             // first row of the tile inside the shard, rows of the shard (ids fit 31 bits)
+    const float* ib;          // the shard's item bias (null: none)
+};
+__device__ __forceinline__ void walk_load(const EvalTcArgs& a, ShardWalk& w) {
+    w.tile_end = a.shard_tile_end[w.q];
+    w.rows = (int)a.shard_rows[w.q];
+    w.ib = a.shard_Ib[w.q];
+}
+__device__ __forceinline__ void walk_init(const EvalTcArgs& a, ShardWalk& w, int gt) {
+    w.gt = gt;
+    w.q = 0;
+    while (w.q + 1 < a.n_shards && gt >= a.shard_tile_end[w.q]) ++w.q;
+    w.n0 = (gt - (w.q ? a.shard_tile_end[w.q - 1] : 0)) * T2_BN;
+    walk_load(a, w);
+}
+__device__ __forceinline__ void walk_next(const EvalTcArgs& a, ShardWalk& w) {
+    ++w.gt;
+    w.n0 += T2_BN;
+    if (w.gt >= w.tile_end && w.q + 1 < a.n_shards) {
+        ++w.q;
+        w.n0 = 0;
+        walk_load(a, w);
+    }
+}
+
 #ifndef HSK_T2_SCHED_NUM
 #define HSK_T2_SCHED_NUM 3     // schedule ratio 3 / 2 (measurement builds override: profiles/r02_eval_tc2_stall_analysis.md)
 #define HSK_T2_SCHED_DEN 2
@@ -165,17 +194,18 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int kb = 0; kb < a.num_kb; ++kb) tma_load_2d_pair(smA + (size_t)kb * TC_TILE_BYTES, &tmA, kb * a.kelems_per_kb, m0, &bar_a);
             int s = 0;
             uint32_t ph = 0;
-            int q = 0;
+            ShardWalk w;
+            walk_init(a, w, t_begin);
             for (int t = 0; t < n_my_tiles; ++t) {
-                while (q + 1 < a.n_shards && t_begin + t >= a.shard_tile_end[q]) ++q;       // the shard this tile belongs to
-                const int lt = t_begin + t - (q ? a.shard_tile_end[q - 1] : 0);
-                const int n0 = lt * T2_BN + (int)cta * TC_BN;      // this CTA's half of the tile (rows of shard q)
+                const int n0 = w.n0 + (int)cta * TC_BN;      // this CTA's half of the tile (rows of shard w.q)
+                const CUtensorMap* map = &tmBs.m[w.q];
                 for (int kb = 0; kb < a.num_kb; ++kb) {
                     mbar_wait(&bar_empty[s], ph ^ 1u);
                     if (leader) mbar_expect_tx(&bar_full[s], 2u * TC_TILE_BYTES);
-                    tma_load_2d_pair(smB + (size_t)s * TC_TILE_BYTES, &tmBs.m[q], kb * a.kelems_per_kb, n0, &bar_full[s]);
+                    tma_load_2d_pair(smB + (size_t)s * TC_TILE_BYTES, map, kb * a.kelems_per_kb, n0, &bar_full[s]);
                     if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
+                walk_next(a, w);
             }
         }
     } else if (warp == 1) {
@@ -224,28 +254,23 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr int STG = T2_BN / Cfg::GROUP;   // bias values a thread stages per tile
         ExCursor ex;
         ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
-        // tile `tt` of this CTA -> its shard and the first row of the tile inside the shard
-        auto shard_of = [&](int tt, int& q, int64_t& n0) {
-            const int gt = t_begin + tt;
-            q = 0;
-            while (q + 1 < a.n_shards && gt >= a.shard_tile_end[q]) ++q;
-            n0 = (int64_t)(gt - (q ? a.shard_tile_end[q - 1] : 0)) * T2_BN;
+        // two walks over this CTA's tiles: `cur` = the tile being scanned, `la` = the tile whose bias row is fetched next (the
+        // prologue fetches tiles 0, 1, 2, iteration t fetches tile t + 3: always the next one)
+        ShardWalk cur, la;
+        walk_init(a, cur, t_begin);
+        la = cur;
+        int la_tt = 0;        // tile (relative to t_begin) `la` stands on
+        auto ib_la = [&](int col) -> float {    // bias of column `col` of the tile `la` stands on (0 beyond the shard / the CTA's range)
+            return (la.ib && la_tt < n_my_tiles && la.n0 + col < la.rows) ? __ldg(la.ib + la.n0 + col) : 0.f;
         };
-        // bias value of column `col` of tile `tt` (0 beyond the shard / without item bias)
-        auto ib_at = [&](int tt, int col) -> float {
-            if (tt >= n_my_tiles) return 0.f;
-            int q;
-            int64_t n0;
-            shard_of(tt, q, n0);
-            const float* ibq = a.shard_Ib[q];
-            return (ibq && n0 + col < a.shard_rows[q]) ? __ldg(ibq + n0 + col) : 0.f;
-        };
-        int cur_q = 0;
+        auto la_next = [&]() { walk_next(a, la); ++la_tt; };
+        int cur_q = cur.q;
 
         // prologue: bias rows of the first two tiles into the stages (through the group's staging tile), stages to the MMA warp
         for (int ts = 0; ts < T2_ACC_STAGES && ts < n_my_tiles; ++ts) {
 #pragma unroll
-            for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_at(ts, sc0 + 32 * h);
+            for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_la(sc0 + 32 * h);
+            la_next();
             named_bar_sync(bar_id, Cfg::GROUP);
             tc_write_bias<Cfg::COLS / 32>(ib_grp + cg * Cfg::COLS, tlane + (uint32_t)ts * T2_BN);
             tc_fence_before();
@@ -254,29 +279,31 @@ eval_topk_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             named_bar_sync(bar_id, Cfg::GROUP);
         }
 #pragma unroll
-        for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_at(T2_ACC_STAGES, sc0 + 32 * h);   // slot 0 <- tile 2
+        for (int h = 0; h < STG; ++h) ib_grp[sc0 + 32 * h] = ib_la(sc0 + 32 * h);   // slot 0 <- tile 2
+        la_next();
         named_bar_sync(bar_id, Cfg::GROUP);
 
         int next_cut = 2;          // tiles after which every row is cut: 2, 3, 4, 6, 9, 13, ... (ratio HSK_T2_SCHED_NUM / DEN)
         for (int t = 0; t < n_my_tiles; ++t) {
             const int as = t & 1;
-            int q;
-            int64_t n0;
-            shard_of(t, q, n0);
+            const int q = cur.q;
+            const int n0 = cur.n0;
             if (q != cur_q) {      // the next shard's item ids start low again: rewind the exclusion cursor
                 cur_q = q;
                 ex_init(ex, a.excl_indices, s_exlo[r], s_exhi[r]);
             }
-            const int ncols = (int)min((int64_t)T2_BN, a.shard_rows[q] - n0);
+            const int ncols = min(T2_BN, cur.rows - n0);
+            walk_next(a, cur);     // (q, n0, ncols of THIS tile are latched above)
             // item id of (shard q, row n) = id_offset + (q + n_shards * n) * id_stride
             const uint32_t id_step = (uint32_t)(a.n_shards * a.id_stride);
-            const uint32_t id_base = (uint32_t)(a.id_offset + ((int64_t)q + a.n_shards * n0) * a.id_stride);
+            const uint32_t id_base = (uint32_t)a.id_offset + ((uint32_t)q + (uint32_t)a.n_shards * (uint32_t)n0) * (uint32_t)a.id_stride;
             const float tau = s_tau[r];
             const uint64_t taukey = s_taukey[r];
             // the bias values the NEXT iteration writes (tile t + 3): in flight during this tile
             float ibn[STG];
 #pragma unroll
-            for (int h = 0; h < STG; ++h) ibn[h] = ib_at(t + 1 + T2_ACC_STAGES, sc0 + 32 * h);
+            for (int h = 0; h < STG; ++h) ibn[h] = ib_la(sc0 + 32 * h);
+            la_next();
             mbar_wait(&bar_tfull[as], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tlane + (uint32_t)as * T2_BN;
