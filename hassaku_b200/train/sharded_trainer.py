@@ -23,7 +23,6 @@ local batch) steps (fixed shapes: the step is replayed as one CUDA graph); the f
 dropped, a different random subset each epoch.
 """
 import logging
-import math
 import os
 
 import numpy as np
