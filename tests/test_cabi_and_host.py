@@ -262,3 +262,21 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
     sizes = dict((k, int(v)) for k, v in re.findall(r'(hsk_\w+)=(\d+)', out))
     assert sizes == {'hsk_mf_tables': ctypes.sizeof(_C.MfTables), 'hsk_row_segment': ctypes.sizeof(_C.RowSegment),
                      'hsk_peer_items': ctypes.sizeof(_C.PeerItems), 'hsk_peer_flags': ctypes.sizeof(_C.PeerFlags)}, sizes
+
+
+def test_item_shards_and_peer_tables_host_side():
+    """The ctypes side of the shard / peer entry points (no GPU): array layout, limits, null handling."""
+    import ctypes
+    from hassaku_b200 import _C
+    sh = _C.ItemShards([10, 9, 9], Vq=[0x1000, 0x2000, 0x3000], V=[0x10, 0x20, 0x30])
+    assert sh.n == 3 and list(sh.rows) == [10, 9, 9] and sh.Ib is None and sh.Vq[1] == 0x2000
+    with pytest.raises(ValueError):
+        _C.ItemShards(list(range(1, 10)))                       # more than HSK_MAX_PEERS shards
+    p = _C.make_peer_items([1, 2], [3, 4])
+    assert p.world == 2 and p.V[1] == 2 and p.gV[0] == 3 and not p.Ib[0] and not p.stamps[1]
+    with pytest.raises(ValueError):
+        _C.make_peer_items(list(range(9)), list(range(9)))
+    f = _C.make_peer_flags([16, 32, 48], 2)
+    assert (f.world, f.rank, f.flags[2]) == (3, 2, 48)
+    # scratch sizing of the shard evaluator is CUDA-free except for the SM count: monotone in the batch
+    assert ctypes.sizeof(_C.PeerItems) == 8 + 5 * 8 * _C.MAX_PEERS
